@@ -1,0 +1,405 @@
+/*
+ * mdf_oracle.c -- CPU restatement of MDF-Net's plane-sweep cost-volume path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the product path (mdf_net_b200/) may
+ * link, import or execute this file; it exists so that tests/, smoke() and
+ * bench.py's cpu_baseline leg have an independent checker for the CUDA
+ * kernels.  It is pinned against outputs of the unmodified reference (torch
+ * CPU) by tests/golden/ (see tests/golden/make_golden.py).
+ *
+ * What is restated (file:line into the reference checkout):
+ *   homo_warping                 net/unit/base.py:85-126
+ *   VectorAggregate.forward      net/unit/homoaggregate.py:25-46 (+ depth_weight :16-20,
+ *                                ConvBNReLU3D net/unit/base.py:50-68, eval-mode BN)
+ *   homo_aggregate_by_variance   net/unit/homoaggregate.py:49-69
+ *   softmax tail of the 3-D CNN  net/unit/regular.py:67-69,130-133
+ *   depth_regression             net/unit/regress.py:5-7
+ *   confidence_regress           net/unit/regress.py:9-25 (+ nearest x2, net/core.py:75-77)
+ *
+ * The arithmetic of the reference lives in PyTorch (third party; the reference
+ * pins torch==1.7.1, this image has 2.11.0).  The pieces of ATen that are
+ * restated here are its published grid_sample algorithm
+ * (ATen/native/GridSampler.h:27-35 unnormalize with align_corners=False,
+ *  ATen/native/cuda/GridSampler.cuh:150-170,220 bilinear taps with zero padding)
+ * plus the rounding behaviour observed on torch CPU in this image:
+ *   - `tensor / python_float` is a true float32 division,
+ *   - the K=3 matmul `rot @ xyz` is  fma(r2,1, fma(r1,y, r0*x)),
+ *   - unnormalize is fused:          ix = fma(xn + 1, W/2, -0.5),
+ *   - the 4-tap blend is             fma(se,wse, fma(sw,wsw, fma(ne,wne, nw*wnw))).
+ * Every other elementwise op of the reference rounds separately, so this file
+ * must be compiled with -ffp-contract=off (the Makefile does).
+ *
+ * Build twice: REAL=float (the oracle) and REAL=double (-DMDF_ORACLE_F64; a
+ * higher-precision evaluation of the same formulae used to measure the fp32
+ * noise floor of the reference itself).
+ */
+#include <math.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifdef MDF_ORACLE_F64
+typedef double REAL;
+#define R_FMA fma
+#define R_EXP exp
+#define R_SQRT sqrt
+#define R_FLOOR floor
+#define SYM(name) name##_f64
+#else
+typedef float REAL;
+#define R_FMA fmaf
+#define R_EXP expf
+#define R_SQRT sqrtf
+#define R_FLOOR floorf
+#define SYM(name) name##_f32
+#endif
+
+#define MDF_OK 0
+#define MDF_EINVAL (-1)
+
+/* ------------------------------------------------------------------------- */
+/* proj = src_proj @ inverse(ref_proj)            (base.py:98)                */
+/* LU with partial pivoting (what LAPACK getrf does for torch.inverse), then  */
+/* A^-1 by solving against the identity; 4x4 product as an fma chain.         */
+/* Output: 12 numbers per batch item: rot (3x3 row-major) then trans (3).     */
+/* ------------------------------------------------------------------------- */
+static int invert4(const REAL *a_in, REAL *inv)
+{
+    REAL a[16];
+    int piv[4];
+    memcpy(a, a_in, sizeof(a));
+    for (int k = 0; k < 4; ++k) {
+        int p = k;
+        REAL best = fabs((double)a[k * 4 + k]);
+        for (int r = k + 1; r < 4; ++r) {
+            REAL v = fabs((double)a[r * 4 + k]);
+            if (v > best) { best = v; p = r; }
+        }
+        piv[k] = p;
+        if (p != k)
+            for (int c = 0; c < 4; ++c) { REAL t = a[k * 4 + c]; a[k * 4 + c] = a[p * 4 + c]; a[p * 4 + c] = t; }
+        if (a[k * 4 + k] == 0) return MDF_EINVAL;
+        for (int r = k + 1; r < 4; ++r) {
+            a[r * 4 + k] = a[r * 4 + k] / a[k * 4 + k];
+            for (int c = k + 1; c < 4; ++c)
+                a[r * 4 + c] = a[r * 4 + c] - a[r * 4 + k] * a[k * 4 + c];
+        }
+    }
+    for (int col = 0; col < 4; ++col) {
+        REAL b[4] = {0, 0, 0, 0};
+        b[col] = 1;
+        for (int k = 0; k < 4; ++k)
+            if (piv[k] != k) { REAL t = b[k]; b[k] = b[piv[k]]; b[piv[k]] = t; }
+        for (int r = 1; r < 4; ++r)
+            for (int c = 0; c < r; ++c) b[r] = b[r] - a[r * 4 + c] * b[c];
+        for (int r = 3; r >= 0; --r) {
+            for (int c = r + 1; c < 4; ++c) b[r] = b[r] - a[r * 4 + c] * b[c];
+            b[r] = b[r] / a[r * 4 + r];
+        }
+        for (int r = 0; r < 4; ++r) inv[r * 4 + col] = b[r];
+    }
+    return MDF_OK;
+}
+
+int SYM(mdf_oracle_compose_proj)(const REAL *src_proj, const REAL *ref_proj, int B, REAL *rot_trans)
+{
+    for (int b = 0; b < B; ++b) {
+        REAL inv[16], p[16];
+        if (invert4(ref_proj + 16 * b, inv) != MDF_OK) return MDF_EINVAL;
+        const REAL *s = src_proj + 16 * b;
+        for (int r = 0; r < 4; ++r)
+            for (int c = 0; c < 4; ++c) {
+                REAL acc = s[r * 4 + 0] * inv[0 * 4 + c];
+                for (int k = 1; k < 4; ++k) acc = R_FMA(s[r * 4 + k], inv[k * 4 + c], acc);
+                p[r * 4 + c] = acc;
+            }
+        REAL *o = rot_trans + 12 * b;
+        for (int r = 0; r < 3; ++r) {
+            for (int c = 0; c < 3; ++c) o[r * 3 + c] = p[r * 4 + c];
+            o[9 + r] = p[r * 4 + 3];
+        }
+    }
+    return MDF_OK;
+}
+
+/* ------------------------------------------------------------------------- */
+/* Sample position of reference pixel (x,y) at depth `depth` in the source     */
+/* view, in the *pixel* units grid_sample ends up using.  base.py:102-119 +    */
+/* ATen unnormalize (align_corners=False).                                     */
+/* ------------------------------------------------------------------------- */
+typedef struct { REAL ix, iy; } sample_pos_t;
+
+static inline sample_pos_t sample_position(const REAL *rt, int x, int y, REAL depth, int H, int W)
+{
+    const REAL fx = (REAL)x, fy = (REAL)y, one = 1;
+    /* rot_xyz = rot @ [x, y, 1]  (base.py:110) */
+    REAL rx = R_FMA(rt[2], one, R_FMA(rt[1], fy, rt[0] * fx));
+    REAL ry = R_FMA(rt[5], one, R_FMA(rt[4], fy, rt[3] * fx));
+    REAL rz = R_FMA(rt[8], one, R_FMA(rt[7], fy, rt[6] * fx));
+    /* * depth (base.py:112), + trans (base.py:114) */
+    REAL X = rx * depth, Y = ry * depth, Z = rz * depth;
+    X = X + rt[9]; Y = Y + rt[10]; Z = Z + rt[11];
+    /* two true divisions (base.py:115) */
+    REAL px = X / Z, py = Y / Z;
+    /* normalise with the align_corners=True formula (base.py:117-118) */
+    REAL xn = px / (REAL)((W - 1) / 2.0) - one;
+    REAL yn = py / (REAL)((H - 1) / 2.0) - one;
+    /* ...but grid_sample runs with align_corners=False (base.py:122-123):
+       ix = ((xn + 1) * W - 1) / 2, evaluated fused as observed on torch CPU */
+    sample_pos_t s;
+    s.ix = R_FMA(xn + one, (REAL)W / 2, (REAL)-0.5);
+    s.iy = R_FMA(yn + one, (REAL)H / 2, (REAL)-0.5);
+    return s;
+}
+
+/* 4 bilinear taps, zero padding.  Returns 0 when no tap can be in bounds. */
+typedef struct { int x0, y0; REAL wnw, wne, wsw, wse; int m_nw, m_ne, m_sw, m_se; } taps_t;
+
+static inline int make_taps(sample_pos_t s, int H, int W, taps_t *t)
+{
+    /* NaN / inf / far-out positions: every tap is out of bounds -> zeros
+       (GridSampler.cuh:140-147 maps non-finite coordinates to -100). */
+    if (!(s.ix > -1 && s.ix < W && s.iy > -1 && s.iy < H)) return 0;
+    REAL fx0 = R_FLOOR(s.ix), fy0 = R_FLOOR(s.iy);
+    REAL fx1 = fx0 + 1, fy1 = fy0 + 1;
+    t->x0 = (int)fx0; t->y0 = (int)fy0;
+    t->wnw = (fx1 - s.ix) * (fy1 - s.iy);
+    t->wne = (s.ix - fx0) * (fy1 - s.iy);
+    t->wsw = (fx1 - s.ix) * (s.iy - fy0);
+    t->wse = (s.ix - fx0) * (s.iy - fy0);
+    int xin0 = t->x0 >= 0 && t->x0 < W, xin1 = t->x0 + 1 >= 0 && t->x0 + 1 < W;
+    int yin0 = t->y0 >= 0 && t->y0 < H, yin1 = t->y0 + 1 >= 0 && t->y0 + 1 < H;
+    t->m_nw = xin0 && yin0; t->m_ne = xin1 && yin0; t->m_sw = xin0 && yin1; t->m_se = xin1 && yin1;
+    return 1;
+}
+
+static inline REAL blend(const REAL *plane, int W, const taps_t *t)
+{
+    const REAL *p = plane + (ptrdiff_t)t->y0 * W + t->x0;
+    REAL nw = t->m_nw ? p[0] : 0, ne = t->m_ne ? p[1] : 0;
+    REAL sw = t->m_sw ? p[W] : 0, se = t->m_se ? p[W + 1] : 0;
+    return R_FMA(se, t->wse, R_FMA(sw, t->wsw, R_FMA(ne, t->wne, nw * t->wnw)));
+}
+
+static inline REAL hypo_at(const REAL *hypos, int per_pixel, int b, int d, int y, int x, int D, int H, int W)
+{
+    return per_pixel ? hypos[(((size_t)b * D + d) * H + y) * W + x] : hypos[(size_t)b * D + d];
+}
+
+/* ------------------------------------------------------------------------- */
+/* homo_warping with a precomposed projection (rot|trans, 12 per batch item). */
+/* out: (B, C, D, H, W)                                                       */
+/* ------------------------------------------------------------------------- */
+int SYM(mdf_oracle_homo_warp)(const REAL *src_fea, const REAL *rot_trans, const REAL *hypos, int per_pixel,
+                              int B, int C, int D, int H, int W, REAL *out)
+{
+    if (B < 0 || C < 0 || D < 0 || H < 0 || W < 0) return MDF_EINVAL;
+    const size_t HW = (size_t)H * W;
+    for (int b = 0; b < B; ++b) {
+        const REAL *rt = rot_trans + 12 * b;
+#pragma omp parallel for collapse(2) schedule(static)
+        for (int d = 0; d < D; ++d)
+            for (int y = 0; y < H; ++y)
+                for (int x = 0; x < W; ++x) {
+                    REAL depth = hypo_at(hypos, per_pixel, b, d, y, x, D, H, W);
+                    taps_t t;
+                    int ok = make_taps(sample_position(rt, x, y, depth, H, W), H, W, &t);
+                    for (int c = 0; c < C; ++c) {
+                        const REAL *plane = src_fea + ((size_t)b * C + c) * HW;
+                        out[((((size_t)b * C + c) * D + d) * H + y) * W + x] = ok ? blend(plane, W, &t) : 0;
+                    }
+                }
+    }
+    return MDF_OK;
+}
+
+/* softmax over n values with stride `st` (max-subtracted, as ATen does) */
+static inline void softmax_n(const REAL *in, int n, REAL *out)
+{
+    REAL m = in[0];
+    for (int k = 1; k < n; ++k) m = in[k] > m ? in[k] : m;
+    REAL sum = 0;
+    for (int k = 0; k < n; ++k) { out[k] = R_EXP(in[k] - m); sum = sum + out[k]; }
+    for (int k = 0; k < n; ++k) out[k] = out[k] / sum;
+}
+
+/* ------------------------------------------------------------------------- */
+/* VectorAggregate.forward, eval mode (homoaggregate.py:25-46).               */
+/*   features: V = N pointers, each (B,C,H,W); features[0] is the reference.    */
+/*   rot_trans: (N-1) pointers, each 12*B (from compose_proj).                 */
+/*   depth-weight parameters (homoaggregate.py:16-20, state-dict names):       */
+/*     cw[G]  = depth_weight.0.conv.weight      bn = {weight,bias,mean,var}    */
+/*     fc_w, fc_b = depth_weight.1.{weight,bias}                               */
+/*   out: (B,G,D,H,W)                                                          */
+/* ------------------------------------------------------------------------- */
+int SYM(mdf_oracle_vector_aggregate)(const REAL *const *features, const REAL *const *rot_trans, int N,
+                                     const REAL *hypos, int per_pixel,
+                                     const REAL *cw, REAL bn_w, REAL bn_b, REAL bn_mean, REAL bn_var, REAL bn_eps,
+                                     REAL fc_w, REAL fc_b,
+                                     int B, int C, int G, int D, int H, int W, REAL *out)
+{
+    if (N < 2 || G <= 0 || C % G != 0 || C / G > 16) return MDF_EINVAL;
+    const int cpg = C / G;
+    const size_t HW = (size_t)H * W;
+    /* eval-mode BatchNorm3d(1) folded the way ATen's CPU kernel applies it */
+    const REAL invstd = 1 / R_SQRT(bn_var + bn_eps);
+    const REAL alpha = invstd * bn_w;
+    const REAL beta = bn_b - bn_mean * alpha;
+    for (int b = 0; b < B; ++b) {
+#pragma omp parallel for collapse(2) schedule(static)
+        for (int d = 0; d < D; ++d)
+            for (int y = 0; y < H; ++y) {
+                REAL *vol = (REAL *)malloc(sizeof(REAL) * G);
+                REAL *vsum = (REAL *)malloc(sizeof(REAL) * G);
+                for (int x = 0; x < W; ++x) {
+                    REAL depth = hypo_at(hypos, per_pixel, b, d, y, x, D, H, W);
+                    REAL wsum = 0;
+                    for (int g = 0; g < G; ++g) vsum[g] = 0;
+                    for (int v = 1; v < N; ++v) {
+                        taps_t t;
+                        int ok = make_taps(sample_position(rot_trans[v - 1] + 12 * b, x, y, depth, H, W), H, W, &t);
+                        REAL z = 0;
+                        for (int g = 0; g < G; ++g) {
+                            REAL rv[16], sv[16], rp[16], sp[16];
+                            for (int k = 0; k < cpg; ++k) {
+                                size_t ch = ((size_t)b * C + (size_t)g * cpg + k) * HW;
+                                rv[k] = features[0][ch + (size_t)y * W + x];
+                                sv[k] = ok ? blend(features[v] + ch, W, &t) : 0;
+                            }
+                            softmax_n(rv, cpg, rp);   /* homoaggregate.py:32 */
+                            softmax_n(sv, cpg, sp);   /* homoaggregate.py:38 */
+                            REAL dot = 0;
+                            for (int k = 0; k < cpg; ++k) dot = dot + sp[k] * rp[k]; /* :39 */
+                            vol[g] = dot;
+                            z = z + cw[g] * dot;      /* Conv3d(G,1,k=1), no bias */
+                        }
+                        REAL a = z * alpha + beta;    /* BatchNorm3d eval */
+                        a = a > 0 ? a : 0;            /* ReLU */
+                        a = a * fc_w + fc_b;          /* Conv3d(1,1,k=1) */
+                        REAL w = 1 / (1 + R_EXP(-a)); /* Sigmoid */
+                        wsum = wsum + w;              /* :41 */
+                        for (int g = 0; g < G; ++g) vsum[g] = vsum[g] + w * vol[g]; /* :42 */
+                    }
+                    for (int g = 0; g < G; ++g)
+                        out[((((size_t)b * G + g) * D + d) * H + y) * W + x] = vsum[g] / wsum; /* :46 */
+                }
+                free(vol); free(vsum);
+            }
+    }
+    return MDF_OK;
+}
+
+/* ------------------------------------------------------------------------- */
+/* homo_aggregate_by_variance (homoaggregate.py:49-69).  out: (B,C,D,H,W)     */
+/* ------------------------------------------------------------------------- */
+int SYM(mdf_oracle_variance_aggregate)(const REAL *const *features, const REAL *const *rot_trans, int N,
+                                       const REAL *hypos, int per_pixel,
+                                       int B, int C, int D, int H, int W, REAL *out)
+{
+    if (N < 2 || C <= 0) return MDF_EINVAL;
+    const size_t HW = (size_t)H * W;
+    const REAL nv = (REAL)N;
+    for (int b = 0; b < B; ++b) {
+#pragma omp parallel for collapse(2) schedule(static)
+        for (int d = 0; d < D; ++d)
+            for (int y = 0; y < H; ++y) {
+                REAL *s1 = (REAL *)malloc(sizeof(REAL) * C), *s2 = (REAL *)malloc(sizeof(REAL) * C);
+                REAL *wv = (REAL *)malloc(sizeof(REAL) * C), *sm = (REAL *)malloc(sizeof(REAL) * C);
+                for (int x = 0; x < W; ++x) {
+                    REAL depth = hypo_at(hypos, per_pixel, b, d, y, x, D, H, W);
+                    for (int c = 0; c < C; ++c) {
+                        REAL r = features[0][((size_t)b * C + c) * HW + (size_t)y * W + x];
+                        s1[c] = r; s2[c] = r * r;       /* :56 (raw reference feature) */
+                    }
+                    for (int v = 1; v < N; ++v) {
+                        taps_t t;
+                        int ok = make_taps(sample_position(rot_trans[v - 1] + 12 * b, x, y, depth, H, W), H, W, &t);
+                        for (int c = 0; c < C; ++c)
+                            wv[c] = ok ? blend(features[v] + ((size_t)b * C + c) * HW, W, &t) : 0;
+                        softmax_n(wv, C, sm);           /* :60 softmax over all channels */
+                        for (int c = 0; c < C; ++c) { s1[c] = s1[c] + sm[c]; s2[c] = s2[c] + sm[c] * sm[c]; }
+                    }
+                    for (int c = 0; c < C; ++c) {
+                        REAL mean = s1[c] / nv;
+                        out[((((size_t)b * C + c) * D + d) * H + y) * W + x] = s2[c] / nv - mean * mean; /* :66 */
+                    }
+                }
+                free(s1); free(s2); free(wv); free(sm);
+            }
+    }
+    return MDF_OK;
+}
+
+/* ------------------------------------------------------------------------- */
+/* Head.  softmax over D (regular.py:69,133), depth_regression (regress.py:5-7) */
+/* and confidence_regress (regress.py:9-25) + nearest x`up` (core.py:75-77).   */
+/* ------------------------------------------------------------------------- */
+int SYM(mdf_oracle_softmax_depth)(const REAL *logits, int B, int D, int H, int W, REAL *prob)
+{
+    const size_t HW = (size_t)H * W;
+    if (D <= 0) return MDF_EINVAL;
+    for (int b = 0; b < B; ++b)
+#pragma omp parallel for schedule(static)
+        for (size_t p = 0; p < HW; ++p) {
+            const REAL *in = logits + (size_t)b * D * HW + p;
+            REAL *o = prob + (size_t)b * D * HW + p;
+            REAL m = in[0];
+            for (int d = 1; d < D; ++d) m = in[d * HW] > m ? in[d * HW] : m;
+            REAL sum = 0;
+            for (int d = 0; d < D; ++d) { o[d * HW] = R_EXP(in[d * HW] - m); sum = sum + o[d * HW]; }
+            for (int d = 0; d < D; ++d) o[d * HW] = o[d * HW] / sum;
+        }
+    return MDF_OK;
+}
+
+int SYM(mdf_oracle_depth_regression)(const REAL *prob, const REAL *hypos, int per_pixel,
+                                     int B, int D, int H, int W, REAL *depth)
+{
+    const size_t HW = (size_t)H * W;
+    for (int b = 0; b < B; ++b)
+#pragma omp parallel for schedule(static)
+        for (size_t p = 0; p < HW; ++p) {
+            REAL acc = 0;
+            for (int d = 0; d < D; ++d) {
+                REAL h = per_pixel ? hypos[((size_t)b * D + d) * HW + p] : hypos[(size_t)b * D + d];
+                acc = acc + prob[((size_t)b * D + d) * HW + p] * h;
+            }
+            depth[(size_t)b * HW + p] = acc;
+        }
+    return MDF_OK;
+}
+
+/* window sum S[k] = n * avg_pool(pad_D(prob, pad_front, pad_back), n)[k],
+   gathered at k = trunc(sum_d prob[d] * d); result replicated up x up. */
+int SYM(mdf_oracle_confidence)(const REAL *prob, int B, int D, int H, int W,
+                               int n, int pad_front, int pad_back, int up, REAL *conf)
+{
+    const size_t HW = (size_t)H * W;
+    const int Dp = D + pad_front + pad_back - n + 1;
+    if (n <= 0 || up <= 0 || Dp <= 0) return MDF_EINVAL;
+    int status = MDF_OK;
+    for (int b = 0; b < B; ++b)
+#pragma omp parallel for schedule(static)
+        for (int y = 0; y < H; ++y)
+            for (int x = 0; x < W; ++x) {
+                const REAL *p = prob + (size_t)b * D * HW + (size_t)y * W + x;
+                REAL e = 0;
+                for (int d = 0; d < D; ++d) e = e + p[d * HW] * (REAL)d;
+                long k = (long)e;                    /* .long() truncates */
+                REAL c;
+                if (k < 0 || k >= Dp) { c = 0; status = MDF_EINVAL; } /* torch.gather would raise */
+                else {
+                    REAL s = 0;
+                    for (int j = 0; j < n; ++j) {
+                        long dd = k - pad_front + j;
+                        s = s + ((dd >= 0 && dd < D) ? p[dd * HW] : 0);
+                    }
+                    c = (REAL)n * (s / (REAL)n);
+                }
+                for (int uy = 0; uy < up; ++uy)
+                    for (int ux = 0; ux < up; ++ux)
+                        conf[((size_t)b * H * up + (size_t)y * up + uy) * ((size_t)W * up) + (size_t)x * up + ux] = c;
+            }
+    return status;
+}

@@ -1,0 +1,248 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in this directory from the UNMODIFIED reference.
+
+Run in the build container only (needs the read-only checkout at /root/reference and
+torch CPU):   python tests/golden/make_golden.py
+
+The reference ships no tests, golden vectors or checkpoints, so parity is
+pinned on outputs of the reference's own functions imported as-is:
+  net.unit.base.homo_warping, net.unit.homoaggregate.{VectorAggregate,
+  homo_aggregate_by_variance}, net.unit.regress.{depth_regression, confidence_regress},
+  net.unit.scale.scale_cam, F.softmax tail of net.unit.regular, and a whole
+  config.model (CoreNet) forward with per-stage tensors captured by hooks.
+Inputs come from mdf_net_b200.synthetic (seeded); each .npz stores inputs and outputs so the
+GPU box (which has no /root/reference) can replay them.
+"""
+import os
+import sys
+
+sys.dont_write_bytecode = True
+REF = os.environ.get("MDF_REFERENCE", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from mdf_net_b200 import synthetic as syn
+
+torch.set_num_threads(1)   # fixed reduction order inside ATen for the goldens
+torch.manual_seed(1)
+
+from net.unit.base import homo_warping                      # noqa: E402
+from net.unit.homoaggregate import VectorAggregate, homo_aggregate_by_variance  # noqa: E402
+from net.unit import regress, scale as ref_scale            # noqa: E402
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **{k: np.asarray(v) for k, v in arrays.items()})
+    print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+def op_rig(B, N, H, W, seed):
+    """Projection matrices at feature resolution (as scale_cam would hand them over)."""
+    K, E = syn.camera_rig(B, N, H, W, seed=seed)
+    ref_proj, src_projs = ref_scale.scale_cam(T(K), T(E), 3)   # stage 3 -> level 0: no rescale
+    return ref_proj, list(src_projs)
+
+
+def set_depth_weight(mod, p):
+    """Load synthetic depth_weight parameters into a reference VectorAggregate."""
+    with torch.no_grad():
+        mod.depth_weight[0].conv.weight.copy_(T(p["cw"]).view(1, -1, 1, 1, 1))
+        bn = mod.depth_weight[0].bn
+        bn.weight.fill_(float(p["bn_weight"])); bn.bias.fill_(float(p["bn_bias"]))
+        bn.running_mean.fill_(float(p["bn_mean"])); bn.running_var.fill_(float(p["bn_var"]))
+        mod.depth_weight[1].weight.fill_(float(p["fc_weight"])); mod.depth_weight[1].bias.fill_(float(p["fc_bias"]))
+
+
+# ---------------------------------------------------------------------------- homo_warping
+def gen_warp():
+    for name, B, C, D, H, W, per_pixel, seed in [
+        ("warp_uniform", 2, 8, 6, 12, 16, False, 11),
+        ("warp_pixel", 2, 6, 5, 10, 14, True, 12),
+    ]:
+        ref_proj, src_projs = op_rig(B, 3, H, W, seed)
+        fea = syn.smooth_features(B, 1, C, H, W, seed=seed)[0]
+        hyp = syn.pixel_hypos(B, D, H, W, seed=seed) if per_pixel else syn.uniform_hypos(B, D)
+        outs, projs = [], []
+        for sp in src_projs:
+            outs.append(homo_warping(T(fea), sp, ref_proj, T(hyp)).numpy())
+            projs.append(torch.matmul(sp, torch.inverse(ref_proj)).numpy())   # base.py:98
+        save(name, src_fea=fea, ref_proj=ref_proj.numpy(), src_projs=np.stack([s.numpy() for s in src_projs]),
+             depth_hypos=hyp, proj=np.stack(projs), warped=np.stack(outs))
+
+    # edge cases: hypotheses that put points behind / on the source camera plane, huge and
+    # non-finite depths, and the identity homography (documents the half-pixel shift)
+    B, C, D, H, W = 1, 4, 8, 9, 11
+    ref_proj, src_projs = op_rig(B, 2, H, W, 13)
+    fea = syn.smooth_features(B, 1, C, H, W, seed=13)[0]
+    hyp = np.array([425.0, -300.0, 0.0, 1e-3, 1e9, np.inf, np.nan, 935.0], np.float32).reshape(1, D, 1, 1)
+    out = homo_warping(T(fea), src_projs[0], ref_proj, T(hyp)).numpy()
+    ident = homo_warping(T(fea), ref_proj, ref_proj, T(hyp[:, :1])).numpy()
+    save("warp_edge", src_fea=fea, ref_proj=ref_proj.numpy(), src_proj=src_projs[0].numpy(), depth_hypos=hyp,
+         warped=out, warped_identity=ident)
+
+
+# ------------------------------------------------------------------------- VectorAggregate
+def gen_vecagg():
+    for name, B, N, C, G, D, H, W, per_pixel, seed in [
+        ("vecagg_s0", 1, 3, 64, 32, 48, 6, 8, False, 21),
+        ("vecagg_s1", 2, 5, 32, 16, 24, 8, 8, True, 22),
+        ("vecagg_s2", 1, 4, 16, 8, 8, 16, 24, True, 23),
+        ("vecagg_cpg4", 1, 3, 16, 4, 6, 8, 10, False, 24),
+        ("vecagg_n2", 2, 2, 16, 8, 4, 7, 9, True, 25),     # ragged sizes, single source view
+    ]:
+        ref_proj, src_projs = op_rig(B, N, H, W, seed)
+        feats = syn.smooth_features(B, N, C, H, W, seed=seed)
+        hyp = syn.pixel_hypos(B, D, H, W, seed=seed) if per_pixel else syn.uniform_hypos(B, D)
+        p = syn.depth_weight_params(G, seed=seed)
+        mod = VectorAggregate(G).eval()
+        set_depth_weight(mod, p)
+        with torch.no_grad():
+            out = mod([T(f) for f in feats], ref_proj, src_projs, T(hyp)).numpy()
+        save(name, features=np.stack(feats), ref_proj=ref_proj.numpy(),
+             src_projs=np.stack([s.numpy() for s in src_projs]), depth_hypos=hyp, groups=G,
+             cost_volume=out, **{"p_" + k: v for k, v in p.items()})
+
+
+def gen_varagg():
+    B, N, C, D, H, W, seed = 1, 3, 16, 8, 8, 12, 31
+    ref_proj, src_projs = op_rig(B, N, H, W, seed)
+    feats = syn.smooth_features(B, N, C, H, W, seed=seed)
+    for name, hyp in [("varagg_uniform", syn.uniform_hypos(B, D)), ("varagg_pixel", syn.pixel_hypos(B, D, H, W, seed=seed))]:
+        out = homo_aggregate_by_variance([T(f) for f in feats], ref_proj, src_projs, T(hyp)).numpy()
+        save(name, features=np.stack(feats), ref_proj=ref_proj.numpy(),
+             src_projs=np.stack([s.numpy() for s in src_projs]), depth_hypos=hyp, cost_volume=out)
+
+
+# ------------------------------------------------------------------------------------ head
+def gen_head():
+    for name, B, D, H, W, seed in [("head_d48", 1, 48, 8, 12, 41), ("head_d24", 2, 24, 8, 12, 42), ("head_d8", 2, 8, 12, 16, 43)]:
+        logits = syn.regulariser_logits(B, D, H, W, seed=seed)
+        prob = F.softmax(T(logits), dim=1)                                   # regular.py:69,133
+        hyp_u, hyp_p = syn.uniform_hypos(B, D), syn.pixel_hypos(B, D, H, W, seed=seed)
+        depth_u = regress.depth_regression(prob, T(hyp_u)).numpy()
+        depth_p = regress.depth_regression(prob, T(hyp_p)).numpy()
+        conf = regress.confidence_regress(prob)
+        conf_up = F.interpolate(conf.unsqueeze(1), size=None, scale_factor=2, mode="nearest",
+                                align_corners=None).squeeze(1)              # core.py:76-77
+        last = T(np.random.default_rng(seed).uniform(0, 1, (B, H // 2, W // 2)).astype(np.float32))
+        conf_blend = regress.confidence_regress(prob, last_confidence=last)
+        save(name, logits=logits, prob=prob.numpy(), hypos_uniform=hyp_u, hypos_pixel=hyp_p,
+             depth_uniform=depth_u, depth_pixel=depth_p, confidence=conf.numpy(), confidence_up=conf_up.numpy(),
+             last_confidence=last.numpy(), confidence_blend=conf_blend.numpy())
+    # known answers: one-hot and uniform probability volumes
+    D, H, W = 8, 2, 8
+    onehot = np.zeros((1, D, H, W), np.float32)
+    for i in range(H * W):
+        onehot[0, i % D, i // W, i % W] = 1.0
+    unif = np.full((1, D, H, W), 1.0 / D, np.float32)
+    save("head_known", onehot=onehot, onehot_conf=regress.confidence_regress(T(onehot)).numpy(),
+         uniform=unif, uniform_conf=regress.confidence_regress(T(unif)).numpy())
+
+
+# -------------------------------------------------------------------------------- scale_cam
+def gen_scale():
+    K, E = syn.camera_rig(2, 4, 64, 80, seed=51)
+    out = {}
+    for stage in range(3):
+        ref_proj, src_projs = ref_scale.scale_cam(T(K), T(E), stage)
+        out[f"ref_proj_{stage}"] = ref_proj.numpy()
+        out[f"src_projs_{stage}"] = np.stack([s.numpy() for s in src_projs])
+    save("scale_cam", intrinsics=K, extrinsics=E, **out)
+
+
+# ---------------------------------------------------------------------- whole CoreNet forward
+def gen_corenet():
+    import config  # builds config.model at import (config.py:186-218)
+    model = config.model.eval()
+    g = torch.Generator().manual_seed(7)
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, (torch.nn.BatchNorm2d, torch.nn.BatchNorm3d)):
+                m.running_mean.copy_(0.1 * torch.randn(m.running_mean.shape, generator=g))
+                m.running_var.copy_(0.5 + torch.rand(m.running_var.shape, generator=g))
+                m.weight.copy_(0.8 + 0.4 * torch.rand(m.weight.shape, generator=g))
+                m.bias.copy_(0.1 * torch.randn(m.bias.shape, generator=g))
+        for i, hm in enumerate(model.Homoaggre):
+            set_depth_weight(hm, syn.depth_weight_params(hm.ngroups, seed=60 + i))
+
+    B, N, H0, W0 = 1, 3, 64, 64
+    rng = np.random.default_rng(61)
+    imgs = rng.uniform(0, 1, (B, N, 3, H0, W0)).astype(np.float32)
+    K, E = syn.camera_rig(B, N, H0, W0, seed=61)
+    depth_range = np.array([[425.0, 935.0]], np.float32)
+
+    with torch.no_grad():
+        # default-init features are ~1e-4 and give a degenerate cost volume: rescale the
+        # FPN output convs to unit-ish feature magnitude, and the prob convs to useful logits
+        feats = model.Backbone(T(imgs[:, 0]))
+        for conv, f in zip((model.Backbone.out4, model.Backbone.out3, model.Backbone.out2), feats):
+            conv.weight.mul_(1.5 / float(f.std()))
+
+    cap = {}
+
+    def hook_homo(i):
+        def fn(mod, args, out):
+            features, ref_proj, src_projs, hyp = args
+            cap[f"s{i}_features"] = np.stack([f.numpy() for f in features])
+            cap[f"s{i}_ref_proj"] = ref_proj.numpy()
+            cap[f"s{i}_src_projs"] = np.stack([s.numpy() for s in src_projs])
+            cap[f"s{i}_depth_hypos"] = hyp.numpy()
+            cap[f"s{i}_cost_volume"] = out.numpy()
+            p = mod.depth_weight
+            cap[f"s{i}_cw"] = p[0].conv.weight.detach().numpy().reshape(-1)
+            cap[f"s{i}_bn"] = np.array([p[0].bn.weight.item(), p[0].bn.bias.item(), p[0].bn.running_mean.item(),
+                                        p[0].bn.running_var.item(), p[0].bn.eps], np.float64)
+            cap[f"s{i}_fc"] = np.array([p[1].weight.item(), p[1].bias.item()], np.float64)
+        return fn
+
+    def hook_prob_conv(i):
+        def fn(mod, args, out):
+            cap[f"s{i}_logits"] = out.squeeze(1).numpy()
+        return fn
+
+    def hook_regular(i):
+        def fn(mod, args, out):
+            cap[f"s{i}_prob"] = out.numpy()
+        return fn
+
+    with torch.no_grad():
+        # first pass to find the logit scale, then rescale prob convs
+        handles = [model.Regular[i].prob.register_forward_hook(hook_prob_conv(i)) for i in range(3)]
+        model(T(imgs), T(E), T(K), T(depth_range))
+        for i in range(3):
+            model.Regular[i].prob.weight.mul_(2.0 / float(np.std(cap[f"s{i}_logits"])))
+        handles += [model.Homoaggre[i].register_forward_hook(hook_homo(i)) for i in range(3)]
+        handles += [model.Regular[i].register_forward_hook(hook_regular(i)) for i in range(3)]
+        depths = []
+        orig = model.Depth_regress
+        model.Depth_regress = lambda p, h: depths.append(orig(p, h)) or depths[-1]
+        out = model(T(imgs), T(E), T(K), T(depth_range))
+        model.Depth_regress = orig
+        for h in handles:
+            h.remove()
+    for i, d in enumerate(depths):
+        cap[f"s{i}_depth"] = d.numpy()
+    cap["confidence"] = out["confidence"].numpy()
+    cap["final_depth"] = out["depth"].numpy()
+    cap["intrinsics"], cap["extrinsics"], cap["depth_range"] = K, E, depth_range
+    keys = sorted(model.Homoaggre.state_dict().keys())
+    cap["homoaggre_state_keys"] = np.array(keys)
+    save("corenet_64x64_n3", **cap)
+
+
+if __name__ == "__main__":
+    only = sys.argv[1:]
+    for fn in (gen_warp, gen_vecagg, gen_varagg, gen_head, gen_scale, gen_corenet):
+        if not only or fn.__name__ in only:
+            fn()

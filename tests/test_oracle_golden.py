@@ -1,0 +1,133 @@
+"""Pin the CPU oracle (oracle/mdf_oracle.c) on outputs of the unmodified reference.
+
+The fixtures under tests/golden/ were produced by tests/golden/make_golden.py, which imports
+the reference's own homo_warping / VectorAggregate / regress functions (torch CPU).
+Tolerances: the coordinate + bilinear restatement is bit-exact once the reference's own 4x4
+`src_proj @ inverse(ref_proj)` is supplied; with the oracle's own 4x4 LU the projection differs
+from MKL's by 1-2 ulp, which moves samples by ~1e-5 px (rel-L2 ~1e-6 on warped features).
+"""
+import numpy as np
+import pytest
+
+from oracle import c_oracle as co
+from conftest import load_golden, rel_l2, max_abs_over_max
+
+
+def _rt_from_proj(proj):
+    B = proj.shape[0]
+    return np.concatenate([proj[:, :3, :3].reshape(B, 9), proj[:, :3, 3]], 1)
+
+
+@pytest.mark.parametrize("name", ["warp_uniform", "warp_pixel"])
+def test_warp_bit_exact_given_reference_projection(name):
+    z = load_golden(name)
+    for v in range(z["src_projs"].shape[0]):
+        w = co.homo_warp(z["src_fea"], z["depth_hypos"], rot_trans=_rt_from_proj(z["proj"][v]))
+        assert np.array_equal(w, z["warped"][v]), "coordinate/bilinear restatement must be bit exact"
+
+
+@pytest.mark.parametrize("name", ["warp_uniform", "warp_pixel"])
+def test_compose_proj_and_warp(name):
+    z = load_golden(name)
+    for v in range(z["src_projs"].shape[0]):
+        rt = co.compose_proj(z["src_projs"][v], z["ref_proj"])
+        ref = _rt_from_proj(z["proj"][v])
+        assert np.abs(rt - ref).max() <= 4e-7 * np.abs(ref).max()
+        w = co.homo_warp(z["src_fea"], z["depth_hypos"], src_proj=z["src_projs"][v], ref_proj=z["ref_proj"])
+        assert rel_l2(w, z["warped"][v]) < 1e-5
+
+
+def test_warp_edge_cases():
+    """z<=0, tiny, huge depths follow the reference exactly; non-finite hypotheses give zeros
+    (the reference's CUDA grid_sample maps NaN to -100, GridSampler.cuh:140-147; its CPU kernel
+    returns NaN there -- documented divergence)."""
+    z = load_golden("warp_edge")
+    w = co.homo_warp(z["src_fea"], z["depth_hypos"], src_proj=z["src_proj"], ref_proj=z["ref_proj"])
+    ref = z["warped"]
+    finite = np.isfinite(z["depth_hypos"].ravel())
+    assert rel_l2(w[:, :, finite], ref[:, :, finite]) < 1e-5
+    assert np.all((w[:, :, finite] != 0) == (ref[:, :, finite] != 0))
+    assert np.all(np.isnan(ref[:, :, ~finite])) and np.all(w[:, :, ~finite] == 0)
+    # z == 0 and depth 1e-3 put every sample far outside: all zeros in both
+    assert np.all(ref[:, :, 2:4] == 0) and np.all(w[:, :, 2:4] == 0)
+    wi = co.homo_warp(z["src_fea"], z["depth_hypos"][:, :1], src_proj=z["ref_proj"], ref_proj=z["ref_proj"])
+    assert rel_l2(wi, z["warped_identity"]) < 1e-5
+    # identity homography is NOT the identity map: half-pixel shift of the align_corners mismatch
+    assert rel_l2(wi[:, :, 0], z["src_fea"]) > 1e-2
+
+
+def _vecagg(z, prec="f32"):
+    p = {k[2:]: z[k] for k in z.files if k.startswith("p_")}
+    return co.vector_aggregate(list(z["features"]), z["depth_hypos"], p, int(z["groups"]),
+                               ref_proj=z["ref_proj"], src_projs=list(z["src_projs"]), prec=prec)
+
+
+@pytest.mark.parametrize("name", ["vecagg_s0", "vecagg_s1", "vecagg_s2", "vecagg_cpg4", "vecagg_n2"])
+def test_vector_aggregate(name):
+    z = load_golden(name)
+    out = _vecagg(z)
+    ref = z["cost_volume"]
+    assert out.shape == ref.shape
+    assert rel_l2(out, ref) < 1e-6
+    assert max_abs_over_max(out, ref) < 1e-5
+    # noise floor: the oracle is as close to a float64 evaluation as the reference itself
+    truth = _vecagg(z, "f64")
+    assert rel_l2(out, truth) < 3 * max(rel_l2(ref, truth), 5e-8)
+
+
+@pytest.mark.parametrize("name", ["varagg_uniform", "varagg_pixel"])
+def test_variance_aggregate(name):
+    z = load_golden(name)
+    out = co.variance_aggregate(list(z["features"]), z["depth_hypos"], ref_proj=z["ref_proj"],
+                                src_projs=list(z["src_projs"]))
+    assert rel_l2(out, z["cost_volume"]) < 1e-6
+    assert max_abs_over_max(out, z["cost_volume"]) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["head_d48", "head_d24", "head_d8"])
+def test_head(name):
+    z = load_golden(name)
+    assert np.abs(co.softmax_depth(z["logits"]) - z["prob"]).max() < 3e-7
+    interval = (935.0 - 425.0) / 47.0   # stage-0 hypothesis interval (depthhypos.py:33)
+    for kind in ("uniform", "pixel"):
+        d = co.depth_regression(z["prob"], z["hypos_" + kind])
+        assert np.abs(d - z["depth_" + kind]).max() < 1e-3 * interval
+    assert np.array_equal(co.confidence_regress(z["prob"]), z["confidence"])
+    assert np.array_equal(co.confidence_regress(z["prob"], upsample=2), z["confidence_up"])
+
+
+def test_head_known_answers():
+    z = load_golden("head_known")
+    assert np.array_equal(co.confidence_regress(z["onehot"]), z["onehot_conf"])
+    assert np.all(z["onehot_conf"] == 1.0)          # window k-1..k+2 always holds the one-hot bin
+    assert np.array_equal(co.confidence_regress(z["uniform"]), z["uniform_conf"])
+    assert np.all(z["uniform_conf"] == 0.5)         # E[idx]=3.5 -> 3, window of 4 out of 8
+
+
+def test_degenerate_features_give_half():
+    """All-equal features: every group similarity is 0.5 regardless of the weights."""
+    z = load_golden("vecagg_s2")
+    feats = [np.full_like(f, 0.37) for f in z["features"]]
+    p = {k[2:]: z[k] for k in z.files if k.startswith("p_")}
+    out = co.vector_aggregate(feats, z["depth_hypos"], p, int(z["groups"]), ref_proj=z["ref_proj"],
+                              src_projs=list(z["src_projs"]))
+    assert np.abs(out - 0.5).max() < 1e-6
+
+
+def test_corenet_stages_teacher_forced():
+    """Replay every stage of a whole reference CoreNet forward (captured by hooks)."""
+    z = load_golden("corenet_64x64_n3")
+    for s in range(3):
+        bn, fc = z[f"s{s}_bn"], z[f"s{s}_fc"]
+        p = {"cw": z[f"s{s}_cw"], "bn_weight": bn[0], "bn_bias": bn[1], "bn_mean": bn[2], "bn_var": bn[3],
+             "bn_eps": bn[4], "fc_weight": fc[0], "fc_bias": fc[1]}
+        G = z[f"s{s}_cw"].size
+        out = co.vector_aggregate(list(z[f"s{s}_features"]), z[f"s{s}_depth_hypos"], p, G,
+                                  ref_proj=z[f"s{s}_ref_proj"], src_projs=list(z[f"s{s}_src_projs"]))
+        assert rel_l2(out, z[f"s{s}_cost_volume"]) < 1e-5, s
+        prob = co.softmax_depth(z[f"s{s}_logits"])
+        assert np.abs(prob - z[f"s{s}_prob"]).max() < 3e-7
+        d = co.depth_regression(z[f"s{s}_prob"], z[f"s{s}_depth_hypos"])
+        assert np.abs(d - z[f"s{s}_depth"]).max() < 1e-3 * (935.0 - 425.0) / 47.0
+    conf = co.confidence_regress(z["s2_prob"], upsample=2)
+    assert np.array_equal(conf, z["confidence"])
