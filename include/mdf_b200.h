@@ -1,0 +1,139 @@
+/*
+ * mdf_b200.h -- C ABI of the B200-native plane-sweep cost-volume path of MDF-Net.
+ *
+ * One shared library (mdf_net_b200/libmdf_b200.so, sm_100a only) exports these entry points.
+ * They are what a binding for the reference's hot path would call; the reference itself is pure
+ * Python/PyTorch, so each entry replaces a *Python call site* (file:line into the reference):
+ *
+ *   mdf_homo_warp_fwd          net/unit/base.py:85-126           homo_warping(...)
+ *   mdf_cost_volume_fwd        net/unit/homoaggregate.py:25-46   VectorAggregate.forward (eval-mode BN)
+ *                              (+ :16-20 depth_weight, net/unit/base.py:50-68 ConvBNReLU3D)
+ *   mdf_variance_volume_fwd    net/unit/homoaggregate.py:49-69   homo_aggregate_by_variance(...)
+ *   mdf_softmax_regress_fwd    net/unit/regular.py:67-69,130-133 F.softmax(x, dim=1)
+ *                              + net/unit/regress.py:5-7         depth_regression(...)
+ *                              + net/unit/regress.py:9-25        confidence_regress(...)   (optional)
+ *   mdf_depth_regression_fwd   net/unit/regress.py:5-7
+ *   mdf_confidence_fwd         net/unit/regress.py:9-25 (+ nearest upsample net/core.py:75-77)
+ *
+ * Conventions:
+ *   - all tensors float32, contiguous, NCHW / NCDHW (W fastest), DEVICE pointers unless noted;
+ *   - the library allocates nothing and keeps no global state: the caller owns inputs, outputs and
+ *     the scratch `workspace` (size from the *_workspace_bytes query, 256-byte aligned);
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant, and runs
+ *     on the device that owns the output pointer; nothing synchronises the device;
+ *   - return value: MDF_OK or a negative status; no exceptions, no exit().  There is NO CPU
+ *     fallback: host pointers are rejected with MDF_ERR_NOT_DEVICE.
+ *   - depth hypotheses are (B,D,1,1) (`hypos_per_pixel` = 0) or (B,D,H,W) (`hypos_per_pixel` = 1);
+ *   - projections are the 4x4 matrices scale_cam returns (net/unit/scale.py:4-20), (B,4,4) each.
+ */
+#ifndef MDF_B200_H_
+#define MDF_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDF_ABI_VERSION 1
+
+#define MDF_OK 0
+#define MDF_ERR_INVALID_SHAPE (-1)   /* negative / inconsistent sizes, C % G != 0, N < 2 ... */
+#define MDF_ERR_UNSUPPORTED (-2)     /* valid but not implemented (e.g. more than MDF_MAX_VIEWS views) */
+#define MDF_ERR_NULL_POINTER (-3)
+#define MDF_ERR_WORKSPACE (-4)       /* workspace missing, misaligned or too small */
+#define MDF_ERR_NOT_DEVICE (-5)      /* a data pointer is not device memory */
+#define MDF_ERR_CUDA (-6)            /* launch / driver error; see mdf_last_cuda_error() */
+
+#define MDF_MAX_VIEWS 32             /* reference + 31 sources (reference default: 5 / 11) */
+
+typedef void *mdf_stream_t;          /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define MDF_API __attribute__((visibility("default")))
+#else
+#define MDF_API
+#endif
+
+MDF_API int mdf_abi_version(void);
+MDF_API const char *mdf_status_string(int status);
+/* cudaError_t of the most recent MDF_ERR_CUDA on the calling thread (0 if none). */
+MDF_API int mdf_last_cuda_error(void);
+
+/* ---- homo_warping: one source view -> (B,C,D,H,W) ------------------------------------------ */
+MDF_API size_t mdf_homo_warp_workspace_bytes(int B);
+
+MDF_API int mdf_homo_warp_fwd(const float *src_fea,        /* (B,C,H,W) */
+                      const float *src_proj,       /* (B,4,4)   */
+                      const float *ref_proj,       /* (B,4,4)   */
+                      const float *depth_hypos, int hypos_per_pixel,
+                      int B, int C, int D, int H, int W,
+                      float *warped,               /* (B,C,D,H,W) */
+                      void *workspace, size_t workspace_bytes,
+                      mdf_stream_t stream);
+
+/* ---- VectorAggregate.forward, eval mode -> cost volume (B,G,D,H,W) -------------------------- */
+MDF_API size_t mdf_cost_volume_workspace_bytes(int B, int N, int C, int G, int D, int H, int W);
+
+MDF_API int mdf_cost_volume_fwd(const float *const *features,   /* HOST array of N device ptrs, each (B,C,H,W); [0] = reference view */
+                        int N,
+                        const float *ref_proj,          /* (B,4,4) */
+                        const float *const *src_projs,  /* HOST array of N-1 device ptrs, each (B,4,4) */
+                        const float *depth_hypos, int hypos_per_pixel,
+                        /* depth_weight parameters, device pointers (state-dict names in comments) */
+                        const float *conv_weight,       /* depth_weight.0.conv.weight  (1,G,1,1,1) */
+                        const float *bn_weight,         /* depth_weight.0.bn.weight        (1,) */
+                        const float *bn_bias,           /* depth_weight.0.bn.bias          (1,) */
+                        const float *bn_mean,           /* depth_weight.0.bn.running_mean  (1,) */
+                        const float *bn_var,            /* depth_weight.0.bn.running_var   (1,) */
+                        float bn_eps,
+                        const float *fc_weight,         /* depth_weight.1.weight (1,1,1,1,1) */
+                        const float *fc_bias,           /* depth_weight.1.bias   (1,) */
+                        int B, int C, int G, int D, int H, int W,
+                        float *cost_volume,             /* (B,G,D,H,W) */
+                        void *workspace, size_t workspace_bytes,
+                        mdf_stream_t stream);
+
+/* Same op, algorithm selection for tests/benchmarks: 0 = auto, 1 = staged (TMA box) kernel,
+ * 2 = direct kernel (any C/G, taps straight from the NCHW features). */
+MDF_API int mdf_cost_volume_fwd_ex(const float *const *features, int N, const float *ref_proj,
+                           const float *const *src_projs, const float *depth_hypos, int hypos_per_pixel,
+                           const float *conv_weight, const float *bn_weight, const float *bn_bias,
+                           const float *bn_mean, const float *bn_var, float bn_eps,
+                           const float *fc_weight, const float *fc_bias,
+                           int B, int C, int G, int D, int H, int W, float *cost_volume,
+                           void *workspace, size_t workspace_bytes, int algo, mdf_stream_t stream);
+
+/* ---- homo_aggregate_by_variance -> (B,C,D,H,W) ---------------------------------------------- */
+MDF_API size_t mdf_variance_volume_workspace_bytes(int B, int N, int C, int D, int H, int W);
+
+MDF_API int mdf_variance_volume_fwd(const float *const *features, int N, const float *ref_proj,
+                            const float *const *src_projs, const float *depth_hypos, int hypos_per_pixel,
+                            int B, int C, int D, int H, int W, float *cost_volume,
+                            void *workspace, size_t workspace_bytes, mdf_stream_t stream);
+
+/* ---- head ---------------------------------------------------------------------------------- */
+/* Fused softmax over D of the regulariser logits + expectation; optionally also the photometric
+ * confidence of the same probability volume.  prob and confidence may be NULL (not produced). */
+MDF_API int mdf_softmax_regress_fwd(const float *logits,        /* (B,D,H,W) */
+                            const float *depth_hypos, int hypos_per_pixel,
+                            int B, int D, int H, int W,
+                            float *prob,                /* (B,D,H,W) or NULL */
+                            float *depth,               /* (B,H,W) */
+                            float *confidence,          /* (B,H*up,W*up) or NULL */
+                            int conf_n, int conf_pad_front, int conf_pad_back, int conf_upsample,
+                            mdf_stream_t stream);
+
+MDF_API int mdf_depth_regression_fwd(const float *prob, const float *depth_hypos, int hypos_per_pixel,
+                             int B, int D, int H, int W, float *depth, mdf_stream_t stream);
+
+/* confidence = (n * avg_pool_D(pad_D(prob, pad_front, pad_back), n))[trunc(sum_d prob_d * d)],
+ * replicated `upsample` x `upsample` (1 = regress.py as is, 2 = with core.py:76-77). */
+MDF_API int mdf_confidence_fwd(const float *prob, int B, int D, int H, int W,
+                       int n, int pad_front, int pad_back, int upsample,
+                       float *confidence, mdf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDF_B200_H_ */

@@ -1,0 +1,12 @@
+"""mdf_net_b200 -- B200-native (sm_100a) plane-sweep cost-volume path of MDF-Net.
+
+Public surface = the reference's own unit names for this path (net/unit/homoaggregate.py,
+net/unit/base.py, net/unit/regress.py), backed by hand-written CUDA kernels behind a C ABI
+(include/mdf_b200.h, mdf_net_b200/libmdf_b200.so).  Importing the package does not need a GPU;
+calling an op without the built library or with CPU tensors raises.
+"""
+from .units import (VectorAggregate, confidence_regress, depth_regression, homo_aggregate_by_variance, homo_warping,
+                    softmax_regress)
+
+__all__ = ["VectorAggregate", "homo_warping", "homo_aggregate_by_variance", "depth_regression", "confidence_regress",
+           "softmax_regress"]

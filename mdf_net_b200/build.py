@@ -1,0 +1,57 @@
+"""Build the sm_100a shared library (mdf_net_b200/libmdf_b200.so) in-tree with nvcc.
+
+`python -m mdf_net_b200.build [--force] [--verbose]`.  nvcc cross-compiles without a GPU; the
+built .so is git-ignored but travels to the GPU box with the repo snapshot.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(PKG, "csrc")
+INCLUDE = os.path.join(os.path.dirname(PKG), "include")
+LIB_PATH = os.path.join(PKG, "libmdf_b200.so")
+SOURCES = ("mdf_cost_volume.cu", "mdf_head.cu", "mdf_backward.cu")
+ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found (set NVCC=...)")
+
+
+def sources() -> list:
+    return [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+
+
+def is_fresh() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return False
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(INCLUDE, f) for f in os.listdir(INCLUDE)]
+    return all(os.path.getmtime(d) <= t for d in deps)
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    if is_fresh() and not force:
+        return LIB_PATH
+    cmd = [_nvcc(), "-O3", "-std=c++17", *ARCH_FLAGS, "-lineinfo", "-shared", "-Xcompiler", "-fPIC,-fvisibility=hidden",
+           "-I", INCLUDE, "-o", LIB_PATH + ".tmp", *sources()]
+    if verbose:
+        cmd[1:1] = ["-Xptxas", "-v"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose:
+        print(r.stdout + r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+    os.replace(LIB_PATH + ".tmp", LIB_PATH)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build_library(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -1,0 +1,262 @@
+"""`torch.library` custom ops (`mdfnet_b200::*`) over the C ABI of libmdf_b200.so.
+
+Each op is a thin shim: it validates dtypes / devices, allocates the output and the scratch
+workspace with torch (the C library allocates nothing), and passes raw device pointers, sizes and
+torch's *current* CUDA stream across the ABI.  Ops are registered for CUDA only: a CPU tensor is a
+hard error, there is no fallback (BASELINE.json north_star).
+
+Reference call sites replaced (file:line into the reference checkout):
+  cost_volume       net/unit/homoaggregate.py:25-46   VectorAggregate.forward (eval-mode BN)
+  homo_warp         net/unit/base.py:85-126           homo_warping
+  variance_volume   net/unit/homoaggregate.py:49-69   homo_aggregate_by_variance
+  softmax_regress   net/unit/regular.py:67-69,130-133 + net/unit/regress.py:5-25
+  depth_regression  net/unit/regress.py:5-7
+  confidence        net/unit/regress.py:9-25 (+ core.py:75-77 nearest upsample)
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _cabi
+
+__all__ = ["cost_volume", "homo_warp", "variance_volume", "softmax_regress", "depth_regression", "confidence",
+           "launch_count", "reset_launch_count"]
+
+# kernels launched through this module since the last reset (bench.py's `gpu_launches`)
+_launches = 0
+
+# kernel launches per C-ABI call (setup + prep + hot kernel, see csrc/*.cu)
+_LAUNCHES_STAGED, _LAUNCHES_DIRECT, _LAUNCHES_SIMPLE = 3, 2, 1
+
+
+def launch_count() -> int:
+    return _launches
+
+
+def reset_launch_count() -> None:
+    global _launches
+    _launches = 0
+
+
+def _count(n: int) -> None:
+    global _launches
+    _launches += n
+
+
+def _stream(t: Tensor):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _f32c(t: Tensor, what: str) -> Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"mdfnet_b200: {what} must be a CUDA tensor (there is no CPU fallback), got {t.device}")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"mdfnet_b200: {what} must be float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def _hypos(h: Tensor, B: int, H: int, W: int) -> Tuple[Tensor, int, int]:
+    """(B,D,1,1) -> per_pixel 0; (B,D,H,W) -> per_pixel 1 (base.py:94 reads D,H,W from the hypotheses)."""
+    if h.dim() != 4 or h.shape[0] != B:
+        raise RuntimeError(f"mdfnet_b200: depth_hypos must be (B,D,1,1) or (B,D,H,W), got {tuple(h.shape)}")
+    D = h.shape[1]
+    if h.shape[2] == 1 and h.shape[3] == 1 and not (H == 1 and W == 1):
+        return _f32c(h, "depth_hypos"), D, 0
+    if h.shape[2] == H and h.shape[3] == W:
+        return _f32c(h, "depth_hypos"), D, 1
+    raise RuntimeError(f"mdfnet_b200: depth_hypos {tuple(h.shape)} does not match the feature size {(H, W)}")
+
+
+def _workspace(nbytes: int, device) -> Tensor:
+    # torch's caching allocator returns >= 512-byte aligned blocks; stream-ordered reuse is safe
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def _check_views(features: Sequence[Tensor], src_projs: Sequence[Tensor]):
+    if len(features) < 2 or len(src_projs) != len(features) - 1:
+        raise RuntimeError(f"mdfnet_b200: need N >= 2 feature maps and N-1 source projections, got "
+                           f"{len(features)} and {len(src_projs)}")
+    shape = features[0].shape
+    if features[0].dim() != 4 or any(f.shape != shape for f in features):
+        raise RuntimeError("mdfnet_b200: all feature maps must share one (B,C,H,W) shape")
+
+
+# ------------------------------------------------------------------------------------- cost volume
+@torch.library.custom_op("mdfnet_b200::cost_volume", mutates_args=(), device_types="cuda")
+def cost_volume(features: List[Tensor], ref_proj: Tensor, src_projs: List[Tensor], depth_hypos: Tensor,
+                conv_weight: Tensor, bn_weight: Tensor, bn_bias: Tensor, bn_mean: Tensor, bn_var: Tensor,
+                bn_eps: float, fc_weight: Tensor, fc_bias: Tensor, groups: int, algo: int = 0) -> Tensor:
+    """Fused plane-sweep cost volume (B,G,D,H,W); eval-mode depth_weight.  algo: 0 auto, 1 staged, 2 direct."""
+    _check_views(features, src_projs)
+    feats = [_f32c(f, "features") for f in features]
+    B, C, H, W = feats[0].shape
+    hyp, D, per_pixel = _hypos(depth_hypos, B, H, W)
+    projs = [_f32c(p, "src_projs") for p in src_projs]
+    refp = _f32c(ref_proj, "ref_proj")
+    params = [_f32c(t, n) for t, n in ((conv_weight, "conv_weight"), (bn_weight, "bn_weight"), (bn_bias, "bn_bias"),
+                                        (bn_mean, "bn_mean"), (bn_var, "bn_var"), (fc_weight, "fc_weight"),
+                                        (fc_bias, "fc_bias"))]
+    if params[0].numel() != groups:
+        raise RuntimeError(f"mdfnet_b200: conv_weight has {params[0].numel()} elements, expected groups={groups}")
+    lib = _cabi.lib()
+    N = len(feats)
+    out = torch.empty((B, groups, D, H, W), dtype=torch.float32, device=feats[0].device)
+    ws_bytes = lib.mdf_cost_volume_workspace_bytes(B, N, C, groups, D, H, W)
+    ws = _workspace(ws_bytes, out.device)
+    st = lib.mdf_cost_volume_fwd_ex(
+        _cabi.ptr_array([f.data_ptr() for f in feats]), N, refp.data_ptr(),
+        _cabi.ptr_array([p.data_ptr() for p in projs]), hyp.data_ptr(), per_pixel,
+        params[0].data_ptr(), params[1].data_ptr(), params[2].data_ptr(), params[3].data_ptr(), params[4].data_ptr(),
+        float(bn_eps), params[5].data_ptr(), params[6].data_ptr(),
+        B, C, groups, D, H, W, out.data_ptr(), ws.data_ptr(), ws.numel(), int(algo), _stream(out))
+    _cabi.check("mdf_cost_volume_fwd", st)
+    staged = algo != 2 and C == 2 * groups and groups in (8, 16, 32)
+    _count(_LAUNCHES_STAGED if staged else _LAUNCHES_DIRECT)
+    return out
+
+
+@cost_volume.register_fake
+def _(features, ref_proj, src_projs, depth_hypos, conv_weight, bn_weight, bn_bias, bn_mean, bn_var, bn_eps,
+      fc_weight, fc_bias, groups, algo=0):
+    B, _, H, W = features[0].shape
+    return features[0].new_empty((B, groups, depth_hypos.shape[1], H, W))
+
+
+# -------------------------------------------------------------------------------------- homo_warp
+@torch.library.custom_op("mdfnet_b200::homo_warp", mutates_args=(), device_types="cuda")
+def homo_warp(src_fea: Tensor, src_proj: Tensor, ref_proj: Tensor, depth_hypos: Tensor) -> Tensor:
+    """homo_warping (base.py:85-126): (B,C,H,W) -> (B,C,D,H,W)."""
+    f = _f32c(src_fea, "src_fea")
+    if f.dim() != 4:
+        raise RuntimeError("mdfnet_b200: src_fea must be (B,C,H,W)")
+    B, C, H, W = f.shape
+    hyp, D, per_pixel = _hypos(depth_hypos, B, H, W)
+    sp, rp = _f32c(src_proj, "src_proj"), _f32c(ref_proj, "ref_proj")
+    lib = _cabi.lib()
+    out = torch.empty((B, C, D, H, W), dtype=torch.float32, device=f.device)
+    ws = _workspace(lib.mdf_homo_warp_workspace_bytes(B), f.device)
+    st = lib.mdf_homo_warp_fwd(f.data_ptr(), sp.data_ptr(), rp.data_ptr(), hyp.data_ptr(), per_pixel, B, C, D, H, W,
+                               out.data_ptr(), ws.data_ptr(), ws.numel(), _stream(out))
+    _cabi.check("mdf_homo_warp_fwd", st)
+    _count(_LAUNCHES_DIRECT)
+    return out
+
+
+@homo_warp.register_fake
+def _(src_fea, src_proj, ref_proj, depth_hypos):
+    B, C, H, W = src_fea.shape
+    return src_fea.new_empty((B, C, depth_hypos.shape[1], H, W))
+
+
+# -------------------------------------------------------------------------------- variance volume
+@torch.library.custom_op("mdfnet_b200::variance_volume", mutates_args=(), device_types="cuda")
+def variance_volume(features: List[Tensor], ref_proj: Tensor, src_projs: List[Tensor], depth_hypos: Tensor) -> Tensor:
+    """homo_aggregate_by_variance (homoaggregate.py:49-69): (B,C,D,H,W)."""
+    _check_views(features, src_projs)
+    feats = [_f32c(f, "features") for f in features]
+    B, C, H, W = feats[0].shape
+    hyp, D, per_pixel = _hypos(depth_hypos, B, H, W)
+    projs = [_f32c(p, "src_projs") for p in src_projs]
+    refp = _f32c(ref_proj, "ref_proj")
+    lib = _cabi.lib()
+    N = len(feats)
+    out = torch.empty((B, C, D, H, W), dtype=torch.float32, device=feats[0].device)
+    ws = _workspace(lib.mdf_variance_volume_workspace_bytes(B, N, C, D, H, W), out.device)
+    st = lib.mdf_variance_volume_fwd(_cabi.ptr_array([f.data_ptr() for f in feats]), N, refp.data_ptr(),
+                                     _cabi.ptr_array([p.data_ptr() for p in projs]), hyp.data_ptr(), per_pixel,
+                                     B, C, D, H, W, out.data_ptr(), ws.data_ptr(), ws.numel(), _stream(out))
+    _cabi.check("mdf_variance_volume_fwd", st)
+    _count(_LAUNCHES_DIRECT)
+    return out
+
+
+@variance_volume.register_fake
+def _(features, ref_proj, src_projs, depth_hypos):
+    B, C, H, W = features[0].shape
+    return features[0].new_empty((B, C, depth_hypos.shape[1], H, W))
+
+
+# ------------------------------------------------------------------------------------------- head
+def _prob(t: Tensor, what: str) -> Tensor:
+    t = _f32c(t, what)
+    if t.dim() != 4:
+        raise RuntimeError(f"mdfnet_b200: {what} must be (B,D,H,W), got {tuple(t.shape)}")
+    return t
+
+
+def _head_hypos(h: Tensor, B: int, D: int, H: int, W: int) -> Tuple[Tensor, int]:
+    hyp, Dh, per_pixel = _hypos(h, B, H, W)
+    if Dh != D:
+        raise RuntimeError(f"mdfnet_b200: depth_hypos has {Dh} planes, the volume has {D}")
+    return hyp, per_pixel
+
+
+@torch.library.custom_op("mdfnet_b200::softmax_regress", mutates_args=(), device_types="cuda")
+def softmax_regress(logits: Tensor, depth_hypos: Tensor, want_prob: bool = True, want_confidence: bool = False,
+                    n: int = 4, pad_front: int = 1, pad_back: int = 2, upsample: int = 2) -> Tuple[Tensor, Tensor, Tensor]:
+    """softmax over D + depth expectation (+ confidence) in one pass.  Returns (prob, depth, confidence);
+    outputs that were not requested are empty tensors."""
+    x = _prob(logits, "logits")
+    B, D, H, W = x.shape
+    hyp, per_pixel = _head_hypos(depth_hypos, B, D, H, W)
+    dev = x.device
+    prob = torch.empty_like(x) if want_prob else torch.empty(0, device=dev)
+    depth = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+    conf = torch.empty((B, H * upsample, W * upsample), dtype=torch.float32, device=dev) if want_confidence \
+        else torch.empty(0, device=dev)
+    st = _cabi.lib().mdf_softmax_regress_fwd(
+        x.data_ptr(), hyp.data_ptr(), per_pixel, B, D, H, W,
+        prob.data_ptr() if want_prob else None, depth.data_ptr(), conf.data_ptr() if want_confidence else None,
+        n, pad_front, pad_back, upsample, _stream(x))
+    _cabi.check("mdf_softmax_regress_fwd", st)
+    _count(_LAUNCHES_SIMPLE)
+    return prob, depth, conf
+
+
+@softmax_regress.register_fake
+def _(logits, depth_hypos, want_prob=True, want_confidence=False, n=4, pad_front=1, pad_back=2, upsample=2):
+    B, D, H, W = logits.shape
+    return (torch.empty_like(logits) if want_prob else logits.new_empty(0), logits.new_empty((B, H, W)),
+            logits.new_empty((B, H * upsample, W * upsample)) if want_confidence else logits.new_empty(0))
+
+
+@torch.library.custom_op("mdfnet_b200::depth_regression", mutates_args=(), device_types="cuda")
+def depth_regression(prob_volume: Tensor, depth_hypos: Tensor) -> Tensor:
+    """regress.py:5-7."""
+    p = _prob(prob_volume, "prob_volume")
+    B, D, H, W = p.shape
+    hyp, per_pixel = _head_hypos(depth_hypos, B, D, H, W)
+    out = torch.empty((B, H, W), dtype=torch.float32, device=p.device)
+    st = _cabi.lib().mdf_depth_regression_fwd(p.data_ptr(), hyp.data_ptr(), per_pixel, B, D, H, W, out.data_ptr(),
+                                              _stream(p))
+    _cabi.check("mdf_depth_regression_fwd", st)
+    _count(_LAUNCHES_SIMPLE)
+    return out
+
+
+@depth_regression.register_fake
+def _(prob_volume, depth_hypos):
+    B, _, H, W = prob_volume.shape
+    return prob_volume.new_empty((B, H, W))
+
+
+@torch.library.custom_op("mdfnet_b200::confidence", mutates_args=(), device_types="cuda")
+def confidence(prob_volume: Tensor, n: int = 4, pad_front: int = 1, pad_back: int = 2, upsample: int = 1) -> Tensor:
+    """regress.py:9-25 (last_confidence=None); upsample=2 folds in core.py:75-77."""
+    p = _prob(prob_volume, "prob_volume")
+    B, D, H, W = p.shape
+    out = torch.empty((B, H * upsample, W * upsample), dtype=torch.float32, device=p.device)
+    st = _cabi.lib().mdf_confidence_fwd(p.data_ptr(), B, D, H, W, n, pad_front, pad_back, upsample, out.data_ptr(),
+                                        _stream(p))
+    _cabi.check("mdf_confidence_fwd", st)
+    _count(_LAUNCHES_SIMPLE)
+    return out
+
+
+@confidence.register_fake
+def _(prob_volume, n=4, pad_front=1, pad_back=2, upsample=1):
+    B, _, H, W = prob_volume.shape
+    return prob_volume.new_empty((B, H * upsample, W * upsample))

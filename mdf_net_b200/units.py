@@ -1,0 +1,93 @@
+"""Drop-in replacements for the reference's hot-path units, same names and call signatures.
+
+They plug into the reference's own injection point, `core.CoreNet(Backbone, Depth_hypos, scale,
+Homoaggre, Regular, Regress, Refine)` (net/core.py:5-26, wired in config.py:186-218):
+
+    Homoaggre = nn.ModuleList([mdf_net_b200.VectorAggregate(g) for g in (32, 16, 8)])
+    Regress   = [mdf_net_b200.depth_regression, mdf_net_b200.confidence_regress]
+
+`VectorAggregate` keeps the reference's state-dict keys (`depth_weight.0.conv.weight`,
+`depth_weight.0.bn.{weight,bias,running_mean,running_var,num_batches_tracked}`,
+`depth_weight.1.{weight,bias}`), so `load_state_dict(strict=True)` of a reference checkpoint works
+(eval.py:15-17).  All compute runs in libmdf_b200.so; tensors must live on a CUDA device.
+"""
+from __future__ import annotations
+
+from typing import Sequence
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from . import ops
+
+
+class _PointwiseConvBNReLU3D(nn.Module):
+    """Parameter container with the sub-module names of the reference's ConvBNReLU3D
+    (net/unit/base.py:50-68) for the k=1 case used by depth_weight; never called as a layer."""
+
+    def __init__(self, in_channels: int, out_channels: int):
+        super().__init__()
+        self.conv = nn.Conv3d(in_channels, out_channels, 1, 1, 0, bias=False)
+        self.bn = nn.BatchNorm3d(out_channels)
+        self.relu = nn.ReLU(inplace=True)
+
+
+class VectorAggregate(nn.Module):
+    """Fused homo_warping + group-softmax similarity + learned view weighting.
+
+    Mirrors net/unit/homoaggregate.py:8-46.  forward(features, ref_proj, src_projs, depth_hypos)
+    -> cost volume (B, ngroups, D, H, W).
+    """
+
+    def __init__(self, ngroups: int = 8, algo: int = 0):
+        super().__init__()
+        self.ngroups = ngroups
+        self.algo = algo
+        # (B,G,D,H,W) -> (B,1,D,H,W): Conv3d(G,1,k=1,no bias) - BN - ReLU - Conv3d(1,1,k=1) - Sigmoid
+        self.depth_weight = nn.Sequential(_PointwiseConvBNReLU3D(ngroups, 1), nn.Conv3d(1, 1, 1, 1, 0), nn.Sigmoid())
+
+    def forward(self, features: Sequence[Tensor], ref_proj: Tensor, src_projs: Sequence[Tensor],
+                depth_hypos: Tensor) -> Tensor:
+        cbr, fc = self.depth_weight[0], self.depth_weight[1]
+        if self.training or torch.is_grad_enabled() and any(t.requires_grad for t in (*features, *self.parameters())):
+            from . import autograd  # train-mode BatchNorm (batch statistics) and the backward pass
+            return autograd.vector_aggregate_train(self, list(features), ref_proj, list(src_projs), depth_hypos)
+        return ops.cost_volume(list(features), ref_proj, list(src_projs), depth_hypos,
+                               cbr.conv.weight, cbr.bn.weight, cbr.bn.bias, cbr.bn.running_mean, cbr.bn.running_var,
+                               cbr.bn.eps, fc.weight, fc.bias, self.ngroups, self.algo)
+
+
+def homo_warping(src_fea: Tensor, src_proj: Tensor, ref_proj: Tensor, depth_hypos: Tensor) -> Tensor:
+    """net/unit/base.py:85-126: warp one source feature map into the reference frustum, (B,C,D,H,W)."""
+    return ops.homo_warp(src_fea, src_proj, ref_proj, depth_hypos)
+
+
+def homo_aggregate_by_variance(features: Sequence[Tensor], ref_proj: Tensor, src_projs: Sequence[Tensor],
+                               depth_hypos: Tensor) -> Tensor:
+    """net/unit/homoaggregate.py:49-69: channel-softmax of the warped sources + cross-view variance."""
+    return ops.variance_volume(list(features), ref_proj, list(src_projs), depth_hypos)
+
+
+def depth_regression(prob_volume: Tensor, depth_hypos: Tensor) -> Tensor:
+    """net/unit/regress.py:5-7: sum_d prob * hypothesis -> (B,H,W)."""
+    return ops.depth_regression(prob_volume, depth_hypos)
+
+
+def confidence_regress(prob_volume: Tensor, last_confidence=None, n: int = 4, pad=(0, 0, 0, 0, 1, 2)) -> Tensor:
+    """net/unit/regress.py:9-25.  The bicubic blend with `last_confidence` (never taken by
+    core.py:75) is done with torch on the op's output, as the reference does."""
+    if tuple(pad[:4]) != (0, 0, 0, 0):
+        raise ValueError("confidence_regress: only the depth axis may be padded (pad[:4] must be 0)")
+    conf = ops.confidence(prob_volume, n, int(pad[4]), int(pad[5]), 1)
+    if last_confidence is not None:
+        last = torch.nn.functional.interpolate(last_confidence.unsqueeze(1), scale_factor=2, mode="bicubic").squeeze(1)
+        conf = 0.8 * last + 0.2 * conf
+    return conf
+
+
+def softmax_regress(logits: Tensor, depth_hypos: Tensor, want_confidence: bool = False, upsample: int = 2):
+    """Fused tail for a regulariser that hands over logits (regular.py:67-69,130-133 without its last
+    line): returns (prob_volume, depth[, confidence at `upsample` x resolution])."""
+    prob, depth, conf = ops.softmax_regress(logits, depth_hypos, True, want_confidence, 4, 1, 2, upsample)
+    return (prob, depth, conf) if want_confidence else (prob, depth)

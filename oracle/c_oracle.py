@@ -109,10 +109,11 @@ def _rot_trans_list(ref_proj, src_projs, rot_trans, prec):
 
 
 def vector_aggregate(features: Sequence, depth_hypos, params: dict, G: int,
-                     ref_proj=None, src_projs=None, rot_trans=None, prec="f32"):
+                     ref_proj=None, src_projs=None, rot_trans=None, prec="f32", rows=None):
     """VectorAggregate.forward in eval mode (homoaggregate.py:25-46).
 
     params: {"cw": (G,), "bn_weight", "bn_bias", "bn_mean", "bn_var", "bn_eps", "fc_weight", "fc_bias"}
+    rows=(y0, y1): evaluate only those rows (bench.py's bounded sample); returns (B,G,D,y1-y0,W).
     """
     feats = [_arr(f, prec) for f in features]
     B, C, H, W = feats[0].shape
@@ -123,16 +124,17 @@ def vector_aggregate(features: Sequence, depth_hypos, params: dict, G: int,
     cw = _arr(np.asarray(params["cw"]).reshape(-1), prec)
     out = np.empty((B, G, D, H, W), _dt(prec))
     R = _real(prec)
-    fn = getattr(_lib(prec), f"mdf_oracle_vector_aggregate_{prec}")
+    y0, y1 = (0, H) if rows is None else (int(rows[0]), int(rows[1]))
+    fn = getattr(_lib(prec), f"mdf_oracle_vector_aggregate_rows_{prec}")
     fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
-                   ctypes.c_void_p, R, R, R, R, R, R, R] + [ctypes.c_int] * 6 + [ctypes.c_void_p]
+                   ctypes.c_void_p, R, R, R, R, R, R, R] + [ctypes.c_int] * 8 + [ctypes.c_void_p]
     rc = fn(_ptr_array(feats), _ptr_array(rts), N, _ptr(h), pp, _ptr(cw),
             float(params["bn_weight"]), float(params["bn_bias"]), float(params["bn_mean"]),
             float(params["bn_var"]), float(params.get("bn_eps", 1e-5)),
             float(params["fc_weight"]), float(params["fc_bias"]),
-            B, C, G, D, H, W, _ptr(out))
+            B, C, G, D, H, W, y0, y1, _ptr(out))
     _check(rc, "vector_aggregate")
-    return out
+    return out if rows is None else out[:, :, :, y0:y1]
 
 
 def variance_aggregate(features: Sequence, depth_hypos, ref_proj=None, src_projs=None, rot_trans=None, prec="f32"):
@@ -180,3 +182,14 @@ def confidence_regress(prob_volume, n=4, pad=(0, 0, 0, 0, 1, 2), upsample=1, pre
     fn = getattr(_lib(prec), f"mdf_oracle_confidence_{prec}")
     _check(fn(_ptr(p), B, D, H, W, int(n), int(pad[4]), int(pad[5]), int(upsample), _ptr(out)), "confidence")
     return out
+
+
+def num_threads() -> int:
+    """Threads the OpenMP build uses (1 when built with OMP=)."""
+    lib = _lib("f32")
+    try:
+        fn = lib.omp_get_max_threads
+    except AttributeError:
+        return 1
+    fn.restype = ctypes.c_int
+    return int(fn())

@@ -233,13 +233,14 @@ static inline void softmax_n(const REAL *in, int n, REAL *out)
 /*     fc_w, fc_b = depth_weight.1.{weight,bias}                               */
 /*   out: (B,G,D,H,W)                                                          */
 /* ------------------------------------------------------------------------- */
-int SYM(mdf_oracle_vector_aggregate)(const REAL *const *features, const REAL *const *rot_trans, int N,
-                                     const REAL *hypos, int per_pixel,
-                                     const REAL *cw, REAL bn_w, REAL bn_b, REAL bn_mean, REAL bn_var, REAL bn_eps,
-                                     REAL fc_w, REAL fc_b,
-                                     int B, int C, int G, int D, int H, int W, REAL *out)
+/* rows [y0, y1) only (bench.py's bounded CPU sample); the other rows of `out` are left untouched */
+int SYM(mdf_oracle_vector_aggregate_rows)(const REAL *const *features, const REAL *const *rot_trans, int N,
+                                          const REAL *hypos, int per_pixel,
+                                          const REAL *cw, REAL bn_w, REAL bn_b, REAL bn_mean, REAL bn_var, REAL bn_eps,
+                                          REAL fc_w, REAL fc_b,
+                                          int B, int C, int G, int D, int H, int W, int y0, int y1, REAL *out)
 {
-    if (N < 2 || G <= 0 || C % G != 0 || C / G > 16) return MDF_EINVAL;
+    if (N < 2 || G <= 0 || C % G != 0 || C / G > 16 || y0 < 0 || y1 > H) return MDF_EINVAL;
     const int cpg = C / G;
     const size_t HW = (size_t)H * W;
     /* eval-mode BatchNorm3d(1) folded the way ATen's CPU kernel applies it */
@@ -249,7 +250,7 @@ int SYM(mdf_oracle_vector_aggregate)(const REAL *const *features, const REAL *co
     for (int b = 0; b < B; ++b) {
 #pragma omp parallel for collapse(2) schedule(static)
         for (int d = 0; d < D; ++d)
-            for (int y = 0; y < H; ++y) {
+            for (int y = y0; y < y1; ++y) {
                 REAL *vol = (REAL *)malloc(sizeof(REAL) * G);
                 REAL *vsum = (REAL *)malloc(sizeof(REAL) * G);
                 for (int x = 0; x < W; ++x) {
@@ -288,6 +289,16 @@ int SYM(mdf_oracle_vector_aggregate)(const REAL *const *features, const REAL *co
             }
     }
     return MDF_OK;
+}
+
+int SYM(mdf_oracle_vector_aggregate)(const REAL *const *features, const REAL *const *rot_trans, int N,
+                                     const REAL *hypos, int per_pixel,
+                                     const REAL *cw, REAL bn_w, REAL bn_b, REAL bn_mean, REAL bn_var, REAL bn_eps,
+                                     REAL fc_w, REAL fc_b,
+                                     int B, int C, int G, int D, int H, int W, REAL *out)
+{
+    return SYM(mdf_oracle_vector_aggregate_rows)(features, rot_trans, N, hypos, per_pixel, cw, bn_w, bn_b, bn_mean,
+                                                 bn_var, bn_eps, fc_w, fc_b, B, C, G, D, H, W, 0, H, out);
 }
 
 /* ------------------------------------------------------------------------- */
