@@ -239,7 +239,7 @@ def run_b200(args, workload):
         return out
 
     dev_views = [convert(v, pin=False) for v in host_views]
-    pin_views = [convert(v, pin=True) for v in host_views]
+    pin_views = [convert(v, pin=True) for v in host_views] if not args.no_e2e else None
 
     def hot_path(view, events=None):
         """3 x (fused cost volume -> fused head).  Returns the per-stage depth maps and the confidence."""
@@ -301,16 +301,18 @@ def run_b200(args, workload):
         cv_ms = [statistics.mean(ev[s][0].elapsed_time(ev[s][1]) for ev in stage_events) for s in range(3)]
 
         # ------------------------------------------------------------------------- end to end (host)
-        for i in range(3):
-            e2e_step(pin_views[i % 2])
-        barrier()
         e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if not args.no_e2e:
+            for i in range(3):
+                e2e_step(pin_views[i % 2])
+        barrier()
         e_start.record()
-        for i in range(args.steps):
-            e2e_step(pin_views[i % 2])
+        if not args.no_e2e:
+            for i in range(args.steps):
+                e2e_step(pin_views[i % 2])
         e_end.record()
         barrier()
-        e2e_ms = e_start.elapsed_time(e_end)
+        e2e_ms = e_start.elapsed_time(e_end) if not args.no_e2e else float("nan")
 
     if world > 1:
         t = torch.tensor([elapsed_ms, e2e_ms], device=dev, dtype=torch.float64)
@@ -330,8 +332,8 @@ def run_b200(args, workload):
             pass
         peak = float(peaks.get("hbm_gbs", FALLBACK_HBM_GBS))
         views = world * args.steps * batch
-        h2d = sum(sum(f.numel() for f in st["features"]) + st["ref_proj"].numel() + sum(q.numel() for q in st["src_projs"])
-                  + st["hypos"].numel() + st["logits"].numel() for st in pin_views[0]) * 4
+        h2d = sum(sum(f.size for f in st["features"]) + st["ref_proj"].size + sum(q.size for q in st["src_projs"])
+                  + st["hypos"].size + st["logits"].size for st in host_views[0]) * 4
         H2, W2 = syn.stage_shapes(h0, w0)[2]
         d2h = 4 * batch * (sum(h * w for h, w in syn.stage_shapes(h0, w0)) + 4 * H2 * W2)
         achieved = sum(cv_bytes) / 1e9 / (sum(cv_ms) / 1e3)
@@ -340,8 +342,8 @@ def run_b200(args, workload):
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": make_config(workload),
-            "e2e": {"value": views / (e2e_ms / 1e3), "unit": "views/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms / args.steps},
+            "e2e": None if args.no_e2e else {"value": views / (e2e_ms / 1e3), "unit": "views/s", "h2d_bytes_per_step": h2d,
+                                             "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback",
@@ -367,6 +369,7 @@ def main():
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="dtu_1600x1152_n5")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args, args.workload)

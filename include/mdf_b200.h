@@ -133,6 +133,15 @@ MDF_API int mdf_confidence_fwd(const float *prob, int B, int D, int H, int W,
                        int n, int pad_front, int pad_back, int upsample,
                        float *confidence, mdf_stream_t stream);
 
+/* ---- diagnostics --------------------------------------------------------------------------- */
+/* Sample positions (pixel units of the source map, as grid_sample uses them: base.py:102-119 +
+ * ATen unnormalize) of every (d, y, x) for one precomposed projection `rot_trans` (12 floats:
+ * rot row-major, then trans), computed with the hot kernel's division-free coordinate chain.
+ * Exists so that the parity tests can pin that chain bit for bit; no product path calls it. */
+MDF_API int mdf_debug_sample_positions(const float *rot_trans, const float *depth_hypos, int hypos_per_pixel,
+                                       int D, int H, int W, float *ix /* (D,H,W) */, float *iy /* (D,H,W) */,
+                                       mdf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,6 +38,7 @@ SIGNATURES = {
     "mdf_softmax_regress_fwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P]),
     "mdf_depth_regression_fwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "mdf_confidence_fwd": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "mdf_debug_sample_positions": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
 }
 
 

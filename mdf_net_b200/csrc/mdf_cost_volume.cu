@@ -9,17 +9,20 @@
 //   setup_kernel            per call: proj = src_proj @ inverse(ref_proj) for every (view, batch) in
 //                           float64 (no host sync, unlike torch.inverse at base.py:98) and the folded
 //                           eval-mode BatchNorm of depth_weight.
-//   prep_kernel             (C/G == 2) source features NCHW -> channels-last "pair difference" maps
-//                           S[v][b][y][x][g] = (f[2g+1]-f[2g])*log2(e), reference -> q = tanh((r0-r1)/2).
-//                           softmax([a,b]) = [sigmoid(a-b), 1-sigmoid(a-b)] and bilinear sampling is
-//                           linear, so gathering the difference map is the same computation with half
-//                           the taps and one exp per group.
+//   prep_kernel             (C/G == 2) source features NCHW -> "pair difference" maps in planar-float4
+//                           layout S4[v][b][j][y][x] = (f[2g+1]-f[2g])*log2(e) for g = 4j..4j+3, reference
+//                           -> q = tanh((r0-r1)/2).  softmax([a,b]) = [sigmoid(a-b), 1-sigmoid(a-b)] and
+//                           bilinear sampling is linear, so gathering the difference map is the same
+//                           computation with half the taps and one exp per group.
 //   cost_volume_staged      the hot kernel: a CTA owns a tile of reference pixels x a slab of depth
 //                           planes; for each source view it finds the bounding box of its samples,
-//                           pulls that box of S into shared memory with ONE TMA tile load (hardware
-//                           zero fill = grid_sample's zero padding, hardware 128/64/32B swizzle =
-//                           conflict-free 128-bit tap reads), then every thread walks its planes:
+//                           pulls that [G/4][BH][BW] float4 box of S4 into shared memory with ONE TMA
+//                           tile load (hardware zero fill = grid_sample's zero padding; neighbouring
+//                           lanes read neighbouring 16-byte texels = conflict-free LDS.128 with
+//                           immediate offsets), then every thread walks its planes:
 //                           4 x LDS.128 per 4 groups -> blend -> sigmoid -> similarity -> view weight.
+//                           Samples outside the box (rough depth maps) are served by further staging
+//                           rounds; there is no slow global-memory path.
 //                           Output stores are 128-byte coalesced rows of the (B,G,D,H,W) volume.
 //   cost_volume_direct      any C/G: taps straight from the NCHW features (no staging), two passes.
 //   homo_warp / variance    the standalone warp and the (unused by config.py) variance aggregate.
@@ -40,9 +43,9 @@ thread_local int g_last_cuda_error = 0;
 // ------------------------------------------------------------------------------------------------
 struct Workspace {
     size_t rt_off;    // [V][B][12] float   rot|trans per source view
-    size_t dwp_off;   // 64 floats: [0]=alpha [1]=beta' [2]=fc_w [3]=fc_b [4]=beta(raw)   [16..16+G)=conv weight (only G<=32 cached)
-    size_t q_off;     // [B][G][H][W] float reference q maps           (staged path)
-    size_t s_off;     // [V][B][H][W][G] float source difference maps  (staged path)
+    size_t dwp_off;   // 64 floats: [0]=alpha [1]=beta' [2]=fc_w [3]=fc_b [4]=beta(raw) [5]=weight of an out-of-image sample
+    size_t q_off;     // [B][G/4][H][W] float4 reference q maps           (staged path)
+    size_t s_off;     // [V][B][G/4][H][W] float4 source difference maps  (staged path)
     size_t total;
 };
 
@@ -122,72 +125,72 @@ __global__ void setup_kernel(SrcPtrs src_projs, const float* __restrict__ ref_pr
         dwp[2] = fc_w[0];
         dwp[3] = fc_b[0];
         dwp[4] = beta;
+        // weight of a (sample, view) pair whose taps all fall outside the source image: every similarity is 0.5
+        const float hv = fmaf(fmaxf(dwp[1], 0.0f), fc_w[0], fc_b[0]);
+        dwp[5] = 1.0f / (1.0f + expf(-hv));
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// prep (C/G == 2): blockDim (32, 8); one block = one image row segment of 32 pixels, one view.
-//   view 0 (reference):  Q[b][g][y][x]    = 2*sigmoid(r[2g]-r[2g+1]) - 1          (plane major)
-//   view v>0:            S[v-1][b][y][x][g] = (f[2g+1]-f[2g]) * log2(e)             (channels last)
+// prep (C/G == 2): one thread per pixel of one view; blockIdx.y = view * B + b.
+//   "planar float4" layout: plane j holds groups 4j..4j+3 of every pixel as one float4
+//   view 0 (reference):  Q4[b][j][y][x]      = 2*sigmoid(r[2g]-r[2g+1]) - 1,  g = 4j..4j+3
+//   view v>0:            S4[v-1][b][j][y][x] = (f[2g+1]-f[2g]) * log2(e)
+// Loads are 128-byte coalesced rows of the NCHW planes, stores are 512-byte coalesced float4 rows.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-prep_kernel(FeaPtrs feas, int B, int G, int H, int W, int xtiles, float* __restrict__ Q, float* __restrict__ S)
+prep_kernel(FeaPtrs feas, int B, int G, int HW, float4* __restrict__ Q4, float4* __restrict__ S4)
 {
-    extern __shared__ float tile[];           // [32][G+1]
-    const int lane = threadIdx.x, wy = threadIdx.y;
-    int it = blockIdx.x;
-    const int xt = it % xtiles; it /= xtiles;
-    const int y = it % H; it /= H;
-    const int b = it % B;
-    const int v = it / B;
-    const int x = xt * 32 + lane;
-    const size_t HW = (size_t)H * W;
-    const float* __restrict__ f = feas.p[v] + (size_t)b * 2 * G * HW + (size_t)y * W;
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= HW) return;
+    const int v = blockIdx.y / B, b = blockIdx.y % B;
+    const float* __restrict__ f = feas.p[v] + (size_t)b * 2 * G * HW + pix;
+    const int J = G / 4;
     if (v == 0) {
-        if (x < W)
-            for (int g = wy; g < G; g += 8) {
-                const float a = __ldg(f + (size_t)(2 * g) * HW + x), c = __ldg(f + (size_t)(2 * g + 1) * HW + x);
-                const float e = expf(c - a);                       // exp(-(a-c))
-                Q[((size_t)(b * G + g) * H + y) * W + x] = 2.0f / (1.0f + e) - 1.0f;
+        float4* __restrict__ dst = Q4 + (size_t)b * J * HW + pix;
+        for (int j = 0; j < J; ++j) {
+            float d[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float a = __ldg(f + (size_t)(8 * j + 2 * k) * HW), c = __ldg(f + (size_t)(8 * j + 2 * k + 1) * HW);
+                d[k] = 2.0f / (1.0f + expf(c - a)) - 1.0f;
             }
+            dst[(size_t)j * HW] = make_float4(d[0], d[1], d[2], d[3]);
+        }
         return;
     }
-    const int ld = G + 1;
-    for (int g = wy; g < G; g += 8) {
-        float d = 0.0f;
-        if (x < W) {
-            const float a = __ldg(f + (size_t)(2 * g) * HW + x), c = __ldg(f + (size_t)(2 * g + 1) * HW + x);
-            d = (c - a) * kLog2e;
+    float4* __restrict__ dst = S4 + ((size_t)(v - 1) * B + b) * J * HW + pix;
+    for (int j = 0; j < J; ++j) {
+        float d[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float a = __ldg(f + (size_t)(8 * j + 2 * k) * HW), c = __ldg(f + (size_t)(8 * j + 2 * k + 1) * HW);
+            d[k] = (c - a) * kLog2e;
         }
-        tile[lane * ld + g] = d;
+        dst[(size_t)j * HW] = make_float4(d[0], d[1], d[2], d[3]);
     }
-    __syncthreads();
-    const int npx = min(32, W - xt * 32);
-    float* __restrict__ dst = S + ((((size_t)(v - 1) * B + b) * H + y) * W + (size_t)xt * 32) * G;
-    for (int k = wy * 32 + lane; k < npx * G; k += 256) dst[k] = tile[(k / G) * ld + (k % G)];
 }
 
 // ------------------------------------------------------------------------------------------------
-// TMA / mbarrier primitives (inline PTX; SASS: UTMALDG, SYNCS)
+// TMA / mbarrier / shared-memory primitives (inline PTX; SASS: UTMALDG, SYNCS, LDS.128)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
 __device__ __forceinline__ void fence_barrier_init()
 {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
 {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
-    const uint32_t addr = smem_u32(bar);
     uint32_t done;
     do {
         asm volatile(
@@ -196,41 +199,47 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t"
             "}"
-            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     } while (!done);
 }
-__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar,
-                                            int c0, int c1, int c2, int c3)
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1, int c2)
 {
     asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
-        " [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
+}
+// ptxas folds `addr + constant` into the immediate offset of LDS.128
+__device__ __forceinline__ float4 lds128(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
 }
 
 // ------------------------------------------------------------------------------------------------
 // staged kernel configuration
-//   G   groups (= channels of the difference map), 32 / 16 / 8 at the three stages
-//   PT  depth planes walked by one thread (accumulators PT*G registers)
-//   TH  tile height in pixels (tile width is one warp = 32 pixels)
-//   PG  plane groups per CTA  -> the CTA's slab is PT*PG planes, blockDim = (32, TH, PG)
-//   BW,BH box (pixels) of the source difference map staged per view
+//   G      groups (channels of the difference map): 32 / 16 / 8 at the three stages
+//   PT     depth planes walked by one thread (accumulators: PT*G registers)
+//   TH     tile height in pixels (tile width is one warp = 32 pixels: 128-byte output rows)
+//   PG     plane groups per CTA -> the CTA's slab is PT*PG planes, blockDim = (32, TH, PG)
+//   BW,BH  box (texels) of one source difference map staged per TMA load: [G/4][BH][BW] float4
 // ------------------------------------------------------------------------------------------------
 template <int G_, int PT_, int TH_, int PG_, int BW_, int BH_, int MINB_>
 struct StagedCfg {
     static constexpr int G = G_, PT = PT_, TH = TH_, PG = PG_, BW = BW_, BH = BH_, MINB = MINB_;
+    static constexpr int J = G / 4;
     static constexpr int THREADS = 32 * TH * PG;
-    static constexpr int PXB = G * 4;                       // bytes per staged pixel
-    static constexpr int BOX_BYTES = BW * BH * PXB;
-    static constexpr int SWZ = (G == 32) ? 7 : (G == 16) ? 3 : 1;   // 128B / 64B / 32B swizzle span
+    static constexpr int PLANE_BYTES = BW * BH * 16;
+    static constexpr int BOX_BYTES = J * PLANE_BYTES;
     static constexpr int SLAB = PT * PG;
-    static constexpr size_t SMEM = BOX_BYTES + 1024 /*align slack*/ + 64;
+    static constexpr size_t SMEM = BOX_BYTES + 128 /*align slack*/ + 64;
+    static_assert(BW * 4 <= 256 && BH <= 256, "TMA box dimensions are limited to 256 elements");
 };
 
 struct StagedArgs {
-    const float* S;       // [V][B][H][W][G]
-    const float* Q;       // [B][G][H][W]
+    const float4* Q4;     // [B][G/4][H][W]
     const float* rt;      // [V][B][12]
     const float* dwp;     // folded depth_weight
     const float* conv_w;  // (G,)
@@ -239,45 +248,19 @@ struct StagedArgs {
     int per_pixel, V, B, D, H, W, tiles_x, tiles_y, slabs;
 };
 
-// sigmoid(a-b) for 4 groups of one sample: 4 x LDS.128 from the swizzled box.
-template <class Cfg>
-__device__ __forceinline__ void taps4(const uint8_t* __restrict__ box, const uint32_t (&A)[4], int j, const Taps& t, float (&p)[4])
-{
-    const float4 nw = *reinterpret_cast<const float4*>(box + (A[0] ^ (uint32_t)(j << 4)));
-    const float4 ne = *reinterpret_cast<const float4*>(box + (A[1] ^ (uint32_t)(j << 4)));
-    const float4 sw = *reinterpret_cast<const float4*>(box + (A[2] ^ (uint32_t)(j << 4)));
-    const float4 se = *reinterpret_cast<const float4*>(box + (A[3] ^ (uint32_t)(j << 4)));
-    p[0] = rcp_approx(1.0f + ex2_approx(blend4(nw.x, ne.x, sw.x, se.x, t)));
-    p[1] = rcp_approx(1.0f + ex2_approx(blend4(nw.y, ne.y, sw.y, se.y, t)));
-    p[2] = rcp_approx(1.0f + ex2_approx(blend4(nw.z, ne.z, sw.z, se.z, t)));
-    p[3] = rcp_approx(1.0f + ex2_approx(blend4(nw.w, ne.w, sw.w, se.w, t)));
-}
-
-// Out-of-box sample: same arithmetic from the global difference map with explicit zero padding.
-template <int G>
-__device__ __noinline__ void taps_global(const float* __restrict__ Sv, int H, int W, const Taps& t, float* __restrict__ p)
-{
-    const bool x0in = (unsigned)t.x0 < (unsigned)W, x1in = (unsigned)(t.x0 + 1) < (unsigned)W;
-    const bool y0in = (unsigned)t.y0 < (unsigned)H, y1in = (unsigned)(t.y0 + 1) < (unsigned)H;
-    const float* base = Sv + ((ptrdiff_t)t.y0 * W + t.x0) * G;
-    for (int g = 0; g < G; ++g) {
-        const float nw = (x0in && y0in) ? __ldg(base + g) : 0.0f;
-        const float ne = (x1in && y0in) ? __ldg(base + G + g) : 0.0f;
-        const float sw = (x0in && y1in) ? __ldg(base + (ptrdiff_t)W * G + g) : 0.0f;
-        const float se = (x1in && y1in) ? __ldg(base + (ptrdiff_t)(W + 1) * G + g) : 0.0f;
-        p[g] = rcp_approx(1.0f + ex2_approx(blend4(nw, ne, sw, se, t)));
-    }
-}
+constexpr int kNone = INT_MAX;
 
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB)
 cost_volume_staged_kernel(const __grid_constant__ CUtensorMap tmap, const StagedArgs a)
 {
-    constexpr int G = Cfg::G, PT = Cfg::PT, TH = Cfg::TH, BW = Cfg::BW, BH = Cfg::BH, PXB = Cfg::PXB;
+    constexpr int G = Cfg::G, J = Cfg::J, PT = Cfg::PT, TH = Cfg::TH, BW = Cfg::BW, BH = Cfg::BH;
+    constexpr int PLANE = Cfg::PLANE_BYTES;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* box = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(box + Cfg::BOX_BYTES);
-    int* org = reinterpret_cast<int*>(box + Cfg::BOX_BYTES + 16);   // [2][2]: (x,y) origin slots
+    const uint32_t box = (smem_u32(smem_raw) + 127u) & ~127u;
+    const uint32_t bar = box + Cfg::BOX_BYTES;
+    // red[slot][0] = min x0, red[slot][1] = min y0 of the samples still to be staged
+    int* red = reinterpret_cast<int*>(smem_raw + (box - smem_u32(smem_raw)) + Cfg::BOX_BYTES + 16);
 
     const int lane = threadIdx.x, ty = threadIdx.y, pg = threadIdx.z;
     const int tid = lane + 32 * (ty + TH * pg);
@@ -293,38 +276,43 @@ cost_volume_staged_kernel(const __grid_constant__ CUtensorMap tmap, const Staged
     const bool pix_ok = (px < W) && (py < H);
     const int d0 = slab * Cfg::SLAB + pg * PT;
     const size_t HW = (size_t)H * W;
-    const GridNorm gn = make_grid_norm(H, W);
+    const GridNormFast gf = make_grid_norm_fast(H, W);
+    const GridNorm& gn = gf.g;
 
     if (tid == 0) {
         mbar_init(bar, 1);
-        org[0] = org[1] = org[2] = org[3] = INT_MAX;
+        red[0] = red[1] = red[2] = red[3] = kNone;
         fence_barrier_init();
     }
 
     // per-thread constants: hypotheses of my planes, cq_g = conv_w[g] * q_g of my pixel
     float depth[PT];
-    bool plane_ok[PT];
+    uint32_t ok_mask = 0;                       // bit i: plane d0+i exists and my pixel is inside the image
 #pragma unroll
     for (int i = 0; i < PT; ++i) {
         const int d = d0 + i;
-        plane_ok[i] = pix_ok && (d < D);
         depth[i] = 0.0f;
-        if (plane_ok[i])
+        if (pix_ok && d < D) {
+            ok_mask |= 1u << i;
             depth[i] = a.per_pixel ? __ldg(a.hypos + ((size_t)b * D + d) * HW + (size_t)py * W + px)
                                    : __ldg(a.hypos + (size_t)b * D + d);
+        }
     }
+    const float4* __restrict__ qp = a.Q4 + (size_t)b * J * HW + (size_t)py * W + px;
     float cq[G];
     float ksum = 0.0f;
-    {
-        const float* qp = a.Q + (size_t)b * G * HW + (size_t)py * W + px;
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
-            cq[g] = pix_ok ? __ldg(a.conv_w + g) * __ldg(qp + (size_t)g * HW) : 0.0f;
-            ksum += cq[g];
-        }
-        ksum *= 0.5f;
+    for (int j = 0; j < J; ++j) {
+        const float4 q = pix_ok ? __ldg(qp + (size_t)j * HW) : make_float4(0.f, 0.f, 0.f, 0.f);
+        cq[4 * j + 0] = __ldg(a.conv_w + 4 * j + 0) * q.x;
+        cq[4 * j + 1] = __ldg(a.conv_w + 4 * j + 1) * q.y;
+        cq[4 * j + 2] = __ldg(a.conv_w + 4 * j + 2) * q.z;
+        cq[4 * j + 3] = __ldg(a.conv_w + 4 * j + 3) * q.w;
+        ksum += (cq[4 * j + 0] + cq[4 * j + 1]) + (cq[4 * j + 2] + cq[4 * j + 3]);
     }
+    ksum *= 0.5f;
     const float alpha = __ldg(a.dwp + 0), betap = __ldg(a.dwp + 1), fcw = __ldg(a.dwp + 2), fcb = __ldg(a.dwp + 3);
+    const float w_void = __ldg(a.dwp + 5);       // view weight of a sample with no tap in bounds (similarity 0.5)
 
     float acc[PT][G];
     float wsum[PT];
@@ -334,10 +322,12 @@ cost_volume_staged_kernel(const __grid_constant__ CUtensorMap tmap, const Staged
 #pragma unroll
         for (int g = 0; g < G; ++g) acc[i][g] = 0.0f;
     }
+    uint64_t n_void = 0;                         // 8 bits per plane: views whose sample fell outside the source image
+    uint32_t iter = 0;                           // CTA-uniform count of staging rounds (mbarrier phase, reduction slot)
     __syncthreads();
 
     for (int v = 0; v < a.V; ++v) {
-        // ---- 1. sample positions of my planes in view v, CTA-wide bounding-box origin ----
+        // ---- 1. sample positions of my planes in view v ----
         float rt[12];
         {
             const float* rp = a.rt + ((size_t)v * a.B + b) * 12;
@@ -346,89 +336,128 @@ cost_volume_staged_kernel(const __grid_constant__ CUtensorMap tmap, const Staged
         }
         const RotXYZ r = rot_xyz(rt, (float)px, (float)py);
         float ix[PT], iy[PT];
-        int mnx = INT_MAX, mny = INT_MAX;
+        uint32_t todo = 0;                       // bit i: sample of plane i still has to be gathered
 #pragma unroll
         for (int i = 0; i < PT; ++i) {
-            sample_position(r, rt, depth[i], gn, ix[i], iy[i]);
-            const bool ok = plane_ok[i] && (ix[i] > -1.0f) && (ix[i] < gn.fw) && (iy[i] > -1.0f) && (iy[i] < gn.fh);
-            if (ok) {
-                mnx = min(mnx, (int)floorf(ix[i]));
-                mny = min(mny, (int)floorf(iy[i]));
-            } else {
-                ix[i] = -2.0f;   // marks "no tap in bounds" for make_taps below
+            sample_position_fast(r, rt, depth[i], gf, ix[i], iy[i]);
+            const bool inside = (ix[i] > -1.0f) && (ix[i] < gn.fw) && (iy[i] > -1.0f) && (iy[i] < gn.fh);
+            if ((ok_mask >> i) & 1u) {
+                if (inside) todo |= 1u << i;
+                else n_void += 1ull << (8 * i);
             }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            mnx = min(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
-            mny = min(mny, __shfl_xor_sync(0xffffffffu, mny, o));
-        }
-        int* slot = org + 2 * (v & 1);
-        if (lane == 0 && mnx != INT_MAX) { atomicMin(slot, mnx); atomicMin(slot + 1, mny); }
-        if (tid == 0) { int* other = org + 2 * ((v + 1) & 1); other[0] = INT_MAX; other[1] = INT_MAX; }
-        __syncthreads();
-        int ox = slot[0], oy = slot[1];
-        if (ox == INT_MAX) { ox = 0; oy = 0; }
 
-        // ---- 2. one TMA tile load of the [BH][BW][G] box (zero filled outside the image) ----
-        if (tid == 0) {
-            mbar_expect_tx(bar, Cfg::BOX_BYTES);
-            tma_load_4d(box, &tmap, bar, 0, ox, oy, v * a.B + b);
-        }
-        mbar_wait(bar, (uint32_t)(v & 1));
-
-        // ---- 3. walk my planes ----
-        const float* Sv = a.S + ((size_t)v * a.B + b) * HW * G;
+        // ---- 2. staging rounds: box origin = min corner of the samples still to do ----
+        bool first = true;
+        while (true) {
+            int* slot = red + 2 * (iter & 1u);
+            // order-preserving integer keys of the (non-negative part of the) positions: floor once, after the min
+            int kx = kNone, ky = kNone;
 #pragma unroll
-        for (int i = 0; i < PT; ++i) {
-            if (!plane_ok[i]) continue;
-            const Taps t = make_taps(ix[i], iy[i], gn);
-            float p[G];
-            if (t.valid) {
-                const int rx = t.x0 - ox, ry = t.y0 - oy;
-                if ((unsigned)rx < (unsigned)(BW - 1) && (unsigned)ry < (unsigned)(BH - 1)) {
-                    const uint32_t o00 = (uint32_t)(ry * BW + rx) * PXB;
-                    uint32_t A[4] = {o00, o00 + PXB, o00 + BW * PXB, o00 + (BW + 1) * PXB};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) A[k] |= ((A[k] >> 7) & Cfg::SWZ) << 4;
-#pragma unroll
-                    for (int j = 0; j < G / 4; ++j) {
-                        float p4[4];
-                        taps4<Cfg>(box, A, j, t, p4);
-                        p[4 * j + 0] = p4[0]; p[4 * j + 1] = p4[1]; p[4 * j + 2] = p4[2]; p[4 * j + 3] = p4[3];
-                    }
-                } else {
-                    taps_global<G>(Sv, H, W, t, p);
+            for (int i = 0; i < PT; ++i)
+                if ((todo >> i) & 1u) {
+                    kx = min(kx, ix[i] < 0.0f ? -1 : __float_as_int(ix[i]));
+                    if (first) ky = min(ky, iy[i] < 0.0f ? -1 : __float_as_int(iy[i]));
                 }
-            } else {
-#pragma unroll
-                for (int g = 0; g < G; ++g) p[g] = 0.5f;   // warped feature = 0 -> softmax = (.5,.5)
+            kx = __reduce_min_sync(0xffffffffu, kx);
+            if (first) ky = __reduce_min_sync(0xffffffffu, ky);
+            if (lane == 0 && kx != kNone) {
+                atomicMin(slot, kx < 0 ? -1 : (int)__int_as_float(kx));
+                if (first) atomicMin(slot + 1, ky < 0 ? -1 : (int)__int_as_float(ky));
             }
-            float z = -ksum;
+            if (tid == 0) { int* other = red + 2 * ((iter + 1u) & 1u); other[0] = kNone; other[1] = kNone; }
+            __syncthreads();
+            const int ox = slot[0];
+            if (ox == kNone) {                   // CTA-uniform: nothing to gather in this view
+                __syncthreads();                 // everybody has read the slot before the next view writes it
+                break;
+            }
+            if (!first) {
+                // later rounds: y origin over the samples whose column fits, so that at least one sample
+                // (the topmost of them) lands inside the box and the loop always makes progress
+                const float xlim = (float)(ox + BW - 1);
+                int m = kNone;
 #pragma unroll
-            for (int g = 0; g < G; ++g) z = fmaf(cq[g], p[g], z);
-            float h = fmaf(z, alpha, betap);              // BatchNorm3d (eval)
-            h = fmaxf(h, 0.0f);                           // ReLU
-            h = fmaf(h, fcw, fcb);                        // Conv3d(1,1,1)
-            const float w = rcp_approx(1.0f + ex2_approx(-kLog2e * h));   // Sigmoid
-            wsum[i] += w;
+                for (int i = 0; i < PT; ++i)
+                    if (((todo >> i) & 1u) && ix[i] < xlim) m = min(m, iy[i] < 0.0f ? -1 : __float_as_int(iy[i]));
+                m = __reduce_min_sync(0xffffffffu, m);
+                if (lane == 0 && m != kNone) atomicMin(slot + 1, m < 0 ? -1 : (int)__int_as_float(m));
+                __syncthreads();
+            }
+            const int oy = slot[1];
+
+            // one TMA tile load of the [G/4][BH][BW] float4 box (zero filled outside the image)
+            if (tid == 0) {
+                mbar_expect_tx(bar, Cfg::BOX_BYTES);
+                tma_load_3d(box, &tmap, bar, ox * 4, oy, (v * a.B + b) * J);
+            }
+            mbar_wait(bar, iter & 1u);
+
+            // ---- 3. gather the samples that landed in the box ----
 #pragma unroll
-            for (int g = 0; g < G; ++g) acc[i][g] = fmaf(w, p[g], acc[i][g]);
+            for (int i = 0; i < PT; ++i) {
+                if (!((todo >> i) & 1u)) continue;
+                float fx0, fy0;
+                int x0, y0;
+                floor_small(ix[i], fx0, x0);
+                floor_small(iy[i], fy0, y0);
+                const int rx = x0 - ox, ry = y0 - oy;
+                if ((unsigned)rx >= (unsigned)(BW - 1) || (unsigned)ry >= (unsigned)(BH - 1)) continue;   // next round
+                todo &= ~(1u << i);
+                const float ax = __fsub_rn(__fadd_rn(fx0, 1.0f), ix[i]), bx = __fsub_rn(ix[i], fx0);
+                const float ay = __fsub_rn(__fadd_rn(fy0, 1.0f), iy[i]), by = __fsub_rn(iy[i], fy0);
+                Taps t;
+                t.wnw = __fmul_rn(ax, ay); t.wne = __fmul_rn(bx, ay); t.wsw = __fmul_rn(ax, by); t.wse = __fmul_rn(bx, by);
+                const uint32_t addr = box + (uint32_t)(ry * BW + rx) * 16u;
+                float p[G];
+                float z = -ksum;
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    const float4 nw = lds128(addr + j * PLANE);                 // constant offsets -> LDS.128 [R + imm]
+                    const float4 ne = lds128(addr + j * PLANE + 16);
+                    const float4 sw = lds128(addr + j * PLANE + BW * 16);
+                    const float4 se = lds128(addr + j * PLANE + BW * 16 + 16);
+                    p[4 * j + 0] = rcp_approx(1.0f + ex2_approx(blend4(nw.x, ne.x, sw.x, se.x, t)));
+                    p[4 * j + 1] = rcp_approx(1.0f + ex2_approx(blend4(nw.y, ne.y, sw.y, se.y, t)));
+                    p[4 * j + 2] = rcp_approx(1.0f + ex2_approx(blend4(nw.z, ne.z, sw.z, se.z, t)));
+                    p[4 * j + 3] = rcp_approx(1.0f + ex2_approx(blend4(nw.w, ne.w, sw.w, se.w, t)));
+                    z = fmaf(cq[4 * j + 0], p[4 * j + 0], z);
+                    z = fmaf(cq[4 * j + 1], p[4 * j + 1], z);
+                    z = fmaf(cq[4 * j + 2], p[4 * j + 2], z);
+                    z = fmaf(cq[4 * j + 3], p[4 * j + 3], z);
+                }
+                float h = fmaf(z, alpha, betap);              // BatchNorm3d (eval)
+                h = fmaxf(h, 0.0f);                           // ReLU
+                h = fmaf(h, fcw, fcb);                        // Conv3d(1,1,1)
+                const float w = rcp_approx(1.0f + ex2_approx(-kLog2e * h));   // Sigmoid
+                wsum[i] += w;
+#pragma unroll
+                for (int g = 0; g < G; ++g) acc[i][g] = fmaf(w, p[g], acc[i][g]);
+            }
+            ++iter;
+            first = false;
+            // the box and the reduction slot are reused: everybody must be done reading; also learn
+            // whether any sample is still waiting for another box
+            if (!__syncthreads_or(todo != 0u)) break;
         }
-        __syncthreads();   // box and origin slot are reused by the next view
     }
 
-    // ---- 4. volume_sum / weight_sum (homoaggregate.py:46), coalesced 128B rows ----
-    const float* qp = a.Q + (size_t)b * G * HW + (size_t)py * W + px;
+    // ---- 4. volume_sum / weight_sum (homoaggregate.py:46), coalesced 128-byte rows ----
 #pragma unroll
     for (int i = 0; i < PT; ++i) {
-        if (!plane_ok[i]) continue;
-        const float rw = __frcp_rn(wsum[i]);
+        if (!((ok_mask >> i) & 1u)) continue;
+        const float nv = (float)((unsigned)(n_void >> (8 * i)) & 255u);
+        const float ws = fmaf(nv, w_void, wsum[i]);
+        const float half_void = 0.5f * nv * w_void;          // void samples: similarity 0.5 in every group
+        const float rw = __frcp_rn(ws);
         float* op = a.out + (((size_t)b * G) * D + (d0 + i)) * HW + (size_t)py * W + px;
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
-            const float q = __ldg(qp + (size_t)g * HW);
-            op[(size_t)g * D * HW] = fmaf(q, fmaf(acc[i][g], rw, -0.5f), 0.5f);
+        for (int j = 0; j < J; ++j) {
+            const float4 q = __ldg(qp + (size_t)j * HW);
+            op[(size_t)(4 * j + 0) * D * HW] = fmaf(q.x, fmaf(acc[i][4 * j + 0] + half_void, rw, -0.5f), 0.5f);
+            op[(size_t)(4 * j + 1) * D * HW] = fmaf(q.y, fmaf(acc[i][4 * j + 1] + half_void, rw, -0.5f), 0.5f);
+            op[(size_t)(4 * j + 2) * D * HW] = fmaf(q.z, fmaf(acc[i][4 * j + 2] + half_void, rw, -0.5f), 0.5f);
+            op[(size_t)(4 * j + 3) * D * HW] = fmaf(q.w, fmaf(acc[i][4 * j + 3] + half_void, rw, -0.5f), 0.5f);
         }
     }
 }
@@ -603,6 +632,28 @@ variance_volume_kernel(const VarArgs a)
 }
 
 // ------------------------------------------------------------------------------------------------
+// diagnostic: the hot kernel's coordinate chain (sample_position_fast), written out for the parity
+// test that pins it bit for bit on the oracle's positions.  Not used by any product path.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+sample_positions_kernel(const float* __restrict__ rt, const float* __restrict__ hypos, int per_pixel, int D, int H, int W,
+                        float* __restrict__ ix_out, float* __restrict__ iy_out)
+{
+    const size_t HW = (size_t)H * W;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)D * HW) return;
+    const int x = (int)(idx % W), y = (int)((idx / W) % H), d = (int)(idx / HW);
+    const GridNormFast gf = make_grid_norm_fast(H, W);
+    float r12[12];
+    for (int k = 0; k < 12; ++k) r12[k] = __ldg(rt + k);
+    const float depth = per_pixel ? __ldg(hypos + idx) : __ldg(hypos + d);
+    float ix, iy;
+    sample_position_fast(rot_xyz(r12, (float)x, (float)y), r12, depth, gf, ix, iy);
+    ix_out[idx] = ix;
+    iy_out[idx] = iy;
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -624,32 +675,36 @@ static EncodeTiledFn get_encode_fn()
 }
 
 template <class Cfg>
-static int launch_staged(const StagedArgs& args, cudaStream_t stream)
+static int launch_staged(const StagedArgs& args, const float* S4, cudaStream_t stream)
 {
     EncodeTiledFn encode = get_encode_fn();
     if (encode == nullptr) return MDF_ERR_UNSUPPORTED;
+    // 3-D view of S4[(v*B+b)*J + j][y][x] (float4 texels): dim0 = 4*W floats, dim1 = H rows, dim2 = planes
     CUtensorMap tmap;
-    const cuuint64_t dims[4] = {(cuuint64_t)Cfg::G, (cuuint64_t)args.W, (cuuint64_t)args.H, (cuuint64_t)args.V * args.B};
-    const cuuint64_t strides[3] = {(cuuint64_t)Cfg::PXB, (cuuint64_t)args.W * Cfg::PXB, (cuuint64_t)args.H * args.W * Cfg::PXB};
-    const cuuint32_t box[4] = {(cuuint32_t)Cfg::G, (cuuint32_t)Cfg::BW, (cuuint32_t)Cfg::BH, 1u};
-    const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
-    const CUtensorMapSwizzle swz = Cfg::G == 32 ? CU_TENSOR_MAP_SWIZZLE_128B
-                                 : Cfg::G == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
-    CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(args.S), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+    const cuuint64_t planes = (cuuint64_t)args.V * args.B * Cfg::J;
+    const cuuint64_t dims[3] = {(cuuint64_t)args.W * 4, (cuuint64_t)args.H, planes};
+    const cuuint64_t strides[2] = {(cuuint64_t)args.W * 16, (cuuint64_t)args.H * args.W * 16};
+    const cuuint32_t box[3] = {(cuuint32_t)Cfg::BW * 4, (cuuint32_t)Cfg::BH, (cuuint32_t)Cfg::J};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(S4), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { g_last_cuda_error = (int)r; return MDF_ERR_CUDA; }
     auto kern = cost_volume_staged_kernel<Cfg>;
     MDF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-    const long long items = (long long)args.tiles_x * args.tiles_y * args.slabs * args.B;
+    StagedArgs a = args;
+    a.tiles_x = (a.W + 31) / 32;
+    a.tiles_y = (a.H + Cfg::TH - 1) / Cfg::TH;
+    a.slabs = (a.D + Cfg::SLAB - 1) / Cfg::SLAB;
+    const long long items = (long long)a.tiles_x * a.tiles_y * a.slabs * a.B;
     if (items <= 0) return MDF_OK;
     if (items > INT_MAX) return MDF_ERR_UNSUPPORTED;
-    kern<<<(unsigned)items, dim3(32, Cfg::TH, Cfg::PG), Cfg::SMEM, stream>>>(tmap, args);
+    kern<<<(unsigned)items, dim3(32, Cfg::TH, Cfg::PG), Cfg::SMEM, stream>>>(tmap, a);
     return launch_status();
 }
 
 //                    G  PT TH PG  BW  BH MINB
-using CfgG32 = StagedCfg<32, 1, 4, 2, 48, 8, 2>;    // 256 thr, box 48 KiB
+using CfgG32 = StagedCfg<32, 1, 4, 2, 40, 8, 2>;    // 256 thr, box 40 KiB, slab 2 planes
 using CfgG16 = StagedCfg<16, 4, 4, 2, 48, 8, 2>;    // 256 thr, box 24 KiB, slab 8 planes
 using CfgG8  = StagedCfg<8, 8, 8, 1, 48, 12, 2>;    // 256 thr, box 18 KiB, slab 8 planes
 
@@ -750,31 +805,25 @@ int mdf_cost_volume_fwd_ex(const float* const* features, int N, const float* ref
         return launch_status();
     }
 
-    float* Q = reinterpret_cast<float*>(wsb + ws.q_off);
-    float* S = reinterpret_cast<float*>(wsb + ws.s_off);
+    float4* Q4 = reinterpret_cast<float4*>(wsb + ws.q_off);
+    float4* S4 = reinterpret_cast<float4*>(wsb + ws.s_off);
     {
         FeaPtrs fp;
         for (int i = 0; i < MDF_MAX_VIEWS; ++i) fp.p[i] = i < N ? features[i] : nullptr;
-        const int xtiles = (W + 31) / 32;
-        const long long blocks = (long long)N * B * H * xtiles;
-        if (blocks > INT_MAX) return MDF_ERR_UNSUPPORTED;
-        prep_kernel<<<(unsigned)blocks, dim3(32, 8), 32 * (G + 1) * sizeof(float), stream>>>(fp, B, G, H, W, xtiles, Q, S);
+        const long long HW = (long long)H * W;
+        if (HW > INT_MAX - 256 || (long long)N * B > 65535) return MDF_ERR_UNSUPPORTED;
+        prep_kernel<<<dim3((unsigned)((HW + 255) / 256), (unsigned)(N * B)), 256, 0, stream>>>(fp, B, G, (int)HW, Q4, S4);
         st = launch_status();
         if (st != MDF_OK) return st;
     }
     StagedArgs a;
-    a.S = S; a.Q = Q; a.rt = rt; a.dwp = dwp; a.conv_w = conv_weight; a.hypos = depth_hypos; a.out = cost_volume;
+    a.Q4 = Q4; a.rt = rt; a.dwp = dwp; a.conv_w = conv_weight; a.hypos = depth_hypos; a.out = cost_volume;
     a.per_pixel = hypos_per_pixel; a.V = V; a.B = B; a.D = D; a.H = H; a.W = W;
-    a.tiles_x = (W + 31) / 32;
-    if (G == 32) {
-        a.tiles_y = (H + CfgG32::TH - 1) / CfgG32::TH; a.slabs = (D + CfgG32::SLAB - 1) / CfgG32::SLAB;
-        return launch_staged<CfgG32>(a, stream);
-    } else if (G == 16) {
-        a.tiles_y = (H + CfgG16::TH - 1) / CfgG16::TH; a.slabs = (D + CfgG16::SLAB - 1) / CfgG16::SLAB;
-        return launch_staged<CfgG16>(a, stream);
-    }
-    a.tiles_y = (H + CfgG8::TH - 1) / CfgG8::TH; a.slabs = (D + CfgG8::SLAB - 1) / CfgG8::SLAB;
-    return launch_staged<CfgG8>(a, stream);
+    a.tiles_x = a.tiles_y = a.slabs = 0;
+    const float* S = reinterpret_cast<const float*>(S4);
+    if (G == 32) return launch_staged<CfgG32>(a, S, stream);
+    if (G == 16) return launch_staged<CfgG16>(a, S, stream);
+    return launch_staged<CfgG8>(a, S, stream);
 }
 
 int mdf_cost_volume_fwd(const float* const* features, int N, const float* ref_proj, const float* const* src_projs,
@@ -786,6 +835,24 @@ int mdf_cost_volume_fwd(const float* const* features, int N, const float* ref_pr
     return mdf_cost_volume_fwd_ex(features, N, ref_proj, src_projs, depth_hypos, hypos_per_pixel, conv_weight, bn_weight,
                                   bn_bias, bn_mean, bn_var, bn_eps, fc_weight, fc_bias, B, C, G, D, H, W, cost_volume,
                                   workspace, workspace_bytes, 0, stream);
+}
+
+int mdf_debug_sample_positions(const float* rot_trans, const float* depth_hypos, int hypos_per_pixel, int D, int H, int W,
+                               float* ix, float* iy, mdf_stream_t stream)
+{
+    if (D < 0 || H < 0 || W < 0) return MDF_ERR_INVALID_SHAPE;
+    const size_t total = (size_t)D * H * W;
+    if (total == 0) return MDF_OK;
+    if (!rot_trans || !depth_hypos || !ix || !iy) return MDF_ERR_NULL_POINTER;
+    const int dev = device_of(ix);
+    if (dev < 0) return dev;
+    const void* ptrs[] = {rot_trans, depth_hypos, iy};
+    const int st = check_on_device(dev, ptrs, 3);
+    if (st != MDF_OK) return st;
+    DeviceGuard guard(dev);
+    sample_positions_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rot_trans, depth_hypos,
+                                                                                              hypos_per_pixel, D, H, W, ix, iy);
+    return launch_status();
 }
 
 size_t mdf_homo_warp_workspace_bytes(int B)

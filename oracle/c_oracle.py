@@ -102,6 +102,19 @@ def homo_warp(src_fea, depth_hypos, rot_trans=None, src_proj=None, ref_proj=None
     return out
 
 
+def sample_positions(rot_trans, depth_hypos, H, W, prec="f32"):
+    """(ix, iy), each (D,H,W): where grid_sample reads for every reference pixel and hypothesis of ONE
+    batch item (base.py:102-119 + ATen unnormalize).  rot_trans: 12 numbers; depth_hypos (D,) or (D,H,W)."""
+    rt = _arr(rot_trans, prec).reshape(12)
+    h = _arr(depth_hypos, prec)
+    D = h.shape[0]
+    per_pixel = 1 if h.ndim == 3 else 0
+    ix = np.empty((D, H, W), _dt(prec)); iy = np.empty((D, H, W), _dt(prec))
+    fn = getattr(_lib(prec), f"mdf_oracle_sample_positions_{prec}")
+    _check(fn(_ptr(rt), _ptr(h), per_pixel, D, H, W, _ptr(ix), _ptr(iy)), "sample_positions")
+    return ix, iy
+
+
 def _rot_trans_list(ref_proj, src_projs, rot_trans, prec):
     if rot_trans is not None:
         return [_arr(r, prec) for r in rot_trans]

@@ -153,6 +153,10 @@ static inline sample_pos_t sample_position(const REAL *rt, int x, int y, REAL de
     return s;
 }
 
+/* positions of every (d,y,x) for one projection; pins the CUDA coordinate chain bit for bit */
+int SYM(mdf_oracle_sample_positions)(const REAL *rot_trans, const REAL *hypos, int per_pixel, int D, int H, int W,
+                                     REAL *ix, REAL *iy);
+
 /* 4 bilinear taps, zero padding.  Returns 0 when no tap can be in bounds. */
 typedef struct { int x0, y0; REAL wnw, wne, wsw, wse; int m_nw, m_ne, m_sw, m_se; } taps_t;
 
@@ -211,6 +215,19 @@ int SYM(mdf_oracle_homo_warp)(const REAL *src_fea, const REAL *rot_trans, const 
                     }
                 }
     }
+    return MDF_OK;
+}
+
+int SYM(mdf_oracle_sample_positions)(const REAL *rot_trans, const REAL *hypos, int per_pixel, int D, int H, int W,
+                                     REAL *ix, REAL *iy)
+{
+    for (int d = 0; d < D; ++d)
+        for (int y = 0; y < H; ++y)
+            for (int x = 0; x < W; ++x) {
+                size_t i = ((size_t)d * H + y) * W + x;
+                sample_pos_t s = sample_position(rot_trans, x, y, per_pixel ? hypos[i] : hypos[d], H, W);
+                ix[i] = s.ix; iy[i] = s.iy;
+            }
     return MDF_OK;
 }
 
