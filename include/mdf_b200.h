@@ -95,7 +95,8 @@ MDF_API int mdf_cost_volume_fwd(const float *const *features,   /* HOST array of
                         mdf_stream_t stream);
 
 /* Same op, algorithm selection for tests/benchmarks: 0 = auto, 1 = staged (TMA box) kernel,
- * 2 = direct kernel (any C/G, taps straight from the NCHW features). */
+ * 2 = direct kernel (any C/G, taps straight from the NCHW features), 16 + k = staged kernel, tuning
+ * variant k (tile / slab / box shapes; MDF_ERR_UNSUPPORTED when k does not exist). */
 MDF_API int mdf_cost_volume_fwd_ex(const float *const *features, int N, const float *ref_proj,
                            const float *const *src_projs, const float *depth_hypos, int hypos_per_pixel,
                            const float *conv_weight, const float *bn_weight, const float *bn_bias,

@@ -9,21 +9,7 @@
 //   setup_kernel            per call: proj = src_proj @ inverse(ref_proj) for every (view, batch) in
 //                           float64 (no host sync, unlike torch.inverse at base.py:98) and the folded
 //                           eval-mode BatchNorm of depth_weight.
-//   prep_kernel             (C/G == 2) source features NCHW -> "pair difference" maps in planar-float4
-//                           layout S4[v][b][j][y][x] = (f[2g+1]-f[2g])*log2(e) for g = 4j..4j+3, reference
-//                           -> q = tanh((r0-r1)/2).  softmax([a,b]) = [sigmoid(a-b), 1-sigmoid(a-b)] and
-//                           bilinear sampling is linear, so gathering the difference map is the same
-//                           computation with half the taps and one exp per group.
-//   cost_volume_staged      the hot kernel: a CTA owns a tile of reference pixels x a slab of depth
-//                           planes; for each source view it finds the bounding box of its samples,
-//                           pulls that [G/4][BH][BW] float4 box of S4 into shared memory with ONE TMA
-//                           tile load (hardware zero fill = grid_sample's zero padding; neighbouring
-//                           lanes read neighbouring 16-byte texels = conflict-free LDS.128 with
-//                           immediate offsets), then every thread walks its planes:
-//                           4 x LDS.128 per 4 groups -> blend -> sigmoid -> similarity -> view weight.
-//                           Samples outside the box (rough depth maps) are served by further staging
-//                           rounds; there is no slow global-memory path.
-//                           Output stores are 128-byte coalesced rows of the (B,G,D,H,W) volume.
+//   prep_kernel, cost_volume_staged   the hot path for C/G == 2: see mdf_staged.cuh
 //   cost_volume_direct      any C/G: taps straight from the NCHW features (no staging), two passes.
 //   homo_warp / variance    the standalone warp and the (unused by config.py) variance aggregate.
 #include <cuda.h>
@@ -33,6 +19,7 @@
 
 #include "mdf_common.cuh"
 #include "mdf_host.cuh"
+#include "mdf_staged.cuh"
 
 namespace mdf {
 
@@ -65,7 +52,6 @@ static Workspace make_workspace(int B, int N, int G, int H, int W, bool staged)
 }
 
 struct SrcPtrs { const float* p[kMaxSrcViews]; };
-struct FeaPtrs { const float* p[MDF_MAX_VIEWS]; };
 
 // ------------------------------------------------------------------------------------------------
 // setup: projections + folded depth_weight parameters
@@ -125,340 +111,10 @@ __global__ void setup_kernel(SrcPtrs src_projs, const float* __restrict__ ref_pr
         dwp[2] = fc_w[0];
         dwp[3] = fc_b[0];
         dwp[4] = beta;
+        for (int g = 0; g < G && g < 32; ++g) dwp[16 + g] = conv_w[g];   // 16-byte aligned copy for float4 loads
         // weight of a (sample, view) pair whose taps all fall outside the source image: every similarity is 0.5
         const float hv = fmaf(fmaxf(dwp[1], 0.0f), fc_w[0], fc_b[0]);
         dwp[5] = 1.0f / (1.0f + expf(-hv));
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// prep (C/G == 2): one thread per pixel of one view; blockIdx.y = view * B + b.
-//   "planar float4" layout: plane j holds groups 4j..4j+3 of every pixel as one float4
-//   view 0 (reference):  Q4[b][j][y][x]      = 2*sigmoid(r[2g]-r[2g+1]) - 1,  g = 4j..4j+3
-//   view v>0:            S4[v-1][b][j][y][x] = (f[2g+1]-f[2g]) * log2(e)
-// Loads are 128-byte coalesced rows of the NCHW planes, stores are 512-byte coalesced float4 rows.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-prep_kernel(FeaPtrs feas, int B, int G, int HW, float4* __restrict__ Q4, float4* __restrict__ S4)
-{
-    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pix >= HW) return;
-    const int v = blockIdx.y / B, b = blockIdx.y % B;
-    const float* __restrict__ f = feas.p[v] + (size_t)b * 2 * G * HW + pix;
-    const int J = G / 4;
-    if (v == 0) {
-        float4* __restrict__ dst = Q4 + (size_t)b * J * HW + pix;
-        for (int j = 0; j < J; ++j) {
-            float d[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float a = __ldg(f + (size_t)(8 * j + 2 * k) * HW), c = __ldg(f + (size_t)(8 * j + 2 * k + 1) * HW);
-                d[k] = 2.0f / (1.0f + expf(c - a)) - 1.0f;
-            }
-            dst[(size_t)j * HW] = make_float4(d[0], d[1], d[2], d[3]);
-        }
-        return;
-    }
-    float4* __restrict__ dst = S4 + ((size_t)(v - 1) * B + b) * J * HW + pix;
-    for (int j = 0; j < J; ++j) {
-        float d[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float a = __ldg(f + (size_t)(8 * j + 2 * k) * HW), c = __ldg(f + (size_t)(8 * j + 2 * k + 1) * HW);
-            d[k] = (c - a) * kLog2e;
-        }
-        dst[(size_t)j * HW] = make_float4(d[0], d[1], d[2], d[3]);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// TMA / mbarrier / shared-memory primitives (inline PTX; SASS: UTMALDG, SYNCS, LDS.128)
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void fence_barrier_init()
-{
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}"
-            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1, int c2)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
-        " [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-// ptxas folds `addr + constant` into the immediate offset of LDS.128
-__device__ __forceinline__ float4 lds128(uint32_t addr)
-{
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
-
-// ------------------------------------------------------------------------------------------------
-// staged kernel configuration
-//   G      groups (channels of the difference map): 32 / 16 / 8 at the three stages
-//   PT     depth planes walked by one thread (accumulators: PT*G registers)
-//   TH     tile height in pixels (tile width is one warp = 32 pixels: 128-byte output rows)
-//   PG     plane groups per CTA -> the CTA's slab is PT*PG planes, blockDim = (32, TH, PG)
-//   BW,BH  box (texels) of one source difference map staged per TMA load: [G/4][BH][BW] float4
-// ------------------------------------------------------------------------------------------------
-template <int G_, int PT_, int TH_, int PG_, int BW_, int BH_, int MINB_>
-struct StagedCfg {
-    static constexpr int G = G_, PT = PT_, TH = TH_, PG = PG_, BW = BW_, BH = BH_, MINB = MINB_;
-    static constexpr int J = G / 4;
-    static constexpr int THREADS = 32 * TH * PG;
-    static constexpr int PLANE_BYTES = BW * BH * 16;
-    static constexpr int BOX_BYTES = J * PLANE_BYTES;
-    static constexpr int SLAB = PT * PG;
-    static constexpr size_t SMEM = BOX_BYTES + 128 /*align slack*/ + 64;
-    static_assert(BW * 4 <= 256 && BH <= 256, "TMA box dimensions are limited to 256 elements");
-};
-
-struct StagedArgs {
-    const float4* Q4;     // [B][G/4][H][W]
-    const float* rt;      // [V][B][12]
-    const float* dwp;     // folded depth_weight
-    const float* conv_w;  // (G,)
-    const float* hypos;
-    float* out;           // (B,G,D,H,W)
-    int per_pixel, V, B, D, H, W, tiles_x, tiles_y, slabs;
-};
-
-constexpr int kNone = INT_MAX;
-
-template <class Cfg>
-__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB)
-cost_volume_staged_kernel(const __grid_constant__ CUtensorMap tmap, const StagedArgs a)
-{
-    constexpr int G = Cfg::G, J = Cfg::J, PT = Cfg::PT, TH = Cfg::TH, BW = Cfg::BW, BH = Cfg::BH;
-    constexpr int PLANE = Cfg::PLANE_BYTES;
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t box = (smem_u32(smem_raw) + 127u) & ~127u;
-    const uint32_t bar = box + Cfg::BOX_BYTES;
-    // red[slot][0] = min x0, red[slot][1] = min y0 of the samples still to be staged
-    int* red = reinterpret_cast<int*>(smem_raw + (box - smem_u32(smem_raw)) + Cfg::BOX_BYTES + 16);
-
-    const int lane = threadIdx.x, ty = threadIdx.y, pg = threadIdx.z;
-    const int tid = lane + 32 * (ty + TH * pg);
-
-    int it = blockIdx.x;
-    const int tile_x = it % a.tiles_x; it /= a.tiles_x;
-    const int tile_y = it % a.tiles_y; it /= a.tiles_y;
-    const int slab = it % a.slabs;
-    const int b = it / a.slabs;
-
-    const int H = a.H, W = a.W, D = a.D;
-    const int px = tile_x * 32 + lane, py = tile_y * TH + ty;
-    const bool pix_ok = (px < W) && (py < H);
-    const int d0 = slab * Cfg::SLAB + pg * PT;
-    const size_t HW = (size_t)H * W;
-    const GridNormFast gf = make_grid_norm_fast(H, W);
-    const GridNorm& gn = gf.g;
-
-    if (tid == 0) {
-        mbar_init(bar, 1);
-        red[0] = red[1] = red[2] = red[3] = kNone;
-        fence_barrier_init();
-    }
-
-    // per-thread constants: hypotheses of my planes, cq_g = conv_w[g] * q_g of my pixel
-    float depth[PT];
-    uint32_t ok_mask = 0;                       // bit i: plane d0+i exists and my pixel is inside the image
-#pragma unroll
-    for (int i = 0; i < PT; ++i) {
-        const int d = d0 + i;
-        depth[i] = 0.0f;
-        if (pix_ok && d < D) {
-            ok_mask |= 1u << i;
-            depth[i] = a.per_pixel ? __ldg(a.hypos + ((size_t)b * D + d) * HW + (size_t)py * W + px)
-                                   : __ldg(a.hypos + (size_t)b * D + d);
-        }
-    }
-    const float4* __restrict__ qp = a.Q4 + (size_t)b * J * HW + (size_t)py * W + px;
-    float cq[G];
-    float ksum = 0.0f;
-#pragma unroll
-    for (int j = 0; j < J; ++j) {
-        const float4 q = pix_ok ? __ldg(qp + (size_t)j * HW) : make_float4(0.f, 0.f, 0.f, 0.f);
-        cq[4 * j + 0] = __ldg(a.conv_w + 4 * j + 0) * q.x;
-        cq[4 * j + 1] = __ldg(a.conv_w + 4 * j + 1) * q.y;
-        cq[4 * j + 2] = __ldg(a.conv_w + 4 * j + 2) * q.z;
-        cq[4 * j + 3] = __ldg(a.conv_w + 4 * j + 3) * q.w;
-        ksum += (cq[4 * j + 0] + cq[4 * j + 1]) + (cq[4 * j + 2] + cq[4 * j + 3]);
-    }
-    ksum *= 0.5f;
-    const float alpha = __ldg(a.dwp + 0), betap = __ldg(a.dwp + 1), fcw = __ldg(a.dwp + 2), fcb = __ldg(a.dwp + 3);
-    const float w_void = __ldg(a.dwp + 5);       // view weight of a sample with no tap in bounds (similarity 0.5)
-
-    float acc[PT][G];
-    float wsum[PT];
-#pragma unroll
-    for (int i = 0; i < PT; ++i) {
-        wsum[i] = 0.0f;
-#pragma unroll
-        for (int g = 0; g < G; ++g) acc[i][g] = 0.0f;
-    }
-    uint64_t n_void = 0;                         // 8 bits per plane: views whose sample fell outside the source image
-    uint32_t iter = 0;                           // CTA-uniform count of staging rounds (mbarrier phase, reduction slot)
-    __syncthreads();
-
-    for (int v = 0; v < a.V; ++v) {
-        // ---- 1. sample positions of my planes in view v ----
-        float rt[12];
-        {
-            const float* rp = a.rt + ((size_t)v * a.B + b) * 12;
-#pragma unroll
-            for (int k = 0; k < 12; ++k) rt[k] = __ldg(rp + k);
-        }
-        const RotXYZ r = rot_xyz(rt, (float)px, (float)py);
-        float ix[PT], iy[PT];
-        uint32_t todo = 0;                       // bit i: sample of plane i still has to be gathered
-#pragma unroll
-        for (int i = 0; i < PT; ++i) {
-            sample_position_fast(r, rt, depth[i], gf, ix[i], iy[i]);
-            const bool inside = (ix[i] > -1.0f) && (ix[i] < gn.fw) && (iy[i] > -1.0f) && (iy[i] < gn.fh);
-            if ((ok_mask >> i) & 1u) {
-                if (inside) todo |= 1u << i;
-                else n_void += 1ull << (8 * i);
-            }
-        }
-
-        // ---- 2. staging rounds: box origin = min corner of the samples still to do ----
-        bool first = true;
-        while (true) {
-            int* slot = red + 2 * (iter & 1u);
-            // order-preserving integer keys of the (non-negative part of the) positions: floor once, after the min
-            int kx = kNone, ky = kNone;
-#pragma unroll
-            for (int i = 0; i < PT; ++i)
-                if ((todo >> i) & 1u) {
-                    kx = min(kx, ix[i] < 0.0f ? -1 : __float_as_int(ix[i]));
-                    if (first) ky = min(ky, iy[i] < 0.0f ? -1 : __float_as_int(iy[i]));
-                }
-            kx = __reduce_min_sync(0xffffffffu, kx);
-            if (first) ky = __reduce_min_sync(0xffffffffu, ky);
-            if (lane == 0 && kx != kNone) {
-                atomicMin(slot, kx < 0 ? -1 : (int)__int_as_float(kx));
-                if (first) atomicMin(slot + 1, ky < 0 ? -1 : (int)__int_as_float(ky));
-            }
-            if (tid == 0) { int* other = red + 2 * ((iter + 1u) & 1u); other[0] = kNone; other[1] = kNone; }
-            __syncthreads();
-            const int ox = slot[0];
-            if (ox == kNone) {                   // CTA-uniform: nothing to gather in this view
-                __syncthreads();                 // everybody has read the slot before the next view writes it
-                break;
-            }
-            if (!first) {
-                // later rounds: y origin over the samples whose column fits, so that at least one sample
-                // (the topmost of them) lands inside the box and the loop always makes progress
-                const float xlim = (float)(ox + BW - 1);
-                int m = kNone;
-#pragma unroll
-                for (int i = 0; i < PT; ++i)
-                    if (((todo >> i) & 1u) && ix[i] < xlim) m = min(m, iy[i] < 0.0f ? -1 : __float_as_int(iy[i]));
-                m = __reduce_min_sync(0xffffffffu, m);
-                if (lane == 0 && m != kNone) atomicMin(slot + 1, m < 0 ? -1 : (int)__int_as_float(m));
-                __syncthreads();
-            }
-            const int oy = slot[1];
-
-            // one TMA tile load of the [G/4][BH][BW] float4 box (zero filled outside the image)
-            if (tid == 0) {
-                mbar_expect_tx(bar, Cfg::BOX_BYTES);
-                tma_load_3d(box, &tmap, bar, ox * 4, oy, (v * a.B + b) * J);
-            }
-            mbar_wait(bar, iter & 1u);
-
-            // ---- 3. gather the samples that landed in the box ----
-#pragma unroll
-            for (int i = 0; i < PT; ++i) {
-                if (!((todo >> i) & 1u)) continue;
-                float fx0, fy0;
-                int x0, y0;
-                floor_small(ix[i], fx0, x0);
-                floor_small(iy[i], fy0, y0);
-                const int rx = x0 - ox, ry = y0 - oy;
-                if ((unsigned)rx >= (unsigned)(BW - 1) || (unsigned)ry >= (unsigned)(BH - 1)) continue;   // next round
-                todo &= ~(1u << i);
-                const float ax = __fsub_rn(__fadd_rn(fx0, 1.0f), ix[i]), bx = __fsub_rn(ix[i], fx0);
-                const float ay = __fsub_rn(__fadd_rn(fy0, 1.0f), iy[i]), by = __fsub_rn(iy[i], fy0);
-                Taps t;
-                t.wnw = __fmul_rn(ax, ay); t.wne = __fmul_rn(bx, ay); t.wsw = __fmul_rn(ax, by); t.wse = __fmul_rn(bx, by);
-                const uint32_t addr = box + (uint32_t)(ry * BW + rx) * 16u;
-                float p[G];
-                float z = -ksum;
-#pragma unroll
-                for (int j = 0; j < J; ++j) {
-                    const float4 nw = lds128(addr + j * PLANE);                 // constant offsets -> LDS.128 [R + imm]
-                    const float4 ne = lds128(addr + j * PLANE + 16);
-                    const float4 sw = lds128(addr + j * PLANE + BW * 16);
-                    const float4 se = lds128(addr + j * PLANE + BW * 16 + 16);
-                    p[4 * j + 0] = rcp_approx(1.0f + ex2_approx(blend4(nw.x, ne.x, sw.x, se.x, t)));
-                    p[4 * j + 1] = rcp_approx(1.0f + ex2_approx(blend4(nw.y, ne.y, sw.y, se.y, t)));
-                    p[4 * j + 2] = rcp_approx(1.0f + ex2_approx(blend4(nw.z, ne.z, sw.z, se.z, t)));
-                    p[4 * j + 3] = rcp_approx(1.0f + ex2_approx(blend4(nw.w, ne.w, sw.w, se.w, t)));
-                    z = fmaf(cq[4 * j + 0], p[4 * j + 0], z);
-                    z = fmaf(cq[4 * j + 1], p[4 * j + 1], z);
-                    z = fmaf(cq[4 * j + 2], p[4 * j + 2], z);
-                    z = fmaf(cq[4 * j + 3], p[4 * j + 3], z);
-                }
-                float h = fmaf(z, alpha, betap);              // BatchNorm3d (eval)
-                h = fmaxf(h, 0.0f);                           // ReLU
-                h = fmaf(h, fcw, fcb);                        // Conv3d(1,1,1)
-                const float w = rcp_approx(1.0f + ex2_approx(-kLog2e * h));   // Sigmoid
-                wsum[i] += w;
-#pragma unroll
-                for (int g = 0; g < G; ++g) acc[i][g] = fmaf(w, p[g], acc[i][g]);
-            }
-            ++iter;
-            first = false;
-            // the box and the reduction slot are reused: everybody must be done reading; also learn
-            // whether any sample is still waiting for another box
-            if (!__syncthreads_or(todo != 0u)) break;
-        }
-    }
-
-    // ---- 4. volume_sum / weight_sum (homoaggregate.py:46), coalesced 128-byte rows ----
-#pragma unroll
-    for (int i = 0; i < PT; ++i) {
-        if (!((ok_mask >> i) & 1u)) continue;
-        const float nv = (float)((unsigned)(n_void >> (8 * i)) & 255u);
-        const float ws = fmaf(nv, w_void, wsum[i]);
-        const float half_void = 0.5f * nv * w_void;          // void samples: similarity 0.5 in every group
-        const float rw = __frcp_rn(ws);
-        float* op = a.out + (((size_t)b * G) * D + (d0 + i)) * HW + (size_t)py * W + px;
-#pragma unroll
-        for (int j = 0; j < J; ++j) {
-            const float4 q = __ldg(qp + (size_t)j * HW);
-            op[(size_t)(4 * j + 0) * D * HW] = fmaf(q.x, fmaf(acc[i][4 * j + 0] + half_void, rw, -0.5f), 0.5f);
-            op[(size_t)(4 * j + 1) * D * HW] = fmaf(q.y, fmaf(acc[i][4 * j + 1] + half_void, rw, -0.5f), 0.5f);
-            op[(size_t)(4 * j + 2) * D * HW] = fmaf(q.z, fmaf(acc[i][4 * j + 2] + half_void, rw, -0.5f), 0.5f);
-            op[(size_t)(4 * j + 3) * D * HW] = fmaf(q.w, fmaf(acc[i][4 * j + 3] + half_void, rw, -0.5f), 0.5f);
-        }
     }
 }
 
@@ -656,58 +312,6 @@ sample_positions_kernel(const float* __restrict__ rt, const float* __restrict__ 
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn()
-{
-    // resolved through the runtime: the library does not link libcuda
-    static EncodeTiledFn fn = []() -> EncodeTiledFn {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-            q != cudaDriverEntryPointSuccess)
-            return nullptr;
-        return reinterpret_cast<EncodeTiledFn>(p);
-    }();
-    return fn;
-}
-
-template <class Cfg>
-static int launch_staged(const StagedArgs& args, const float* S4, cudaStream_t stream)
-{
-    EncodeTiledFn encode = get_encode_fn();
-    if (encode == nullptr) return MDF_ERR_UNSUPPORTED;
-    // 3-D view of S4[(v*B+b)*J + j][y][x] (float4 texels): dim0 = 4*W floats, dim1 = H rows, dim2 = planes
-    CUtensorMap tmap;
-    const cuuint64_t planes = (cuuint64_t)args.V * args.B * Cfg::J;
-    const cuuint64_t dims[3] = {(cuuint64_t)args.W * 4, (cuuint64_t)args.H, planes};
-    const cuuint64_t strides[2] = {(cuuint64_t)args.W * 16, (cuuint64_t)args.H * args.W * 16};
-    const cuuint32_t box[3] = {(cuuint32_t)Cfg::BW * 4, (cuuint32_t)Cfg::BH, (cuuint32_t)Cfg::J};
-    const cuuint32_t estr[3] = {1u, 1u, 1u};
-    CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(S4), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { g_last_cuda_error = (int)r; return MDF_ERR_CUDA; }
-    auto kern = cost_volume_staged_kernel<Cfg>;
-    MDF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-    StagedArgs a = args;
-    a.tiles_x = (a.W + 31) / 32;
-    a.tiles_y = (a.H + Cfg::TH - 1) / Cfg::TH;
-    a.slabs = (a.D + Cfg::SLAB - 1) / Cfg::SLAB;
-    const long long items = (long long)a.tiles_x * a.tiles_y * a.slabs * a.B;
-    if (items <= 0) return MDF_OK;
-    if (items > INT_MAX) return MDF_ERR_UNSUPPORTED;
-    kern<<<(unsigned)items, dim3(32, Cfg::TH, Cfg::PG), Cfg::SMEM, stream>>>(tmap, a);
-    return launch_status();
-}
-
-//                    G  PT TH PG  BW  BH MINB
-using CfgG32 = StagedCfg<32, 1, 4, 2, 40, 8, 2>;    // 256 thr, box 40 KiB, slab 2 planes
-using CfgG16 = StagedCfg<16, 4, 4, 2, 48, 8, 2>;    // 256 thr, box 24 KiB, slab 8 planes
-using CfgG8  = StagedCfg<8, 8, 8, 1, 48, 12, 2>;    // 256 thr, box 18 KiB, slab 8 planes
-
 static int run_setup(const float* const* src_projs, const float* ref_proj, int V, int B, float* rt,
                      const float* conv_w, const float* bn_w, const float* bn_b, const float* bn_mean,
                      const float* bn_var, float bn_eps, const float* fc_w, const float* fc_b, int G, float* dwp,
@@ -770,7 +374,8 @@ int mdf_cost_volume_fwd_ex(const float* const* features, int N, const float* ref
         return MDF_ERR_NULL_POINTER;
     const int V = N - 1;
     const bool staged = staged_supported(C, G) && algo != 2;
-    if (algo == 1 && !staged) return MDF_ERR_UNSUPPORTED;
+    if ((algo == 1 || algo >= 16) && !staged) return MDF_ERR_UNSUPPORTED;
+    if (algo < 0 || (algo > 2 && algo < 16)) return MDF_ERR_UNSUPPORTED;
     const Workspace ws = make_workspace(B, N, G, H, W, staged);
     if (!workspace || ((uintptr_t)workspace & 255) != 0 || workspace_bytes < ws.total) return MDF_ERR_WORKSPACE;
 
@@ -817,13 +422,12 @@ int mdf_cost_volume_fwd_ex(const float* const* features, int N, const float* ref
         if (st != MDF_OK) return st;
     }
     StagedArgs a;
-    a.Q4 = Q4; a.rt = rt; a.dwp = dwp; a.conv_w = conv_weight; a.hypos = depth_hypos; a.out = cost_volume;
+    a.Q4 = Q4; a.rt = rt; a.dwp = dwp; a.conv_w = dwp + 16; a.hypos = depth_hypos; a.out = cost_volume;
     a.per_pixel = hypos_per_pixel; a.V = V; a.B = B; a.D = D; a.H = H; a.W = W;
+    a.gn = make_grid_norm(H, W);
     a.tiles_x = a.tiles_y = a.slabs = 0;
     const float* S = reinterpret_cast<const float*>(S4);
-    if (G == 32) return launch_staged<CfgG32>(a, S, stream);
-    if (G == 16) return launch_staged<CfgG16>(a, S, stream);
-    return launch_staged<CfgG8>(a, S, stream);
+    return launch_staged_variant(G, algo >= 16 ? algo - 16 : 0, a, S, stream);
 }
 
 int mdf_cost_volume_fwd(const float* const* features, int N, const float* ref_proj, const float* const* src_projs,

@@ -1,0 +1,528 @@
+// mdf_staged.cuh -- the hot kernel of the plane-sweep cost volume (C/G == 2) and its layout pass.
+//
+//   prep_kernel             source features NCHW -> "pair difference" maps in planar-float4 layout
+//                           S4[v][b][j][y][x] = (f[2g+1]-f[2g])*log2(e) for g = 4j..4j+3, and the reference
+//                           view -> q = 2*sigmoid(r[2g]-r[2g+1]) - 1.  softmax([a,b]) = [sigmoid(a-b),
+//                           1-sigmoid(a-b)] and bilinear sampling is linear, so gathering the difference
+//                           map is the reference's computation with half the taps and one exp per group:
+//                               similarity_g = 0.5 + q_g * (sigmoid(warp(S)_g) - 0.5)
+//   cost_volume_staged      a CTA owns a tile of reference pixels x a slab of depth planes.  For each
+//                           source view it finds the bounding box of its samples, pulls that
+//                           [G/4][BH][BW] float4 box of S4 into shared memory with ONE TMA tile load
+//                           (hardware zero fill = grid_sample's zero padding; neighbouring lanes read
+//                           neighbouring 16-byte texels = conflict-free LDS.128 with immediate offsets),
+//                           then every thread walks its planes: 4 x LDS.128 per 4 groups -> blend ->
+//                           sigmoid -> similarity -> learned view weight -> weighted mean.  Samples that
+//                           fall outside the box (rough depth maps, silhouettes) are served by further
+//                           staging rounds; there is no slow global-memory path.  Output stores are
+//                           128-byte coalesced rows of the (B,G,D,H,W) volume.
+//
+// Reference: net/unit/base.py:85-126 (homo_warping), net/unit/homoaggregate.py:25-46 (+16-20).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <limits.h>
+#include <stdint.h>
+
+#include "mdf_common.cuh"
+#include "mdf_host.cuh"
+
+namespace mdf {
+
+struct FeaPtrs { const float* p[MDF_MAX_VIEWS]; };
+
+// ------------------------------------------------------------------------------------------------
+// prep: one thread per pixel of one view; blockIdx.y = view * B + b.
+// Loads are 128-byte coalesced rows of the NCHW planes, stores are 512-byte coalesced float4 rows.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+prep_kernel(FeaPtrs feas, int B, int G, int HW, float4* __restrict__ Q4, float4* __restrict__ S4)
+{
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= HW) return;
+    const int v = blockIdx.y / B, b = blockIdx.y % B;
+    const float* __restrict__ f = feas.p[v] + (size_t)b * 2 * G * HW + pix;
+    const int J = G / 4;
+    if (v == 0) {
+        float4* __restrict__ dst = Q4 + (size_t)b * J * HW + pix;
+        for (int j = 0; j < J; ++j) {
+            float d[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float a = __ldg(f + (size_t)(8 * j + 2 * k) * HW), c = __ldg(f + (size_t)(8 * j + 2 * k + 1) * HW);
+                d[k] = 2.0f / (1.0f + expf(c - a)) - 1.0f;
+            }
+            dst[(size_t)j * HW] = make_float4(d[0], d[1], d[2], d[3]);
+        }
+        return;
+    }
+    float4* __restrict__ dst = S4 + ((size_t)(v - 1) * B + b) * J * HW + pix;
+    for (int j = 0; j < J; ++j) {
+        float d[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float a = __ldg(f + (size_t)(8 * j + 2 * k) * HW), c = __ldg(f + (size_t)(8 * j + 2 * k + 1) * HW);
+            d[k] = (c - a) * kLog2e;
+        }
+        dst[(size_t)j * HW] = make_float4(d[0], d[1], d[2], d[3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA / mbarrier / shared-memory primitives (inline PTX; SASS: UTMALDG, SYNCS, LDS.128)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1, int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+// ptxas folds `addr + constant` into the immediate offset of LDS
+__device__ __forceinline__ float4 lds128(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float lds32(uint32_t addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// configuration
+//   G      groups (channels of the difference map): 32 / 16 / 8 at the three stages
+//   PT     depth planes walked by one thread (accumulators: PT*G registers)
+//   TH     tile height in pixels (tile width is one warp = 32 pixels: 128-byte output rows)
+//   PG     plane groups per CTA -> the CTA's slab is PT*PG planes, blockDim = (32, TH, PG)
+//   BW,BH  box (texels) of one source difference map staged per TMA load: [G/4][BH][BW] float4
+//   MINB   CTAs per SM the register allocation aims at
+//   CQS    keep the per-pixel similarity weights cq_g = conv_w[g]*q_g in shared memory instead of registers
+// ------------------------------------------------------------------------------------------------
+template <int G_, int PT_, int TH_, int PG_, int BW_, int BH_, int MINB_, bool CQS_>
+struct StagedCfg {
+    static constexpr int G = G_, PT = PT_, TH = TH_, PG = PG_, BW = BW_, BH = BH_, MINB = MINB_;
+    static constexpr bool CQS = CQS_;
+    static constexpr int J = G / 4;
+    static constexpr int NCQ = CQS ? 1 : G;
+    static constexpr int THREADS = 32 * TH * PG;
+    static constexpr int WARPS = THREADS / 32;
+    static constexpr int PLANE_BYTES = BW * BH * 16;
+    static constexpr int BOX_BYTES = J * PLANE_BYTES;          // multiple of 128
+    static constexpr int CQ_BYTES = CQS ? G * 4 * THREADS : 0;
+    static constexpr int RT_BYTES = kMaxSrcViews * 12 * 4;
+    static constexpr int SLAB = PT * PG;
+    static constexpr int OFF_CQ = 2 * BOX_BYTES;               // two boxes: the gather of view v overlaps the load of v+1
+    static constexpr int OFF_RT = OFF_CQ + CQ_BYTES;
+    static constexpr int OFF_BAR = (OFF_RT + RT_BYTES + 15) / 16 * 16;   // 3 mbarriers: box 0, box 1, retry loads
+    static constexpr int OFF_CTL = OFF_BAR + 32;                          // 16 ints of control words
+    static constexpr size_t SMEM = OFF_CTL + 64 + 128 /*alignment slack*/;   // 16 control words
+    static_assert(BW * 2 <= 256 && BH <= 256, "TMA box dimensions are limited to 256 elements");
+    static_assert(PT <= 8, "plane bookkeeping uses 8 bits per plane");
+};
+
+struct StagedArgs {
+    const float4* Q4;     // [B][G/4][H][W]
+    const float* rt;      // [V][B][12]
+    const float* dwp;     // folded depth_weight
+    const float* conv_w;  // (G,), 16-byte aligned
+    const float* hypos;
+    float* out;           // (B,G,D,H,W)
+    GridNorm gn;
+    int per_pixel, V, B, D, H, W, tiles_x, tiles_y, slabs;
+};
+
+constexpr int kNone = INT_MAX;
+
+// order-preserving integer key of a sample coordinate in (-1, size): negative -> -1, else its bit pattern
+__device__ __forceinline__ int coord_key(float v) { return v < 0.0f ? -1 : __float_as_int(v); }
+__device__ __forceinline__ int key_floor(int k) { return k < 0 ? -1 : (int)__int_as_float(k); }
+
+// control words in shared memory
+// (bounding-box words are per view parity: view v+1 is prepared while slower warps may still prepare view v)
+enum { kMinX = 0, kMinY = 1, kCount = 2, kSetStride = 4 /* two sets */, kOrg0 = 8 /* ox,oy of box 0, box 1 */, kRetry = 12 /* [2][2] */ };
+
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB)
+cost_volume_staged_kernel(const __grid_constant__ CUtensorMap tmap, const StagedArgs a)
+{
+    constexpr int G = Cfg::G, J = Cfg::J, PT = Cfg::PT, TH = Cfg::TH, BW = Cfg::BW, BH = Cfg::BH, NCQ = Cfg::NCQ;
+    constexpr int PLANE = Cfg::PLANE_BYTES, THREADS = Cfg::THREADS;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t pad = (128u - (smem_u32(smem_raw) & 127u)) & 127u;
+    const uint32_t box0 = smem_u32(smem_raw) + pad;
+    const uint32_t bar0 = box0 + Cfg::OFF_BAR;           // +0: box 0, +8: box 1, +16: retry loads
+    const uint32_t rt_s = box0 + Cfg::OFF_RT;
+    volatile int* ctl = reinterpret_cast<volatile int*>(smem_raw + pad + Cfg::OFF_CTL);
+    int* ctl_nv = reinterpret_cast<int*>(smem_raw + pad + Cfg::OFF_CTL);
+
+    const int lane = threadIdx.x, ty = threadIdx.y, pg = threadIdx.z;
+    const int tid = lane + 32 * (ty + TH * pg);
+    const uint32_t cq_s = box0 + Cfg::OFF_CQ + (uint32_t)tid * 16u;
+
+    int it = blockIdx.x;
+    const int tile_x = it % a.tiles_x; it /= a.tiles_x;
+    const int tile_y = it % a.tiles_y; it /= a.tiles_y;
+    const int slab = it % a.slabs;
+    const int b = it / a.slabs;
+
+    const int H = a.H, W = a.W, D = a.D;
+    const int px = tile_x * 32 + lane, py = tile_y * TH + ty;
+    const bool pix_ok = (px < W) && (py < H);
+    const int d0 = slab * Cfg::SLAB + pg * PT;
+    const size_t HW = (size_t)H * W;
+    GridNormFast gf;
+    gf.g = a.gn;
+    gf.r_half_wm1 = refine_rcp(a.gn.half_wm1);
+    gf.r_half_hm1 = refine_rcp(a.gn.half_hm1);
+
+    if (tid == 0) {
+        mbar_init(bar0, 1); mbar_init(bar0 + 8, 1); mbar_init(bar0 + 16, 1);
+        ctl[kMinX] = kNone; ctl[kMinY] = kNone; ctl[kCount] = 0;
+        ctl[kSetStride + kMinX] = kNone; ctl[kSetStride + kMinY] = kNone; ctl[kSetStride + kCount] = 0;
+        ctl[kRetry + 0] = ctl[kRetry + 1] = ctl[kRetry + 2] = ctl[kRetry + 3] = kNone;
+        fence_barrier_init();
+    }
+    // rot | trans of every source view of this batch item -> shared memory
+    for (int k = tid; k < a.V * 12; k += THREADS) {
+        const float val = __ldg(a.rt + ((size_t)(k / 12) * a.B + b) * 12 + (k % 12));
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(rt_s + 4u * k), "f"(val) : "memory");
+    }
+
+    // per-thread constants: hypotheses of my planes, cq_g = conv_w[g] * q_g of my pixel
+    float depth[PT];
+    uint32_t ok_mask = 0;                       // bit i: plane d0+i exists and my pixel is inside the image
+#pragma unroll
+    for (int i = 0; i < PT; ++i) {
+        const int d = d0 + i;
+        depth[i] = 0.0f;
+        if (pix_ok && d < D) {
+            ok_mask |= 1u << i;
+            depth[i] = a.per_pixel ? __ldg(a.hypos + ((size_t)b * D + d) * HW + (size_t)py * W + px)
+                                   : __ldg(a.hypos + (size_t)b * D + d);
+        }
+    }
+    const float4* __restrict__ qp = a.Q4 + (size_t)b * J * HW + (size_t)py * W + px;
+    float cq[NCQ];
+    float ksum = 0.0f;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        const float4 q = pix_ok ? __ldg(qp + (size_t)j * HW) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 cw = __ldg(reinterpret_cast<const float4*>(a.conv_w) + j);
+        const float4 c = make_float4(cw.x * q.x, cw.y * q.y, cw.z * q.z, cw.w * q.w);
+        if (Cfg::CQS) {
+            sts128(cq_s + (uint32_t)j * THREADS * 16u, c);
+        } else {
+            cq[(4 * j + 0) % NCQ] = c.x; cq[(4 * j + 1) % NCQ] = c.y; cq[(4 * j + 2) % NCQ] = c.z; cq[(4 * j + 3) % NCQ] = c.w;
+        }
+        ksum += (c.x + c.y) + (c.z + c.w);
+    }
+    ksum *= 0.5f;
+    const float alpha = __ldg(a.dwp + 0), betap = __ldg(a.dwp + 1), fcw = __ldg(a.dwp + 2), fcb = __ldg(a.dwp + 3);
+
+    float acc[PT][G];
+    float wsum[PT];
+#pragma unroll
+    for (int i = 0; i < PT; ++i) {
+        wsum[i] = 0.0f;
+#pragma unroll
+        for (int g = 0; g < G; ++g) acc[i][g] = 0.0f;
+    }
+    uint64_t n_void = 0;                         // 8 bits per plane: views whose sample fell outside the source image
+    uint32_t riter = 0;                          // CTA-uniform count of retry loads (mbarrier phase, reduction slot)
+    __syncthreads();
+
+    // Positions of my planes in view v; returns the mask of samples that have to be gathered.  Contributes
+    // this warp's corner to the CTA-wide bounding box; the LAST warp to arrive (no barrier: nobody waits)
+    // issues the TMA load of view v's box into buffer v & 1.
+    auto prepare_view = [&](int v, float (&ix)[PT], float (&iy)[PT]) -> uint32_t {
+        uint32_t todo = 0;
+        float rt[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) rt[k] = lds32(rt_s + (uint32_t)(v * 12 + k) * 4u);
+        const RotXYZ r = rot_xyz(rt, (float)px, (float)py);
+        int kx = kNone, ky = kNone;
+#pragma unroll
+        for (int i = 0; i < PT; ++i) {
+            sample_position_fast(r, rt, depth[i], gf, ix[i], iy[i]);
+            const bool inside = (ix[i] > -1.0f) && (ix[i] < a.gn.fw) && (iy[i] > -1.0f) && (iy[i] < a.gn.fh);
+            if ((ok_mask >> i) & 1u) {
+                if (inside) {
+                    todo |= 1u << i;
+                    kx = min(kx, coord_key(ix[i]));
+                    ky = min(ky, coord_key(iy[i]));
+                } else {
+                    n_void += 1ull << (8 * i);
+                }
+            }
+        }
+        kx = __reduce_min_sync(0xffffffffu, kx);
+        ky = __reduce_min_sync(0xffffffffu, ky);
+        if (lane == 0) {
+            const int set = kSetStride * (v & 1);
+            if (kx != kNone) { atomicMin(ctl_nv + set + kMinX, key_floor(kx)); atomicMin(ctl_nv + set + kMinY, key_floor(ky)); }
+            __threadfence_block();
+            if (atomicAdd(ctl_nv + set + kCount, 1) == Cfg::WARPS - 1) {
+                __threadfence_block();
+                int ox = ctl[set + kMinX], oy = ctl[set + kMinY];
+                if (ox == kNone) { ox = 0; oy = 0; }          // no sample of the whole CTA lands in this view
+                ctl[set + kMinX] = kNone; ctl[set + kMinY] = kNone; ctl[set + kCount] = 0;
+                ctl[kOrg0 + 2 * (v & 1)] = ox; ctl[kOrg0 + 2 * (v & 1) + 1] = oy;
+                const uint32_t bar = bar0 + 8u * (v & 1);
+                mbar_expect_tx(bar, Cfg::BOX_BYTES);
+                // the tensor map counts in 8-byte elements: 2 per texel
+                tma_load_3d(box0 + (uint32_t)(v & 1) * Cfg::BOX_BYTES, &tmap, bar, ox * 2, oy, (v * a.B + b) * J);
+            }
+        }
+        return todo;
+    };
+
+    float ix[PT], iy[PT];
+    uint32_t todo = prepare_view(0, ix, iy);
+
+    for (int v = 0; v < a.V; ++v) {
+        // ---- 1. get view v+1 going: positions, bounding box, TMA load into the other buffer ----
+        float nx[PT], ny[PT];
+        uint32_t ntodo = 0;
+        if (v + 1 < a.V) ntodo = prepare_view(v + 1, nx, ny);
+
+        // ---- 2. gather view v: round 0 from the prefetched box, further rounds for samples outside it ----
+        const uint32_t box = box0 + (uint32_t)(v & 1) * Cfg::BOX_BYTES;
+        int ox, oy;
+        mbar_wait(bar0 + 8u * (v & 1), (uint32_t)(v >> 1) & 1u);
+        ox = ctl[kOrg0 + 2 * (v & 1)];
+        oy = ctl[kOrg0 + 2 * (v & 1) + 1];
+        while (true) {
+#pragma unroll
+            for (int i = 0; i < PT; ++i) {
+                if (!((todo >> i) & 1u)) continue;
+                float fx0, fy0;
+                int x0, y0;
+                floor_small(ix[i], fx0, x0);
+                floor_small(iy[i], fy0, y0);
+                const int rx = x0 - ox, ry = y0 - oy;
+                if ((unsigned)rx >= (unsigned)(BW - 1) || (unsigned)ry >= (unsigned)(BH - 1)) continue;   // next round
+                todo &= ~(1u << i);
+                const float ax = __fsub_rn(__fadd_rn(fx0, 1.0f), ix[i]), bx = __fsub_rn(ix[i], fx0);
+                const float ay = __fsub_rn(__fadd_rn(fy0, 1.0f), iy[i]), by = __fsub_rn(iy[i], fy0);
+                Taps t;
+                t.wnw = __fmul_rn(ax, ay); t.wne = __fmul_rn(bx, ay); t.wsw = __fmul_rn(ax, by); t.wse = __fmul_rn(bx, by);
+                const uint32_t addr = box + (uint32_t)(ry * BW + rx) * 16u;
+                float p[G];
+                float z = -ksum;
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    const float4 nw = lds128(addr + j * PLANE);                 // constant offsets -> LDS.128 [R + imm]
+                    const float4 ne = lds128(addr + j * PLANE + 16);
+                    const float4 sw = lds128(addr + j * PLANE + BW * 16);
+                    const float4 se = lds128(addr + j * PLANE + BW * 16 + 16);
+                    float4 c;
+                    if (Cfg::CQS) c = lds128(cq_s + (uint32_t)j * THREADS * 16u);
+                    else c = make_float4(cq[(4 * j + 0) % NCQ], cq[(4 * j + 1) % NCQ], cq[(4 * j + 2) % NCQ], cq[(4 * j + 3) % NCQ]);
+                    p[4 * j + 0] = rcp_approx(1.0f + ex2_approx(blend4(nw.x, ne.x, sw.x, se.x, t)));
+                    p[4 * j + 1] = rcp_approx(1.0f + ex2_approx(blend4(nw.y, ne.y, sw.y, se.y, t)));
+                    p[4 * j + 2] = rcp_approx(1.0f + ex2_approx(blend4(nw.z, ne.z, sw.z, se.z, t)));
+                    p[4 * j + 3] = rcp_approx(1.0f + ex2_approx(blend4(nw.w, ne.w, sw.w, se.w, t)));
+                    z = fmaf(c.x, p[4 * j + 0], z);
+                    z = fmaf(c.y, p[4 * j + 1], z);
+                    z = fmaf(c.z, p[4 * j + 2], z);
+                    z = fmaf(c.w, p[4 * j + 3], z);
+                }
+                float h = fmaf(z, alpha, betap);              // BatchNorm3d (eval)
+                h = fmaxf(h, 0.0f);                           // ReLU
+                h = fmaf(h, fcw, fcb);                        // Conv3d(1,1,1)
+                const float w = rcp_approx(1.0f + ex2_approx(-kLog2e * h));   // Sigmoid
+                wsum[i] += w;
+#pragma unroll
+                for (int g = 0; g < G; ++g) acc[i][g] = fmaf(w, p[g], acc[i][g]);
+            }
+            // everybody is done with this box; does any sample still wait for another one?
+            if (!__syncthreads_or(todo != 0u)) break;
+
+            // ---- retry round (rough depth maps, silhouettes): synchronous load into the same buffer.
+            // x origin = min over the samples left; y origin = min over those whose column fits, so the
+            // topmost of them lands inside the box and the loop always makes progress.
+            int* slot = ctl_nv + kRetry + 2 * (riter & 1u);
+            int kx = kNone;
+#pragma unroll
+            for (int i = 0; i < PT; ++i)
+                if ((todo >> i) & 1u) kx = min(kx, coord_key(ix[i]));
+            kx = __reduce_min_sync(0xffffffffu, kx);
+            if (lane == 0 && kx != kNone) atomicMin(slot, key_floor(kx));
+            if (tid == 0) { volatile int* other = ctl + kRetry + 2 * ((riter + 1u) & 1u); other[0] = kNone; other[1] = kNone; }
+            __syncthreads();
+            ox = ctl[kRetry + 2 * (riter & 1u)];
+            const float xlim = (float)(ox + BW - 1);
+            int m = kNone;
+#pragma unroll
+            for (int i = 0; i < PT; ++i)
+                if (((todo >> i) & 1u) && ix[i] < xlim) m = min(m, coord_key(iy[i]));
+            m = __reduce_min_sync(0xffffffffu, m);
+            if (lane == 0 && m != kNone) atomicMin(slot + 1, key_floor(m));
+            __syncthreads();
+            oy = ctl[kRetry + 2 * (riter & 1u) + 1];
+            if (tid == 0) {
+                mbar_expect_tx(bar0 + 16, Cfg::BOX_BYTES);
+                tma_load_3d(box, &tmap, bar0 + 16, ox * 2, oy, (v * a.B + b) * J);
+            }
+            mbar_wait(bar0 + 16, riter & 1u);
+            ++riter;
+        }
+#pragma unroll
+        for (int i = 0; i < PT; ++i) { ix[i] = nx[i]; iy[i] = ny[i]; }
+        todo = ntodo;
+    }
+
+    // ---- 3. volume_sum / weight_sum (homoaggregate.py:46), coalesced 128-byte rows ----
+    const float w_void = __ldg(a.dwp + 5);       // view weight of a sample with no tap in bounds (similarity 0.5)
+#pragma unroll
+    for (int i = 0; i < PT; ++i) {
+        if (!((ok_mask >> i) & 1u)) continue;
+        const float nv = (float)((unsigned)(n_void >> (8 * i)) & 255u);
+        const float ws = fmaf(nv, w_void, wsum[i]);
+        const float half_void = 0.5f * nv * w_void;          // void samples: similarity 0.5 in every group
+        const float rw = __frcp_rn(ws);
+        float* op = a.out + (((size_t)b * G) * D + (d0 + i)) * HW + (size_t)py * W + px;
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const float4 q = __ldg(qp + (size_t)j * HW);
+            op[(size_t)(4 * j + 0) * D * HW] = fmaf(q.x, fmaf(acc[i][4 * j + 0] + half_void, rw, -0.5f), 0.5f);
+            op[(size_t)(4 * j + 1) * D * HW] = fmaf(q.y, fmaf(acc[i][4 * j + 1] + half_void, rw, -0.5f), 0.5f);
+            op[(size_t)(4 * j + 2) * D * HW] = fmaf(q.z, fmaf(acc[i][4 * j + 2] + half_void, rw, -0.5f), 0.5f);
+            op[(size_t)(4 * j + 3) * D * HW] = fmaf(q.w, fmaf(acc[i][4 * j + 3] + half_void, rw, -0.5f), 0.5f);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn()
+{
+    // resolved through the runtime: the library does not link libcuda
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+template <class Cfg>
+static int launch_staged(const StagedArgs& args, const float* S4, cudaStream_t stream)
+{
+    EncodeTiledFn encode = get_encode_fn();
+    if (encode == nullptr) return MDF_ERR_UNSUPPORTED;
+    // 3-D view of S4[(v*B+b)*J + j][y][x] (16-byte texels) in 8-byte elements: dim0 = 2*W, dim1 = H rows,
+    // dim2 = planes.  (8-byte elements because a box dimension is limited to 256 elements.)
+    CUtensorMap tmap;
+    const cuuint64_t planes = (cuuint64_t)args.V * args.B * Cfg::J;
+    const cuuint64_t dims[3] = {(cuuint64_t)args.W * 2, (cuuint64_t)args.H, planes};
+    const cuuint64_t strides[2] = {(cuuint64_t)args.W * 16, (cuuint64_t)args.H * args.W * 16};
+    const cuuint32_t box[3] = {(cuuint32_t)Cfg::BW * 2, (cuuint32_t)Cfg::BH, (cuuint32_t)Cfg::J};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<float*>(S4), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { g_last_cuda_error = (int)r; return MDF_ERR_CUDA; }
+    auto kern = cost_volume_staged_kernel<Cfg>;
+    MDF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    StagedArgs a = args;
+    a.gn = make_grid_norm(a.H, a.W);
+    a.tiles_x = (a.W + 31) / 32;
+    a.tiles_y = (a.H + Cfg::TH - 1) / Cfg::TH;
+    a.slabs = (a.D + Cfg::SLAB - 1) / Cfg::SLAB;
+    const long long items = (long long)a.tiles_x * a.tiles_y * a.slabs * a.B;
+    if (items <= 0) return MDF_OK;
+    if (items > INT_MAX) return MDF_ERR_UNSUPPORTED;
+    kern<<<(unsigned)items, dim3(32, Cfg::TH, Cfg::PG), Cfg::SMEM, stream>>>(tmap, a);
+    return launch_status();
+}
+
+// Tuning variants per G (algo = 16 + k selects variant k; variant 0 is the default).
+//                         G  PT TH PG  BW  BH MINB CQS
+using CfgG32_0 = StagedCfg<32, 1, 4, 2, 40, 7, 2, true>;     // 256 thr, 2 x 35 KiB boxes + cq 32 KiB = 104 KiB, slab 2 planes
+using CfgG32_1 = StagedCfg<32, 1, 2, 4, 40, 6, 2, true>;     // tile 32x2, slab 4 planes
+using CfgG32_2 = StagedCfg<32, 1, 4, 4, 40, 8, 1, true>;     // 512 thr, slab 4 planes
+using CfgG32_3 = StagedCfg<32, 1, 4, 1, 40, 8, 3, false>;    // 128 thr x 3
+using CfgG16_0 = StagedCfg<16, 2, 4, 2, 64, 8, 2, false>;    // 256 thr x 2 CTAs, 2 x 32 KiB boxes, slab 4 planes
+using CfgG16_1 = StagedCfg<16, 4, 4, 2, 64, 8, 2, true>;     // slab 8 planes
+using CfgG16_2 = StagedCfg<16, 2, 4, 2, 48, 8, 3, true>;     // 3 CTAs (85 registers)
+using CfgG16_3 = StagedCfg<16, 1, 4, 2, 48, 8, 3, false>;    // slab 2 planes
+using CfgG8_0  = StagedCfg<8, 4, 4, 2, 64, 10, 2, false>;    // 256 thr x 2 CTAs, 2 x 20 KiB boxes, slab 8 planes
+using CfgG8_1  = StagedCfg<8, 4, 8, 1, 64, 12, 2, false>;    // tile 32x8, slab 4 planes
+using CfgG8_2  = StagedCfg<8, 2, 4, 2, 64, 10, 3, false>;    // 3 CTAs, slab 4 planes
+using CfgG8_3  = StagedCfg<8, 8, 4, 1, 64, 10, 4, false>;    // 128 thr x 4 CTAs, slab 8 planes
+
+static int launch_staged_variant(int G, int variant, const StagedArgs& a, const float* S, cudaStream_t stream)
+{
+    if (G == 32) {
+        switch (variant) {
+            case 0: return launch_staged<CfgG32_0>(a, S, stream);
+            case 1: return launch_staged<CfgG32_1>(a, S, stream);
+            case 2: return launch_staged<CfgG32_2>(a, S, stream);
+            case 3: return launch_staged<CfgG32_3>(a, S, stream);
+        }
+    } else if (G == 16) {
+        switch (variant) {
+            case 0: return launch_staged<CfgG16_0>(a, S, stream);
+            case 1: return launch_staged<CfgG16_1>(a, S, stream);
+            case 2: return launch_staged<CfgG16_2>(a, S, stream);
+            case 3: return launch_staged<CfgG16_3>(a, S, stream);
+        }
+    } else if (G == 8) {
+        switch (variant) {
+            case 0: return launch_staged<CfgG8_0>(a, S, stream);
+            case 1: return launch_staged<CfgG8_1>(a, S, stream);
+            case 2: return launch_staged<CfgG8_2>(a, S, stream);
+            case 3: return launch_staged<CfgG8_3>(a, S, stream);
+        }
+    }
+    return MDF_ERR_UNSUPPORTED;
+}
+
+}  // namespace mdf
