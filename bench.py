@@ -62,7 +62,7 @@ def make_view(h0, w0, nviews, batch, seed):
             H=H, W=W, C=C, D=D, G=G,
             features=syn.smooth_features(batch, nviews, C, H, W, seed=seed + 10 + s),
             ref_proj=P[:, 0].copy(), src_projs=[P[:, v].copy() for v in range(1, nviews)],
-            hypos=syn.uniform_hypos(batch, D) if s == 0 else syn.pixel_hypos(batch, D, H, W, seed=seed + 20 + s),
+            hypos=syn.uniform_hypos(batch, D) if s == 0 else syn.scene_hypos(batch, D, H, W, seed=seed),
             params=syn.depth_weight_params(G, seed=seed + 30 + s),
             logits=syn.regulariser_logits(batch, D, H, W, seed=seed + 40 + s)))
     return stages

@@ -33,6 +33,8 @@ struct Workspace {
     size_t dwp_off;   // 64 floats: [0]=alpha [1]=beta' [2]=fc_w [3]=fc_b [4]=beta(raw) [5]=weight of an out-of-image sample
     size_t q_off;     // [B][G/4][H][W] float4 reference q maps           (staged path)
     size_t s_off;     // [V][B][G/4][H][W] float4 source difference maps  (staged path)
+    size_t cq_off;    // [B][G/4][H][W] float4 conv_w * q                 (staged path)
+    size_t ks_off;    // [B][H][W] float 0.5 * sum_g cq_g                 (staged path)
     size_t total;
 };
 
@@ -47,6 +49,10 @@ static Workspace make_workspace(int B, int N, int G, int H, int W, bool staged)
     if (staged) off = align_up(off + (size_t)B * G * H * W * sizeof(float), 256);
     w.s_off = off;
     if (staged) off = align_up(off + V * B * (size_t)H * W * G * sizeof(float), 256);
+    w.cq_off = off;
+    if (staged) off = align_up(off + (size_t)B * G * H * W * sizeof(float), 256);
+    w.ks_off = off;
+    if (staged) off = align_up(off + (size_t)B * H * W * sizeof(float), 256);
     w.total = off;
     return w;
 }
@@ -412,22 +418,25 @@ int mdf_cost_volume_fwd_ex(const float* const* features, int N, const float* ref
 
     float4* Q4 = reinterpret_cast<float4*>(wsb + ws.q_off);
     float4* S4 = reinterpret_cast<float4*>(wsb + ws.s_off);
+    float4* CQ4 = reinterpret_cast<float4*>(wsb + ws.cq_off);
+    float* KS = reinterpret_cast<float*>(wsb + ws.ks_off);
     {
         FeaPtrs fp;
         for (int i = 0; i < MDF_MAX_VIEWS; ++i) fp.p[i] = i < N ? features[i] : nullptr;
         const long long HW = (long long)H * W;
         if (HW > INT_MAX - 256 || (long long)N * B > 65535) return MDF_ERR_UNSUPPORTED;
-        prep_kernel<<<dim3((unsigned)((HW + 255) / 256), (unsigned)(N * B)), 256, 0, stream>>>(fp, B, G, (int)HW, Q4, S4);
+        prep_kernel<<<dim3((unsigned)((HW + 255) / 256), (unsigned)(N * B)), 256, 0, stream>>>(fp, B, G, (int)HW, dwp + 16, Q4, CQ4, KS, S4);
         st = launch_status();
         if (st != MDF_OK) return st;
     }
     StagedArgs a;
-    a.Q4 = Q4; a.rt = rt; a.dwp = dwp; a.conv_w = dwp + 16; a.hypos = depth_hypos; a.out = cost_volume;
+    a.rt = rt; a.dwp = dwp; a.ks = KS; a.hypos = depth_hypos; a.out = cost_volume;
     a.per_pixel = hypos_per_pixel; a.V = V; a.B = B; a.D = D; a.H = H; a.W = W;
     a.gn = make_grid_norm(H, W);
     a.tiles_x = a.tiles_y = a.slabs = 0;
-    const float* S = reinterpret_cast<const float*>(S4);
-    return launch_staged_variant(G, algo >= 16 ? algo - 16 : 0, a, S, stream);
+    StagedBuffers buf;
+    buf.S4 = reinterpret_cast<const float*>(S4); buf.Q4 = reinterpret_cast<const float*>(Q4); buf.CQ4 = reinterpret_cast<const float*>(CQ4);
+    return launch_staged_variant(G, algo >= 16 ? algo - 16 : 0, a, buf, stream);
 }
 
 int mdf_cost_volume_fwd(const float* const* features, int N, const float* ref_proj, const float* const* src_projs,

@@ -37,7 +37,8 @@ struct FeaPtrs { const float* p[MDF_MAX_VIEWS]; };
 // Loads are 128-byte coalesced rows of the NCHW planes, stores are 512-byte coalesced float4 rows.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-prep_kernel(FeaPtrs feas, int B, int G, int HW, float4* __restrict__ Q4, float4* __restrict__ S4)
+prep_kernel(FeaPtrs feas, int B, int G, int HW, const float* __restrict__ conv_w /* 16-byte aligned */,
+            float4* __restrict__ Q4, float4* __restrict__ CQ4, float* __restrict__ KS, float4* __restrict__ S4)
 {
     const int pix = blockIdx.x * blockDim.x + threadIdx.x;
     if (pix >= HW) return;
@@ -45,7 +46,10 @@ prep_kernel(FeaPtrs feas, int B, int G, int HW, float4* __restrict__ Q4, float4*
     const float* __restrict__ f = feas.p[v] + (size_t)b * 2 * G * HW + pix;
     const int J = G / 4;
     if (v == 0) {
-        float4* __restrict__ dst = Q4 + (size_t)b * J * HW + pix;
+        // reference view: q_g = 2*sigmoid(r[2g]-r[2g+1]) - 1, cq_g = conv_w[g]*q_g, ks = 0.5*sum_g cq_g
+        float4* __restrict__ qd = Q4 + (size_t)b * J * HW + pix;
+        float4* __restrict__ cd = CQ4 + (size_t)b * J * HW + pix;
+        float ks = 0.0f;
         for (int j = 0; j < J; ++j) {
             float d[4];
 #pragma unroll
@@ -53,8 +57,13 @@ prep_kernel(FeaPtrs feas, int B, int G, int HW, float4* __restrict__ Q4, float4*
                 const float a = __ldg(f + (size_t)(8 * j + 2 * k) * HW), c = __ldg(f + (size_t)(8 * j + 2 * k + 1) * HW);
                 d[k] = 2.0f / (1.0f + expf(c - a)) - 1.0f;
             }
-            dst[(size_t)j * HW] = make_float4(d[0], d[1], d[2], d[3]);
+            const float4 cw = __ldg(reinterpret_cast<const float4*>(conv_w) + j);
+            const float4 c = make_float4(cw.x * d[0], cw.y * d[1], cw.z * d[2], cw.w * d[3]);
+            qd[(size_t)j * HW] = make_float4(d[0], d[1], d[2], d[3]);
+            cd[(size_t)j * HW] = c;
+            ks += (c.x + c.y) + (c.z + c.w);
         }
+        KS[(size_t)b * HW + pix] = 0.5f * ks;
         return;
     }
     float4* __restrict__ dst = S4 + ((size_t)(v - 1) * B + b) * J * HW + pix;
@@ -146,27 +155,33 @@ struct StagedCfg {
     static constexpr int WARPS = THREADS / 32;
     static constexpr int PLANE_BYTES = BW * BH * 16;
     static constexpr int BOX_BYTES = J * PLANE_BYTES;          // multiple of 128
-    static constexpr int CQ_BYTES = CQS ? G * 4 * THREADS : 0;
+    static constexpr int TILE_BYTES = J * TH * 32 * 16;        // per-pixel float4 planes of the CTA's tile (q, cq)
     static constexpr int RT_BYTES = kMaxSrcViews * 12 * 4;
     static constexpr int SLAB = PT * PG;
-    static constexpr int OFF_CQ = 2 * BOX_BYTES;               // two boxes: the gather of view v overlaps the load of v+1
-    static constexpr int OFF_RT = OFF_CQ + CQ_BYTES;
-    static constexpr int OFF_BAR = (OFF_RT + RT_BYTES + 15) / 16 * 16;   // 3 mbarriers: box 0, box 1, retry loads
-    static constexpr int OFF_CTL = OFF_BAR + 32;                          // 16 ints of control words
-    static constexpr size_t SMEM = OFF_CTL + 64 + 128 /*alignment slack*/;   // 16 control words
+    static constexpr int OFF_Q = 2 * BOX_BYTES;                // two boxes: the gather of view v overlaps the load of v+1
+    static constexpr int OFF_CQ = OFF_Q + TILE_BYTES;
+    static constexpr int OFF_RT = OFF_CQ + TILE_BYTES;
+    static constexpr int OFF_BAR = (OFF_RT + RT_BYTES + 15) / 16 * 16;   // 4 mbarriers: box 0, box 1, retry loads, tiles
+    static constexpr int OFF_CTL = OFF_BAR + 32;                          // control words, see enum below
+    static constexpr size_t SMEM = OFF_CTL + 4 * (16 + 2 * kMaxSrcViews) + 128 /*alignment slack*/;
     static_assert(BW * 2 <= 256 && BH <= 256, "TMA box dimensions are limited to 256 elements");
     static_assert(PT <= 8, "plane bookkeeping uses 8 bits per plane");
 };
 
 struct StagedArgs {
-    const float4* Q4;     // [B][G/4][H][W]
     const float* rt;      // [V][B][12]
     const float* dwp;     // folded depth_weight
-    const float* conv_w;  // (G,), 16-byte aligned
+    const float* ks;      // [B][H][W]  0.5 * sum_g cq_g
     const float* hypos;
     float* out;           // (B,G,D,H,W)
     GridNorm gn;
     int per_pixel, V, B, D, H, W, tiles_x, tiles_y, slabs;
+};
+
+struct StagedMaps {
+    CUtensorMap s4;       // source difference maps  [V*B*J][H][W] float4
+    CUtensorMap q4;       // reference q              [B*J][H][W]   float4
+    CUtensorMap cq4;      // conv_w * q               [B*J][H][W]   float4
 };
 
 constexpr int kNone = INT_MAX;
@@ -175,27 +190,29 @@ constexpr int kNone = INT_MAX;
 __device__ __forceinline__ int coord_key(float v) { return v < 0.0f ? -1 : __float_as_int(v); }
 __device__ __forceinline__ int key_floor(int k) { return k < 0 ? -1 : (int)__int_as_float(k); }
 
-// control words in shared memory
-// (bounding-box words are per view parity: view v+1 is prepared while slower warps may still prepare view v)
-enum { kMinX = 0, kMinY = 1, kCount = 2, kSetStride = 4 /* two sets */, kOrg0 = 8 /* ox,oy of box 0, box 1 */, kRetry = 12 /* [2][2] */ };
+// control words in shared memory.  The bounding-box words exist once per view parity: view v+1 is
+// prepared while slower warps may still be preparing view v.
+enum { kMinX = 0, kMinY = 1, kCount = 2, kSetStride = 4, kRetry = 8 /* [2][2] */, kLeft = 12, kOrg = 16 /* [V][2] */ };
 
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB)
-cost_volume_staged_kernel(const __grid_constant__ CUtensorMap tmap, const StagedArgs a)
+cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedArgs a)
 {
     constexpr int G = Cfg::G, J = Cfg::J, PT = Cfg::PT, TH = Cfg::TH, BW = Cfg::BW, BH = Cfg::BH, NCQ = Cfg::NCQ;
     constexpr int PLANE = Cfg::PLANE_BYTES, THREADS = Cfg::THREADS;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t pad = (128u - (smem_u32(smem_raw) & 127u)) & 127u;
     const uint32_t box0 = smem_u32(smem_raw) + pad;
-    const uint32_t bar0 = box0 + Cfg::OFF_BAR;           // +0: box 0, +8: box 1, +16: retry loads
+    const uint32_t bar0 = box0 + Cfg::OFF_BAR;           // +0: box 0, +8: box 1, +16: retry loads, +24: q / cq tiles
     const uint32_t rt_s = box0 + Cfg::OFF_RT;
     volatile int* ctl = reinterpret_cast<volatile int*>(smem_raw + pad + Cfg::OFF_CTL);
     int* ctl_nv = reinterpret_cast<int*>(smem_raw + pad + Cfg::OFF_CTL);
 
     const int lane = threadIdx.x, ty = threadIdx.y, pg = threadIdx.z;
     const int tid = lane + 32 * (ty + TH * pg);
-    const uint32_t cq_s = box0 + Cfg::OFF_CQ + (uint32_t)tid * 16u;
+    const uint32_t q_s = box0 + Cfg::OFF_Q + (uint32_t)(ty * 32 + lane) * 16u;      // [j][ty][lane] float4
+    const uint32_t cq_s = box0 + Cfg::OFF_CQ + (uint32_t)(ty * 32 + lane) * 16u;
+    constexpr uint32_t TJ = TH * 32 * 16;                                           // plane stride of the tiles
 
     int it = blockIdx.x;
     const int tile_x = it % a.tiles_x; it /= a.tiles_x;
@@ -214,11 +231,16 @@ cost_volume_staged_kernel(const __grid_constant__ CUtensorMap tmap, const Staged
     gf.r_half_hm1 = refine_rcp(a.gn.half_hm1);
 
     if (tid == 0) {
-        mbar_init(bar0, 1); mbar_init(bar0 + 8, 1); mbar_init(bar0 + 16, 1);
+        mbar_init(bar0, 1); mbar_init(bar0 + 8, 1); mbar_init(bar0 + 16, 1); mbar_init(bar0 + 24, 1);
         ctl[kMinX] = kNone; ctl[kMinY] = kNone; ctl[kCount] = 0;
         ctl[kSetStride + kMinX] = kNone; ctl[kSetStride + kMinY] = kNone; ctl[kSetStride + kCount] = 0;
         ctl[kRetry + 0] = ctl[kRetry + 1] = ctl[kRetry + 2] = ctl[kRetry + 3] = kNone;
+        ctl[kLeft] = 0;
         fence_barrier_init();
+        // q and cq = conv_w * q of the tile's pixels: two TMA tile loads (zero fill beyond the image)
+        mbar_expect_tx(bar0 + 24, 2 * Cfg::TILE_BYTES);
+        tma_load_3d(box0 + Cfg::OFF_Q, &maps.q4, bar0 + 24, tile_x * 64, tile_y * TH, b * J);
+        tma_load_3d(box0 + Cfg::OFF_CQ, &maps.cq4, bar0 + 24, tile_x * 64, tile_y * TH, b * J);
     }
     // rot | trans of every source view of this batch item -> shared memory
     for (int k = tid; k < a.V * 12; k += THREADS) {
@@ -226,7 +248,7 @@ cost_volume_staged_kernel(const __grid_constant__ CUtensorMap tmap, const Staged
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(rt_s + 4u * k), "f"(val) : "memory");
     }
 
-    // per-thread constants: hypotheses of my planes, cq_g = conv_w[g] * q_g of my pixel
+    // per-thread constants: hypotheses of my planes
     float depth[PT];
     uint32_t ok_mask = 0;                       // bit i: plane d0+i exists and my pixel is inside the image
 #pragma unroll
@@ -239,60 +261,48 @@ cost_volume_staged_kernel(const __grid_constant__ CUtensorMap tmap, const Staged
                                    : __ldg(a.hypos + (size_t)b * D + d);
         }
     }
-    const float4* __restrict__ qp = a.Q4 + (size_t)b * J * HW + (size_t)py * W + px;
-    float cq[NCQ];
-    float ksum = 0.0f;
-#pragma unroll
-    for (int j = 0; j < J; ++j) {
-        const float4 q = pix_ok ? __ldg(qp + (size_t)j * HW) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 cw = __ldg(reinterpret_cast<const float4*>(a.conv_w) + j);
-        const float4 c = make_float4(cw.x * q.x, cw.y * q.y, cw.z * q.z, cw.w * q.w);
-        if (Cfg::CQS) {
-            sts128(cq_s + (uint32_t)j * THREADS * 16u, c);
-        } else {
-            cq[(4 * j + 0) % NCQ] = c.x; cq[(4 * j + 1) % NCQ] = c.y; cq[(4 * j + 2) % NCQ] = c.z; cq[(4 * j + 3) % NCQ] = c.w;
-        }
-        ksum += (c.x + c.y) + (c.z + c.w);
-    }
-    ksum *= 0.5f;
+    const float ksum = pix_ok ? __ldg(a.ks + (size_t)b * HW + (size_t)py * W + px) : 0.0f;
     const float alpha = __ldg(a.dwp + 0), betap = __ldg(a.dwp + 1), fcw = __ldg(a.dwp + 2), fcb = __ldg(a.dwp + 3);
 
-    float acc[PT][G];
+    float2 acc[PT][G / 2];                       // pairs of groups: the core runs on packed FFMA2 / FMUL2 / FADD2
     float wsum[PT];
 #pragma unroll
     for (int i = 0; i < PT; ++i) {
         wsum[i] = 0.0f;
 #pragma unroll
-        for (int g = 0; g < G; ++g) acc[i][g] = 0.0f;
+        for (int g = 0; g < G / 2; ++g) acc[i][g] = make_float2(0.0f, 0.0f);
     }
     uint64_t n_void = 0;                         // 8 bits per plane: views whose sample fell outside the source image
-    uint32_t riter = 0;                          // CTA-uniform count of retry loads (mbarrier phase, reduction slot)
-    __syncthreads();
+    uint32_t left = 0;                           // bit v: some sample of mine did not fit view v's box
+    __syncthreads();                             // rt_s, mbarriers and control words are set up
 
-    // Positions of my planes in view v; returns the mask of samples that have to be gathered.  Contributes
-    // this warp's corner to the CTA-wide bounding box; the LAST warp to arrive (no barrier: nobody waits)
-    // issues the TMA load of view v's box into buffer v & 1.
-    auto prepare_view = [&](int v, float (&ix)[PT], float (&iy)[PT]) -> uint32_t {
+    // sample positions of my planes in view v; returns the mask of samples with at least one tap in bounds
+    auto positions = [&](int v, float (&ix)[PT], float (&iy)[PT], bool count_void) -> uint32_t {
         uint32_t todo = 0;
         float rt[12];
 #pragma unroll
         for (int k = 0; k < 12; ++k) rt[k] = lds32(rt_s + (uint32_t)(v * 12 + k) * 4u);
         const RotXYZ r = rot_xyz(rt, (float)px, (float)py);
-        int kx = kNone, ky = kNone;
 #pragma unroll
         for (int i = 0; i < PT; ++i) {
             sample_position_fast(r, rt, depth[i], gf, ix[i], iy[i]);
             const bool inside = (ix[i] > -1.0f) && (ix[i] < a.gn.fw) && (iy[i] > -1.0f) && (iy[i] < a.gn.fh);
             if ((ok_mask >> i) & 1u) {
-                if (inside) {
-                    todo |= 1u << i;
-                    kx = min(kx, coord_key(ix[i]));
-                    ky = min(ky, coord_key(iy[i]));
-                } else {
-                    n_void += 1ull << (8 * i);
-                }
+                if (inside) todo |= 1u << i;
+                else if (count_void) n_void += 1ull << (8 * i);
             }
         }
+        return todo;
+    };
+
+    // Contribute this warp's corner to the CTA-wide bounding box of view v; the LAST warp to arrive issues
+    // the TMA load of the box into buffer v & 1.  No barrier: nobody waits here.  (All warps of the CTA
+    // have finished gathering view v-2 from that buffer when the last of them arrives.)
+    auto announce = [&](int v, const float (&ix)[PT], const float (&iy)[PT], uint32_t todo) {
+        int kx = kNone, ky = kNone;
+#pragma unroll
+        for (int i = 0; i < PT; ++i)
+            if ((todo >> i) & 1u) { kx = min(kx, coord_key(ix[i])); ky = min(ky, coord_key(iy[i])); }
         kx = __reduce_min_sync(0xffffffffu, kx);
         ky = __reduce_min_sync(0xffffffffu, ky);
         if (lane == 0) {
@@ -304,129 +314,181 @@ cost_volume_staged_kernel(const __grid_constant__ CUtensorMap tmap, const Staged
                 int ox = ctl[set + kMinX], oy = ctl[set + kMinY];
                 if (ox == kNone) { ox = 0; oy = 0; }          // no sample of the whole CTA lands in this view
                 ctl[set + kMinX] = kNone; ctl[set + kMinY] = kNone; ctl[set + kCount] = 0;
-                ctl[kOrg0 + 2 * (v & 1)] = ox; ctl[kOrg0 + 2 * (v & 1) + 1] = oy;
+                ctl[kOrg + 2 * v] = ox; ctl[kOrg + 2 * v + 1] = oy;
                 const uint32_t bar = bar0 + 8u * (v & 1);
                 mbar_expect_tx(bar, Cfg::BOX_BYTES);
-                // the tensor map counts in 8-byte elements: 2 per texel
-                tma_load_3d(box0 + (uint32_t)(v & 1) * Cfg::BOX_BYTES, &tmap, bar, ox * 2, oy, (v * a.B + b) * J);
+                // the tensor maps count in 8-byte elements: 2 per texel
+                tma_load_3d(box0 + (uint32_t)(v & 1) * Cfg::BOX_BYTES, &maps.s4, bar, ox * 2, oy, (v * a.B + b) * J);
             }
+        }
+    };
+
+    float cq[NCQ];
+    // gather the samples of `todo` that lie inside the box with origin (ox, oy); returns the rest
+    auto gather = [&](uint32_t box, int ox, int oy, const float (&ix)[PT], const float (&iy)[PT], uint32_t todo) -> uint32_t {
+#pragma unroll
+        for (int i = 0; i < PT; ++i) {
+            if (!((todo >> i) & 1u)) continue;
+            float fx0, fy0;
+            int x0, y0;
+            floor_small(ix[i], fx0, x0);
+            floor_small(iy[i], fy0, y0);
+            const int rx = x0 - ox, ry = y0 - oy;
+            if ((unsigned)rx >= (unsigned)(BW - 1) || (unsigned)ry >= (unsigned)(BH - 1)) continue;   // not in this box
+            todo &= ~(1u << i);
+            const float ax = __fsub_rn(__fadd_rn(fx0, 1.0f), ix[i]), bx = __fsub_rn(ix[i], fx0);
+            const float ay = __fsub_rn(__fadd_rn(fy0, 1.0f), iy[i]), by = __fsub_rn(iy[i], fy0);
+            const float wnw = __fmul_rn(ax, ay), wne = __fmul_rn(bx, ay), wsw = __fmul_rn(ax, by), wse = __fmul_rn(bx, by);
+            const float2 Wnw = make_float2(wnw, wnw), Wne = make_float2(wne, wne);
+            const float2 Wsw = make_float2(wsw, wsw), Wse = make_float2(wse, wse);
+            const uint32_t addr = box + (uint32_t)(ry * BW + rx) * 16u;
+            float2 p[G / 2];
+            float2 z2 = make_float2(-ksum, 0.0f);
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                const float4 nw = lds128(addr + j * PLANE);                 // constant offsets -> LDS.128 [R + imm]
+                const float4 ne = lds128(addr + j * PLANE + 16);
+                const float4 sw = lds128(addr + j * PLANE + BW * 16);
+                const float4 se = lds128(addr + j * PLANE + BW * 16 + 16);
+                float4 c;
+                if (Cfg::CQS) c = lds128(cq_s + (uint32_t)j * TJ);
+                else c = make_float4(cq[(4 * j + 0) % NCQ], cq[(4 * j + 1) % NCQ], cq[(4 * j + 2) % NCQ], cq[(4 * j + 3) % NCQ]);
+                // bilinear blend, two groups per instruction; per component the reference's order
+                // fma(se,wse, fma(sw,wsw, fma(ne,wne, nw*wnw)))
+                float2 t01 = __fmul2_rn(make_float2(nw.x, nw.y), Wnw), t23 = __fmul2_rn(make_float2(nw.z, nw.w), Wnw);
+                t01 = __ffma2_rn(make_float2(ne.x, ne.y), Wne, t01); t23 = __ffma2_rn(make_float2(ne.z, ne.w), Wne, t23);
+                t01 = __ffma2_rn(make_float2(sw.x, sw.y), Wsw, t01); t23 = __ffma2_rn(make_float2(sw.z, sw.w), Wsw, t23);
+                t01 = __ffma2_rn(make_float2(se.x, se.y), Wse, t01); t23 = __ffma2_rn(make_float2(se.z, se.w), Wse, t23);
+                // sigmoid(a-b) = 1 / (1 + 2^t).  t is capped so that (1+2^t0)(1+2^t1) cannot become inf * 0;
+                // beyond the cap the similarity is below 1e-18 either way.  One MUFU.RCP serves two groups:
+                // r = 1/(u0*u1), 1/u0 = r*u1, 1/u1 = r*u0.
+                const float2 one2 = make_float2(1.0f, 1.0f);
+                const float2 u01 = __fadd2_rn(make_float2(ex2_approx(fminf(t01.x, 62.0f)), ex2_approx(fminf(t01.y, 62.0f))), one2);
+                const float2 u23 = __fadd2_rn(make_float2(ex2_approx(fminf(t23.x, 62.0f)), ex2_approx(fminf(t23.y, 62.0f))), one2);
+                const float r01 = rcp_approx(u01.x * u01.y), r23 = rcp_approx(u23.x * u23.y);
+                const float2 p01 = __fmul2_rn(make_float2(r01, r01), make_float2(u01.y, u01.x));
+                const float2 p23 = __fmul2_rn(make_float2(r23, r23), make_float2(u23.y, u23.x));
+                p[2 * j] = p01; p[2 * j + 1] = p23;
+                z2 = __ffma2_rn(make_float2(c.x, c.y), p01, z2);
+                z2 = __ffma2_rn(make_float2(c.z, c.w), p23, z2);
+            }
+            const float z = z2.x + z2.y;
+            float h = fmaf(z, alpha, betap);              // BatchNorm3d (eval)
+            h = fmaxf(h, 0.0f);                           // ReLU
+            h = fmaf(h, fcw, fcb);                        // Conv3d(1,1,1)
+            const float w = rcp_approx(1.0f + ex2_approx(-kLog2e * h));   // Sigmoid
+            wsum[i] += w;
+            const float2 w2 = make_float2(w, w);
+#pragma unroll
+            for (int g = 0; g < G / 2; ++g) acc[i][g] = __ffma2_rn(w2, p[g], acc[i][g]);
         }
         return todo;
     };
 
     float ix[PT], iy[PT];
-    uint32_t todo = prepare_view(0, ix, iy);
+    uint32_t todo = positions(0, ix, iy, true);
+    announce(0, ix, iy, todo);
+    mbar_wait(bar0 + 24, 0);                     // q / cq tiles have landed
+    if (!Cfg::CQS) {
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const float4 c = lds128(cq_s + (uint32_t)j * TJ);
+            cq[(4 * j + 0) % NCQ] = c.x; cq[(4 * j + 1) % NCQ] = c.y; cq[(4 * j + 2) % NCQ] = c.z; cq[(4 * j + 3) % NCQ] = c.w;
+        }
+    }
 
+    // ---- main loop: no block-wide barrier; warps run freely, the box of view v+1 streams in while view v
+    //      is gathered ----
     for (int v = 0; v < a.V; ++v) {
-        // ---- 1. get view v+1 going: positions, bounding box, TMA load into the other buffer ----
         float nx[PT], ny[PT];
         uint32_t ntodo = 0;
-        if (v + 1 < a.V) ntodo = prepare_view(v + 1, nx, ny);
-
-        // ---- 2. gather view v: round 0 from the prefetched box, further rounds for samples outside it ----
-        const uint32_t box = box0 + (uint32_t)(v & 1) * Cfg::BOX_BYTES;
-        int ox, oy;
-        mbar_wait(bar0 + 8u * (v & 1), (uint32_t)(v >> 1) & 1u);
-        ox = ctl[kOrg0 + 2 * (v & 1)];
-        oy = ctl[kOrg0 + 2 * (v & 1) + 1];
-        while (true) {
-#pragma unroll
-            for (int i = 0; i < PT; ++i) {
-                if (!((todo >> i) & 1u)) continue;
-                float fx0, fy0;
-                int x0, y0;
-                floor_small(ix[i], fx0, x0);
-                floor_small(iy[i], fy0, y0);
-                const int rx = x0 - ox, ry = y0 - oy;
-                if ((unsigned)rx >= (unsigned)(BW - 1) || (unsigned)ry >= (unsigned)(BH - 1)) continue;   // next round
-                todo &= ~(1u << i);
-                const float ax = __fsub_rn(__fadd_rn(fx0, 1.0f), ix[i]), bx = __fsub_rn(ix[i], fx0);
-                const float ay = __fsub_rn(__fadd_rn(fy0, 1.0f), iy[i]), by = __fsub_rn(iy[i], fy0);
-                Taps t;
-                t.wnw = __fmul_rn(ax, ay); t.wne = __fmul_rn(bx, ay); t.wsw = __fmul_rn(ax, by); t.wse = __fmul_rn(bx, by);
-                const uint32_t addr = box + (uint32_t)(ry * BW + rx) * 16u;
-                float p[G];
-                float z = -ksum;
-#pragma unroll
-                for (int j = 0; j < J; ++j) {
-                    const float4 nw = lds128(addr + j * PLANE);                 // constant offsets -> LDS.128 [R + imm]
-                    const float4 ne = lds128(addr + j * PLANE + 16);
-                    const float4 sw = lds128(addr + j * PLANE + BW * 16);
-                    const float4 se = lds128(addr + j * PLANE + BW * 16 + 16);
-                    float4 c;
-                    if (Cfg::CQS) c = lds128(cq_s + (uint32_t)j * THREADS * 16u);
-                    else c = make_float4(cq[(4 * j + 0) % NCQ], cq[(4 * j + 1) % NCQ], cq[(4 * j + 2) % NCQ], cq[(4 * j + 3) % NCQ]);
-                    p[4 * j + 0] = rcp_approx(1.0f + ex2_approx(blend4(nw.x, ne.x, sw.x, se.x, t)));
-                    p[4 * j + 1] = rcp_approx(1.0f + ex2_approx(blend4(nw.y, ne.y, sw.y, se.y, t)));
-                    p[4 * j + 2] = rcp_approx(1.0f + ex2_approx(blend4(nw.z, ne.z, sw.z, se.z, t)));
-                    p[4 * j + 3] = rcp_approx(1.0f + ex2_approx(blend4(nw.w, ne.w, sw.w, se.w, t)));
-                    z = fmaf(c.x, p[4 * j + 0], z);
-                    z = fmaf(c.y, p[4 * j + 1], z);
-                    z = fmaf(c.z, p[4 * j + 2], z);
-                    z = fmaf(c.w, p[4 * j + 3], z);
-                }
-                float h = fmaf(z, alpha, betap);              // BatchNorm3d (eval)
-                h = fmaxf(h, 0.0f);                           // ReLU
-                h = fmaf(h, fcw, fcb);                        // Conv3d(1,1,1)
-                const float w = rcp_approx(1.0f + ex2_approx(-kLog2e * h));   // Sigmoid
-                wsum[i] += w;
-#pragma unroll
-                for (int g = 0; g < G; ++g) acc[i][g] = fmaf(w, p[g], acc[i][g]);
-            }
-            // everybody is done with this box; does any sample still wait for another one?
-            if (!__syncthreads_or(todo != 0u)) break;
-
-            // ---- retry round (rough depth maps, silhouettes): synchronous load into the same buffer.
-            // x origin = min over the samples left; y origin = min over those whose column fits, so the
-            // topmost of them lands inside the box and the loop always makes progress.
-            int* slot = ctl_nv + kRetry + 2 * (riter & 1u);
-            int kx = kNone;
-#pragma unroll
-            for (int i = 0; i < PT; ++i)
-                if ((todo >> i) & 1u) kx = min(kx, coord_key(ix[i]));
-            kx = __reduce_min_sync(0xffffffffu, kx);
-            if (lane == 0 && kx != kNone) atomicMin(slot, key_floor(kx));
-            if (tid == 0) { volatile int* other = ctl + kRetry + 2 * ((riter + 1u) & 1u); other[0] = kNone; other[1] = kNone; }
-            __syncthreads();
-            ox = ctl[kRetry + 2 * (riter & 1u)];
-            const float xlim = (float)(ox + BW - 1);
-            int m = kNone;
-#pragma unroll
-            for (int i = 0; i < PT; ++i)
-                if (((todo >> i) & 1u) && ix[i] < xlim) m = min(m, coord_key(iy[i]));
-            m = __reduce_min_sync(0xffffffffu, m);
-            if (lane == 0 && m != kNone) atomicMin(slot + 1, key_floor(m));
-            __syncthreads();
-            oy = ctl[kRetry + 2 * (riter & 1u) + 1];
-            if (tid == 0) {
-                mbar_expect_tx(bar0 + 16, Cfg::BOX_BYTES);
-                tma_load_3d(box, &tmap, bar0 + 16, ox * 2, oy, (v * a.B + b) * J);
-            }
-            mbar_wait(bar0 + 16, riter & 1u);
-            ++riter;
+        if (v + 1 < a.V) {
+            ntodo = positions(v + 1, nx, ny, true);
+            announce(v + 1, nx, ny, ntodo);
         }
+        mbar_wait(bar0 + 8u * (v & 1), (uint32_t)(v >> 1) & 1u);
+        const int ox = ctl[kOrg + 2 * v], oy = ctl[kOrg + 2 * v + 1];
+        todo = gather(box0 + (uint32_t)(v & 1) * Cfg::BOX_BYTES, ox, oy, ix, iy, todo);
+        if (todo != 0u) left |= 1u << v;
 #pragma unroll
         for (int i = 0; i < PT; ++i) { ix[i] = nx[i]; iy[i] = ny[i]; }
         todo = ntodo;
     }
 
-    // ---- 3. volume_sum / weight_sum (homoaggregate.py:46), coalesced 128-byte rows ----
+    // ---- samples that did not fit their view's box (rough depth maps, silhouettes): synchronous staging
+    //      rounds.  x origin = min over the samples left; y origin = min over those whose column fits, so the
+    //      topmost of them lands inside the box and every round makes progress. ----
+    if (__syncthreads_or(left != 0u)) {
+        if (left != 0u) atomicOr(ctl_nv + kLeft, (int)left);
+        __syncthreads();
+        uint32_t views = (uint32_t)ctl[kLeft];
+        uint32_t riter = 0;                          // CTA-uniform count of retry loads (mbarrier phase, slot)
+        while (views != 0u) {
+            const int v = __ffs(views) - 1;
+            views &= views - 1u;
+            todo = positions(v, ix, iy, false);
+            {   // drop what round 0 already gathered
+                const int ox0 = ctl[kOrg + 2 * v], oy0 = ctl[kOrg + 2 * v + 1];
+#pragma unroll
+                for (int i = 0; i < PT; ++i) {
+                    if (!((todo >> i) & 1u)) continue;
+                    float f; int x0, y0;
+                    floor_small(ix[i], f, x0);
+                    floor_small(iy[i], f, y0);
+                    if ((unsigned)(x0 - ox0) < (unsigned)(BW - 1) && (unsigned)(y0 - oy0) < (unsigned)(BH - 1)) todo &= ~(1u << i);
+                }
+            }
+            while (__syncthreads_or(todo != 0u)) {
+                int* slot = ctl_nv + kRetry + 2 * (riter & 1u);
+                int kx = kNone;
+#pragma unroll
+                for (int i = 0; i < PT; ++i)
+                    if ((todo >> i) & 1u) kx = min(kx, coord_key(ix[i]));
+                kx = __reduce_min_sync(0xffffffffu, kx);
+                if (lane == 0 && kx != kNone) atomicMin(slot, key_floor(kx));
+                if (tid == 0) { volatile int* other = ctl + kRetry + 2 * ((riter + 1u) & 1u); other[0] = kNone; other[1] = kNone; }
+                __syncthreads();
+                const int ox = ctl[kRetry + 2 * (riter & 1u)];
+                const float xlim = (float)(ox + BW - 1);
+                int m = kNone;
+#pragma unroll
+                for (int i = 0; i < PT; ++i)
+                    if (((todo >> i) & 1u) && ix[i] < xlim) m = min(m, coord_key(iy[i]));
+                m = __reduce_min_sync(0xffffffffu, m);
+                if (lane == 0 && m != kNone) atomicMin(slot + 1, key_floor(m));
+                __syncthreads();
+                const int oy = ctl[kRetry + 2 * (riter & 1u) + 1];
+                if (tid == 0) {
+                    mbar_expect_tx(bar0 + 16, Cfg::BOX_BYTES);
+                    tma_load_3d(box0, &maps.s4, bar0 + 16, ox * 2, oy, (v * a.B + b) * J);
+                }
+                mbar_wait(bar0 + 16, riter & 1u);
+                ++riter;
+                todo = gather(box0, ox, oy, ix, iy, todo);
+            }
+        }
+    }
+
+    // ---- volume_sum / weight_sum (homoaggregate.py:46), coalesced 128-byte rows ----
     const float w_void = __ldg(a.dwp + 5);       // view weight of a sample with no tap in bounds (similarity 0.5)
 #pragma unroll
     for (int i = 0; i < PT; ++i) {
         if (!((ok_mask >> i) & 1u)) continue;
         const float nv = (float)((unsigned)(n_void >> (8 * i)) & 255u);
         const float ws = fmaf(nv, w_void, wsum[i]);
-        const float half_void = 0.5f * nv * w_void;          // void samples: similarity 0.5 in every group
         const float rw = __frcp_rn(ws);
+        // out = 0.5 + q * ((acc + 0.5*nv*w_void) / ws - 0.5); void samples have similarity 0.5 in every group
+        const float c0 = fmaf(0.5f * nv * w_void, rw, -0.5f);
+        const float2 rw2 = make_float2(rw, rw), c02 = make_float2(c0, c0), half2 = make_float2(0.5f, 0.5f);
         float* op = a.out + (((size_t)b * G) * D + (d0 + i)) * HW + (size_t)py * W + px;
+        const size_t gstride = (size_t)D * HW;
 #pragma unroll
         for (int j = 0; j < J; ++j) {
-            const float4 q = __ldg(qp + (size_t)j * HW);
-            op[(size_t)(4 * j + 0) * D * HW] = fmaf(q.x, fmaf(acc[i][4 * j + 0] + half_void, rw, -0.5f), 0.5f);
-            op[(size_t)(4 * j + 1) * D * HW] = fmaf(q.y, fmaf(acc[i][4 * j + 1] + half_void, rw, -0.5f), 0.5f);
-            op[(size_t)(4 * j + 2) * D * HW] = fmaf(q.z, fmaf(acc[i][4 * j + 2] + half_void, rw, -0.5f), 0.5f);
-            op[(size_t)(4 * j + 3) * D * HW] = fmaf(q.w, fmaf(acc[i][4 * j + 3] + half_void, rw, -0.5f), 0.5f);
+            const float4 q = lds128(q_s + (uint32_t)j * TJ);
+            const float2 o01 = __ffma2_rn(make_float2(q.x, q.y), __ffma2_rn(acc[i][2 * j], rw2, c02), half2);
+            const float2 o23 = __ffma2_rn(make_float2(q.z, q.w), __ffma2_rn(acc[i][2 * j + 1], rw2, c02), half2);
+            op[0] = o01.x; op[gstride] = o01.y; op[2 * gstride] = o23.x; op[3 * gstride] = o23.y;
+            op += 4 * gstride;
         }
     }
 }
@@ -452,23 +514,33 @@ static EncodeTiledFn get_encode_fn()
     return fn;
 }
 
-template <class Cfg>
-static int launch_staged(const StagedArgs& args, const float* S4, cudaStream_t stream)
+static int encode_planes(CUtensorMap* tmap, const float* base, int W, int H, long long planes, int box_w, int box_h, int box_planes)
 {
     EncodeTiledFn encode = get_encode_fn();
     if (encode == nullptr) return MDF_ERR_UNSUPPORTED;
-    // 3-D view of S4[(v*B+b)*J + j][y][x] (16-byte texels) in 8-byte elements: dim0 = 2*W, dim1 = H rows,
-    // dim2 = planes.  (8-byte elements because a box dimension is limited to 256 elements.)
-    CUtensorMap tmap;
-    const cuuint64_t planes = (cuuint64_t)args.V * args.B * Cfg::J;
-    const cuuint64_t dims[3] = {(cuuint64_t)args.W * 2, (cuuint64_t)args.H, planes};
-    const cuuint64_t strides[2] = {(cuuint64_t)args.W * 16, (cuuint64_t)args.H * args.W * 16};
-    const cuuint32_t box[3] = {(cuuint32_t)Cfg::BW * 2, (cuuint32_t)Cfg::BH, (cuuint32_t)Cfg::J};
+    // 3-D view of float4 planes [plane][y][x] in 8-byte elements: dim0 = 2*W, dim1 = H rows, dim2 = planes.
+    // (8-byte elements because a box dimension is limited to 256 elements.)
+    const cuuint64_t dims[3] = {(cuuint64_t)W * 2, (cuuint64_t)H, (cuuint64_t)planes};
+    const cuuint64_t strides[2] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
+    const cuuint32_t box[3] = {(cuuint32_t)box_w * 2, (cuuint32_t)box_h, (cuuint32_t)box_planes};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
-    CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<float*>(S4), dims, strides, box, estr,
+    CUresult r = encode(tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<float*>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { g_last_cuda_error = (int)r; return MDF_ERR_CUDA; }
+    return MDF_OK;
+}
+
+struct StagedBuffers { const float* S4; const float* Q4; const float* CQ4; };
+
+template <class Cfg>
+static int launch_staged(const StagedArgs& args, const StagedBuffers& buf, cudaStream_t stream)
+{
+    StagedMaps maps;
+    int st = encode_planes(&maps.s4, buf.S4, args.W, args.H, (long long)args.V * args.B * Cfg::J, Cfg::BW, Cfg::BH, Cfg::J);
+    if (st == MDF_OK) st = encode_planes(&maps.q4, buf.Q4, args.W, args.H, (long long)args.B * Cfg::J, 32, Cfg::TH, Cfg::J);
+    if (st == MDF_OK) st = encode_planes(&maps.cq4, buf.CQ4, args.W, args.H, (long long)args.B * Cfg::J, 32, Cfg::TH, Cfg::J);
+    if (st != MDF_OK) return st;
     auto kern = cost_volume_staged_kernel<Cfg>;
     MDF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     StagedArgs a = args;
@@ -479,26 +551,26 @@ static int launch_staged(const StagedArgs& args, const float* S4, cudaStream_t s
     const long long items = (long long)a.tiles_x * a.tiles_y * a.slabs * a.B;
     if (items <= 0) return MDF_OK;
     if (items > INT_MAX) return MDF_ERR_UNSUPPORTED;
-    kern<<<(unsigned)items, dim3(32, Cfg::TH, Cfg::PG), Cfg::SMEM, stream>>>(tmap, a);
+    kern<<<(unsigned)items, dim3(32, Cfg::TH, Cfg::PG), Cfg::SMEM, stream>>>(maps, a);
     return launch_status();
 }
 
 // Tuning variants per G (algo = 16 + k selects variant k; variant 0 is the default).
 //                         G  PT TH PG  BW  BH MINB CQS
-using CfgG32_0 = StagedCfg<32, 1, 4, 2, 40, 7, 2, true>;     // 256 thr, 2 x 35 KiB boxes + cq 32 KiB = 104 KiB, slab 2 planes
-using CfgG32_1 = StagedCfg<32, 1, 2, 4, 40, 6, 2, true>;     // tile 32x2, slab 4 planes
-using CfgG32_2 = StagedCfg<32, 1, 4, 4, 40, 8, 1, true>;     // 512 thr, slab 4 planes
-using CfgG32_3 = StagedCfg<32, 1, 4, 1, 40, 8, 3, false>;    // 128 thr x 3
+using CfgG32_0 = StagedCfg<32, 1, 4, 2, 40, 7, 2, true>;     // 256 thr x 2 CTAs; 2 x 35 KiB boxes + 2 x 16 KiB tiles
+using CfgG32_1 = StagedCfg<32, 1, 4, 2, 40, 8, 2, true>;     // 2 x 40 KiB boxes
+using CfgG32_2 = StagedCfg<32, 1, 2, 4, 40, 6, 2, true>;     // tile 32x2, slab 4 planes
+using CfgG32_3 = StagedCfg<32, 1, 4, 1, 40, 7, 4, true>;     // 128 thr x 4 CTAs
 using CfgG16_0 = StagedCfg<16, 2, 4, 2, 64, 8, 2, false>;    // 256 thr x 2 CTAs, 2 x 32 KiB boxes, slab 4 planes
-using CfgG16_1 = StagedCfg<16, 4, 4, 2, 64, 8, 2, true>;     // slab 8 planes
-using CfgG16_2 = StagedCfg<16, 2, 4, 2, 48, 8, 3, true>;     // 3 CTAs (85 registers)
-using CfgG16_3 = StagedCfg<16, 1, 4, 2, 48, 8, 3, false>;    // slab 2 planes
+using CfgG16_1 = StagedCfg<16, 1, 4, 2, 48, 8, 3, false>;    // 3 CTAs (85 registers), slab 2 planes
+using CfgG16_2 = StagedCfg<16, 2, 4, 1, 64, 8, 4, false>;    // 128 thr x 4 CTAs, slab 2 planes
+using CfgG16_3 = StagedCfg<16, 4, 4, 2, 64, 8, 2, true>;     // slab 8 planes
 using CfgG8_0  = StagedCfg<8, 4, 4, 2, 64, 10, 2, false>;    // 256 thr x 2 CTAs, 2 x 20 KiB boxes, slab 8 planes
-using CfgG8_1  = StagedCfg<8, 4, 8, 1, 64, 12, 2, false>;    // tile 32x8, slab 4 planes
-using CfgG8_2  = StagedCfg<8, 2, 4, 2, 64, 10, 3, false>;    // 3 CTAs, slab 4 planes
-using CfgG8_3  = StagedCfg<8, 8, 4, 1, 64, 10, 4, false>;    // 128 thr x 4 CTAs, slab 8 planes
+using CfgG8_1  = StagedCfg<8, 2, 4, 2, 64, 10, 3, false>;    // 3 CTAs, slab 4 planes
+using CfgG8_2  = StagedCfg<8, 4, 4, 1, 64, 10, 4, false>;    // 128 thr x 4 CTAs, slab 4 planes
+using CfgG8_3  = StagedCfg<8, 8, 4, 1, 64, 10, 2, false>;    // 128 thr, slab 8 planes
 
-static int launch_staged_variant(int G, int variant, const StagedArgs& a, const float* S, cudaStream_t stream)
+static int launch_staged_variant(int G, int variant, const StagedArgs& a, const StagedBuffers& S, cudaStream_t stream)
 {
     if (G == 32) {
         switch (variant) {

@@ -118,6 +118,63 @@ def pixel_hypos(batch: int, ndepths: int, h: int, w: int, seed: int = 3,
     return np.clip(hyp, np.float32(dmin), np.float32(dmax)).astype(np.float32)
 
 
+def _upsample2x_bilinear(a: np.ndarray) -> np.ndarray:
+    """(B,1,h,w) -> (B,1,2h,2w), F.interpolate(scale_factor=2, mode='bilinear', align_corners=False) semantics:
+    the way the reference carries depth / interval maps to the next stage (depthhypos.py:42-52)."""
+    def up(x, axis):
+        n = x.shape[axis]
+        pos = (np.arange(2 * n, dtype=np.float32) + 0.5) / 2.0 - 0.5
+        pos = np.clip(pos, 0.0, n - 1)
+        i0 = np.floor(pos).astype(np.int64)
+        i1 = np.minimum(i0 + 1, n - 1)
+        w1 = (pos - i0).astype(np.float32)
+        shape = [1] * x.ndim
+        shape[axis] = 2 * n
+        w1 = w1.reshape(shape)
+        return np.take(x, i0, axis=axis) * (1.0 - w1) + np.take(x, i1, axis=axis) * w1
+    return up(up(a, 2), 3).astype(np.float32)
+
+
+def scene_depth(batch: int, h: int, w: int, seed: int = 6) -> np.ndarray:
+    """A DTU-like synthetic scene as a depth map (B,1,h,w) in mm: a slanted background plane around 780 mm
+    and a few ellipsoidal objects (520-640 mm at the centre, bowl shaped, 50-200 mm silhouette jumps),
+    with fine surface relief.  Evaluated analytically in normalised image coordinates, so every
+    resolution sees the same scene."""
+    rng = np.random.default_rng(seed)
+    v, u = np.meshgrid((np.arange(h, dtype=np.float32) + 0.5) / h, (np.arange(w, dtype=np.float32) + 0.5) / w, indexing="ij")
+    out = np.empty((batch, 1, h, w), np.float32)
+    for b in range(batch):
+        z = 780.0 + 60.0 * (u - 0.5) - 40.0 * (v - 0.5) + 3.0 * np.sin(40.0 * u + b) * np.cos(35.0 * v)
+        for _ in range(4):
+            cu, cv = rng.uniform(0.2, 0.8), rng.uniform(0.25, 0.75)
+            ru, rv = rng.uniform(0.10, 0.28), rng.uniform(0.12, 0.30)
+            peak = rng.uniform(520.0, 640.0)
+            rr = ((u - cu) / ru) ** 2 + ((v - cv) / rv) ** 2
+            obj = peak + 90.0 * rr + 2.0 * np.sin(90.0 * u) * np.sin(80.0 * v)
+            z = np.where(rr < 1.0, np.minimum(z, obj), z)
+        out[b, 0] = z
+    return out
+
+
+def scene_hypos(batch: int, ndepths: int, h: int, w: int, seed: int = 6, dmin: float = DTU_DEPTH_RANGE[0],
+                dmax: float = DTU_DEPTH_RANGE[1], range_mm: Tuple[float, float] = (8.0, 30.0)) -> np.ndarray:
+    """Stage-1/2 hypotheses (B,D,H,W) the way the reference forms them (depthhypos.py:40-74): the depth and
+    the per-pixel search range of the previous (half resolution) stage are bilinearly upsampled x2, then
+    d - r/2 + k*r/(D-1), clamped to the depth range.  The previous stage's depth is `scene_depth` at half
+    resolution; the range varies smoothly between range_mm[0] and range_mm[1]."""
+    rng = np.random.default_rng(seed + 1)
+    hh, hw = (h + 1) // 2, (w + 1) // 2
+    d0 = _upsample2x_bilinear(scene_depth(batch, hh, hw, seed))[:, :, :h, :w]
+    v, u = np.meshgrid(np.linspace(0, 1, hh, dtype=np.float32), np.linspace(0, 1, hw, dtype=np.float32), indexing="ij")
+    ph = rng.uniform(0, 6.28, 4)
+    t = 0.5 + 0.25 * np.sin(5.0 * u + ph[0]) * np.cos(4.0 * v + ph[1]) + 0.25 * np.sin(9.0 * v + ph[2]) * np.cos(7.0 * u + ph[3])
+    r = (range_mm[0] + (range_mm[1] - range_mm[0]) * t).astype(np.float32)
+    r = _upsample2x_bilinear(np.broadcast_to(r, (batch, 1, hh, hw)).copy())[:, :, :h, :w]
+    k = np.arange(ndepths, dtype=np.float32).reshape(1, ndepths, 1, 1)
+    hyp = d0 - np.float32(0.5) * r + k * (r / np.float32(ndepths - 1))
+    return np.clip(hyp, np.float32(dmin), np.float32(dmax)).astype(np.float32)
+
+
 def depth_weight_params(groups: int, seed: int = 4) -> dict:
     """Non-degenerate depth_weight parameters (homoaggregate.py:16-20)."""
     rng = np.random.default_rng(seed)

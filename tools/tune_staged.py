@@ -20,7 +20,7 @@ cvb, _ = bench.algorithmic_bytes(h0, w0, nviews, batch)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for s, st in enumerate(view):
     if rough and s > 0:
-        st["hypos"] = syn.pixel_hypos(batch, st["D"], st["H"], st["W"], seed=5, smooth=False)
+        st["hypos"] = syn.pixel_hypos(batch, st["D"], st["H"], st["W"], seed=5, smooth="iid" not in sys.argv)
     p = st["params"]
     f32 = lambda v: cu(np.asarray(v, np.float32).reshape(-1))
     args = ([cu(f) for f in st["features"]], cu(st["ref_proj"]), [cu(q) for q in st["src_projs"]], cu(st["hypos"]),
