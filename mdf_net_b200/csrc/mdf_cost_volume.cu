@@ -19,6 +19,7 @@
 
 #include "mdf_common.cuh"
 #include "mdf_host.cuh"
+#include "mdf_setup.cuh"
 #include "mdf_staged.cuh"
 
 namespace mdf {
@@ -55,73 +56,6 @@ static Workspace make_workspace(int B, int N, int G, int H, int W, bool staged)
     if (staged) off = align_up(off + (size_t)B * H * W * sizeof(float), 256);
     w.total = off;
     return w;
-}
-
-struct SrcPtrs { const float* p[kMaxSrcViews]; };
-
-// ------------------------------------------------------------------------------------------------
-// setup: projections + folded depth_weight parameters
-// ------------------------------------------------------------------------------------------------
-__device__ void compose_proj_f64(const float* __restrict__ src, const float* __restrict__ ref, float* __restrict__ out12)
-{
-    // Gauss-Jordan with partial pivoting in float64, then rows 0..2 of src @ inv(ref), rounded once.
-    double a[4][8];
-    for (int r = 0; r < 4; ++r)
-        for (int c = 0; c < 4; ++c) { a[r][c] = (double)ref[r * 4 + c]; a[r][4 + c] = (r == c) ? 1.0 : 0.0; }
-    for (int k = 0; k < 4; ++k) {
-        int p = k; double best = fabs(a[k][k]);
-        for (int r = k + 1; r < 4; ++r) { double v = fabs(a[r][k]); if (v > best) { best = v; p = r; } }
-        if (p != k) for (int c = 0; c < 8; ++c) { double t = a[k][c]; a[k][c] = a[p][c]; a[p][c] = t; }
-        const double inv = 1.0 / a[k][k];
-        for (int c = 0; c < 8; ++c) a[k][c] *= inv;
-        for (int r = 0; r < 4; ++r) {
-            if (r == k) continue;
-            const double f = a[r][k];
-            for (int c = 0; c < 8; ++c) a[r][c] -= f * a[k][c];
-        }
-    }
-    for (int r = 0; r < 3; ++r) {
-        double row[4];
-        for (int c = 0; c < 4; ++c) {
-            double acc = 0.0;
-            for (int k = 0; k < 4; ++k) acc += (double)src[r * 4 + k] * a[k][4 + c];
-            row[c] = acc;
-        }
-        out12[r * 3 + 0] = (float)row[0]; out12[r * 3 + 1] = (float)row[1]; out12[r * 3 + 2] = (float)row[2];
-        out12[9 + r] = (float)row[3];
-    }
-}
-
-__global__ void setup_kernel(SrcPtrs src_projs, const float* __restrict__ ref_proj, int V, int B,
-                             float* __restrict__ rt_all,
-                             const float* __restrict__ conv_w, const float* __restrict__ bn_w,
-                             const float* __restrict__ bn_b, const float* __restrict__ bn_mean,
-                             const float* __restrict__ bn_var, float bn_eps,
-                             const float* __restrict__ fc_w, const float* __restrict__ fc_b, int G,
-                             float* __restrict__ dwp)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < V * B) {
-        const int v = i / B, b = i % B;
-        compose_proj_f64(src_projs.p[v] + 16 * b, ref_proj + 16 * b, rt_all + (size_t)i * 12);
-    }
-    if (i == 0 && dwp != nullptr) {
-        // eval-mode BatchNorm3d(1) folded as ATen applies it: alpha = weight/sqrt(var+eps), beta = bias - mean*alpha
-        const float invstd = __frcp_rn(__fsqrt_rn(__fadd_rn(bn_var[0], bn_eps)));
-        const float alpha = __fmul_rn(invstd, bn_w[0]);
-        const float beta = __fsub_rn(bn_b[0], __fmul_rn(bn_mean[0], alpha));
-        float cw_sum = 0.0f;
-        for (int g = 0; g < G; ++g) cw_sum += conv_w[g];
-        dwp[0] = alpha;
-        dwp[1] = beta + alpha * 0.5f * cw_sum;   // staged kernel accumulates sum_g cw_g*(vol_g - 0.5)
-        dwp[2] = fc_w[0];
-        dwp[3] = fc_b[0];
-        dwp[4] = beta;
-        for (int g = 0; g < G && g < 32; ++g) dwp[16 + g] = conv_w[g];   // 16-byte aligned copy for float4 loads
-        // weight of a (sample, view) pair whose taps all fall outside the source image: every similarity is 0.5
-        const float hv = fmaf(fmaxf(dwp[1], 0.0f), fc_w[0], fc_b[0]);
-        dwp[5] = 1.0f / (1.0f + expf(-hv));
-    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -326,8 +260,8 @@ static int run_setup(const float* const* src_projs, const float* ref_proj, int V
     SrcPtrs sp;
     for (int v = 0; v < kMaxSrcViews; ++v) sp.p[v] = v < V ? src_projs[v] : nullptr;
     const int n = V * B;
-    setup_kernel<<<(n + 63) / 64, 64, 0, stream>>>(sp, ref_proj, V, B, rt, conv_w, bn_w, bn_b, bn_mean, bn_var, bn_eps,
-                                                   fc_w, fc_b, G, dwp);
+    const DepthWeightPtrs dw = {conv_w, bn_w, bn_b, bn_mean, bn_var, fc_w, fc_b, bn_eps};
+    setup_kernel<<<(n + 63) / 64, 64, 0, stream>>>(sp, ref_proj, V, B, rt, dw, G, dwp);
     return launch_status();
 }
 
@@ -402,9 +336,12 @@ int mdf_cost_volume_fwd_ex(const float* const* features, int N, const float* ref
     uint8_t* wsb = static_cast<uint8_t*>(workspace);
     float* rt = reinterpret_cast<float*>(wsb + ws.rt_off);
     float* dwp = reinterpret_cast<float*>(wsb + ws.dwp_off);
-    int st = run_setup(src_projs, ref_proj, V, B, rt, conv_weight, bn_weight, bn_bias, bn_mean, bn_var, bn_eps,
+    int st = MDF_OK;
+    if (!staged) {   // (the staged path does this work inside its prep kernel)
+        st = run_setup(src_projs, ref_proj, V, B, rt, conv_weight, bn_weight, bn_bias, bn_mean, bn_var, bn_eps,
                        fc_weight, fc_bias, G, dwp, stream);
-    if (st != MDF_OK) return st;
+        if (st != MDF_OK) return st;
+    }
 
     if (!staged) {
         DirectArgs a;
@@ -424,8 +361,12 @@ int mdf_cost_volume_fwd_ex(const float* const* features, int N, const float* ref
         FeaPtrs fp;
         for (int i = 0; i < MDF_MAX_VIEWS; ++i) fp.p[i] = i < N ? features[i] : nullptr;
         const long long HW = (long long)H * W;
-        if (HW > INT_MAX - 256 || (long long)N * B > 65535) return MDF_ERR_UNSUPPORTED;
-        prep_kernel<<<dim3((unsigned)((HW + 255) / 256), (unsigned)(N * B)), 256, 0, stream>>>(fp, B, G, (int)HW, dwp + 16, Q4, CQ4, KS, S4);
+        if (HW > INT_MAX - 256 || (long long)N * B > 65535 || (long long)V * B > 256) return MDF_ERR_UNSUPPORTED;
+        PrepSetup su;
+        for (int v = 0; v < kMaxSrcViews; ++v) su.src_projs.p[v] = v < V ? src_projs[v] : nullptr;
+        su.ref_proj = ref_proj; su.V = V; su.rt = rt; su.dwp = dwp;
+        su.dw = {conv_weight, bn_weight, bn_bias, bn_mean, bn_var, fc_weight, fc_bias, bn_eps};
+        prep_kernel<<<dim3((unsigned)((HW + 255) / 256), (unsigned)(N * B)), 256, 0, stream>>>(fp, B, G, (int)HW, su, Q4, CQ4, KS, S4);
         st = launch_status();
         if (st != MDF_OK) return st;
     }

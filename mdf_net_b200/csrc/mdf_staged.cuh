@@ -1,6 +1,7 @@
 // mdf_staged.cuh -- the hot kernel of the plane-sweep cost volume (C/G == 2) and its layout pass.
 //
-//   prep_kernel             source features NCHW -> "pair difference" maps in planar-float4 layout
+//   prep_kernel             (also does the per-call scalar work of mdf_setup.cuh in its first block)
+//                           source features NCHW -> "pair difference" maps in planar-float4 layout
 //                           S4[v][b][j][y][x] = (f[2g+1]-f[2g])*log2(e) for g = 4j..4j+3, and the reference
 //                           view -> q = 2*sigmoid(r[2g]-r[2g+1]) - 1.  softmax([a,b]) = [sigmoid(a-b),
 //                           1-sigmoid(a-b)] and bilinear sampling is linear, so gathering the difference
@@ -27,6 +28,7 @@
 
 #include "mdf_common.cuh"
 #include "mdf_host.cuh"
+#include "mdf_setup.cuh"
 
 namespace mdf {
 
@@ -36,10 +38,22 @@ struct FeaPtrs { const float* p[MDF_MAX_VIEWS]; };
 // prep: one thread per pixel of one view; blockIdx.y = view * B + b.
 // Loads are 128-byte coalesced rows of the NCHW planes, stores are 512-byte coalesced float4 rows.
 // ------------------------------------------------------------------------------------------------
+struct PrepSetup {          // the per-call scalar work (mdf_setup.cuh) rides along in block (0,0)
+    SrcPtrs src_projs;
+    const float* ref_proj;
+    int V;
+    float* rt;
+    float* dwp;
+    DepthWeightPtrs dw;
+};
+
 __global__ void __launch_bounds__(256)
-prep_kernel(FeaPtrs feas, int B, int G, int HW, const float* __restrict__ conv_w /* 16-byte aligned */,
+prep_kernel(FeaPtrs feas, int B, int G, int HW, PrepSetup su,
             float4* __restrict__ Q4, float4* __restrict__ CQ4, float* __restrict__ KS, float4* __restrict__ S4)
 {
+    if (blockIdx.x == 0 && blockIdx.y == 0)
+        setup_work(threadIdx.x, su.src_projs, su.ref_proj, su.V, B, su.rt, su.dw, G, su.dwp);
+    const float* __restrict__ conv_w = su.dw.conv_w;
     const int pix = blockIdx.x * blockDim.x + threadIdx.x;
     if (pix >= HW) return;
     const int v = blockIdx.y / B, b = blockIdx.y % B;
@@ -57,8 +71,8 @@ prep_kernel(FeaPtrs feas, int B, int G, int HW, const float* __restrict__ conv_w
                 const float a = __ldg(f + (size_t)(8 * j + 2 * k) * HW), c = __ldg(f + (size_t)(8 * j + 2 * k + 1) * HW);
                 d[k] = 2.0f / (1.0f + expf(c - a)) - 1.0f;
             }
-            const float4 cw = __ldg(reinterpret_cast<const float4*>(conv_w) + j);
-            const float4 c = make_float4(cw.x * d[0], cw.y * d[1], cw.z * d[2], cw.w * d[3]);
+            const float4 c = make_float4(__ldg(conv_w + 4 * j) * d[0], __ldg(conv_w + 4 * j + 1) * d[1],
+                                         __ldg(conv_w + 4 * j + 2) * d[2], __ldg(conv_w + 4 * j + 3) * d[3]);
             qd[(size_t)j * HW] = make_float4(d[0], d[1], d[2], d[3]);
             cd[(size_t)j * HW] = c;
             ks += (c.x + c.y) + (c.z + c.w);

@@ -28,8 +28,8 @@ __all__ = ["cost_volume", "homo_warp", "variance_volume", "softmax_regress", "de
 # kernels launched through this module since the last reset (bench.py's `gpu_launches`)
 _launches = 0
 
-# kernel launches per C-ABI call (setup + prep + hot kernel, see csrc/*.cu)
-_LAUNCHES_STAGED, _LAUNCHES_DIRECT, _LAUNCHES_SIMPLE = 3, 2, 1
+# kernel launches per C-ABI call (staged: prep [+ setup work] + hot kernel; direct: setup + kernel; see csrc/*.cu)
+_LAUNCHES_STAGED, _LAUNCHES_DIRECT, _LAUNCHES_SIMPLE = 2, 2, 1
 
 
 def launch_count() -> int:
