@@ -105,6 +105,35 @@ MDF_API int mdf_cost_volume_fwd_ex(const float *const *features, int N, const fl
                            int B, int C, int G, int D, int H, int W, float *cost_volume,
                            void *workspace, size_t workspace_bytes, int algo, mdf_stream_t stream);
 
+/* ---- VectorAggregate under autograd / in train mode (C == 2*G, G in {8,16,32}) ---------------
+ * Reference: net/unit/homoaggregate.py:25-46 driven by torch autograd (train.py:33-50).
+ * training != 0: BatchNorm3d uses the batch statistics of each source view's z over (B,D,H,W) (the module is
+ * applied once per view, homoaggregate.py:40); `batch_stats` (device, (N-1,2) floats, may be NULL) receives
+ * (mean, unbiased variance) per view so that the caller can apply the momentum update of the running
+ * statistics in view order.  training == 0: running statistics (the gradient of an eval-mode forward).
+ * Gradients: `grad_features` is a HOST array of N device pointers (each (B,C,H,W), overwritten; an entry may
+ * be NULL to skip that view); `grad_params` (device, 4+G floats) = d bn.weight, d bn.bias, d fc.weight,
+ * d fc.bias, d conv.weight[G].  Projections and hypotheses get no gradient (base.py:97 is under no_grad). */
+MDF_API size_t mdf_cost_volume_train_workspace_bytes(int B, int N, int C, int G, int D, int H, int W);
+
+MDF_API int mdf_cost_volume_train_fwd(const float *const *features, int N, const float *ref_proj,
+                                      const float *const *src_projs, const float *depth_hypos, int hypos_per_pixel,
+                                      const float *conv_weight, const float *bn_weight, const float *bn_bias,
+                                      const float *bn_mean, const float *bn_var, float bn_eps,
+                                      const float *fc_weight, const float *fc_bias, int training,
+                                      int B, int C, int G, int D, int H, int W, float *cost_volume,
+                                      float *batch_stats, void *workspace, size_t workspace_bytes, mdf_stream_t stream);
+
+MDF_API int mdf_cost_volume_bwd(const float *const *features, int N, const float *ref_proj,
+                                const float *const *src_projs, const float *depth_hypos, int hypos_per_pixel,
+                                const float *conv_weight, const float *bn_weight, const float *bn_bias,
+                                const float *bn_mean, const float *bn_var, float bn_eps,
+                                const float *fc_weight, const float *fc_bias, int training,
+                                int B, int C, int G, int D, int H, int W,
+                                const float *cost_volume /* saved forward output */, const float *grad_out,
+                                float *const *grad_features, float *grad_params,
+                                void *workspace, size_t workspace_bytes, mdf_stream_t stream);
+
 /* ---- homo_aggregate_by_variance -> (B,C,D,H,W) ---------------------------------------------- */
 MDF_API size_t mdf_variance_volume_workspace_bytes(int B, int N, int C, int D, int H, int W);
 

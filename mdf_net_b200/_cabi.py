@@ -38,6 +38,11 @@ SIGNATURES = {
     "mdf_softmax_regress_fwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P]),
     "mdf_depth_regression_fwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "mdf_confidence_fwd": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "mdf_cost_volume_train_workspace_bytes": (c_size_t, [_I] * 7),
+    "mdf_cost_volume_train_fwd": (_I, [_P, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P, c_float, _P, _P, _I,
+                                       _I, _I, _I, _I, _I, _I, _P, _P, _P, c_size_t, _P]),
+    "mdf_cost_volume_bwd": (_I, [_P, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P, c_float, _P, _P, _I,
+                                 _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, c_size_t, _P]),
     "mdf_debug_sample_positions": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
 }
 

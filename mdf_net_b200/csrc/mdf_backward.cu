@@ -1,0 +1,661 @@
+// mdf_backward.cu -- train-mode forward and the backward pass of the fused cost volume (C/G == 2).
+//
+// Reference: VectorAggregate.forward under autograd (net/unit/homoaggregate.py:25-46), with
+// depth_weight = Conv3d(G,1,k=1) - BatchNorm3d(1) - ReLU - Conv3d(1,1,k=1) - Sigmoid (:16-20; base.py:50-68).
+// Gradients flow to every feature map and to the 5 depth_weight parameters; the sampling grid is built
+// under no_grad (base.py:97), so projections and hypotheses get none.  In train mode BatchNorm3d uses the
+// statistics of z_v over (B,D,H,W), separately for every source view (the module is called once per view),
+// which makes forward and backward two-phase: a statistics sweep, then the sweep that uses them.
+//
+// Notation per (b,d,y,x) and source view v:
+//   t_vg  = bilinear sample of S_v (S = (f[2g+1]-f[2g])*log2e)      p_vg = 1/(1+2^t_vg)
+//   sim_vg = 0.5 + q_g (p_vg - 0.5)      z_v = sum_g cw_g sim_vg     h_v = a_v z_v + b_v   (BatchNorm)
+//   w_v = sigmoid(fcw*relu(h_v) + fcb)   out_g = sum_v w_v sim_vg / sum_v w_v
+//
+// These kernels are the simple, correct version of the training path: one thread per (b,d,y,x), taps through
+// L1/L2 straight from the planar-float4 maps the prep kernel writes.  (The eval-mode forward is the tuned
+// TMA-staged kernel of mdf_staged.cuh.)  Feature gradients are scattered with 128-bit vector reductions
+// (red.global.add.v4.f32) into a difference-gradient map dS4 -- half the atomics of scattering into both
+// channels of a pair -- and a finishing kernel turns dS4 / dQ4 into NCHW feature gradients.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mdf_common.cuh"
+#include "mdf_host.cuh"
+#include "mdf_setup.cuh"
+#include "mdf_staged.cuh"   // FeaPtrs, prep_kernel
+
+namespace mdf {
+
+constexpr float kLn2 = 0.6931471805599453f;
+
+struct TrainArgs {
+    const float4* S4;     // [V][B][J][H][W]
+    const float4* Q4;     // [B][J][H][W]
+    const float* rt;      // [V][B][12]
+    const float* cw;      // (G,)
+    const float* bnv;     // [V][4]: a_v, b_v (h = a z + b), 1/sqrt(var+eps), mean   (written by bn_fold_kernel)
+    const float* fc;      // [2]: fcw, fcb  (device copies)
+    const float* hypos;
+    int per_pixel, V, B, D, H, W;
+};
+
+__device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+
+// bilinear sample of one float4 plane with zero padding, per component in the reference's tap order
+__device__ __forceinline__ float4 sample4(const float4* __restrict__ plane, int H, int W, const Taps& t)
+{
+    const bool x0in = (unsigned)t.x0 < (unsigned)W, x1in = (unsigned)(t.x0 + 1) < (unsigned)W;
+    const bool y0in = (unsigned)t.y0 < (unsigned)H, y1in = (unsigned)(t.y0 + 1) < (unsigned)H;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* p = plane + (ptrdiff_t)t.y0 * W + t.x0;
+    const float4 nw = (x0in && y0in) ? ldg4(p) : zero, ne = (x1in && y0in) ? ldg4(p + 1) : zero;
+    const float4 sw = (x0in && y1in) ? ldg4(p + W) : zero, se = (x1in && y1in) ? ldg4(p + W + 1) : zero;
+    return make_float4(blend4(nw.x, ne.x, sw.x, se.x, t), blend4(nw.y, ne.y, sw.y, se.y, t),
+                       blend4(nw.z, ne.z, sw.z, se.z, t), blend4(nw.w, ne.w, sw.w, se.w, t));
+}
+
+__device__ __forceinline__ float sigm2(float t) { return 1.0f / (1.0f + exp2f(t)); }     // 1/(1+2^t)
+
+struct Elem { int x, y, d, b; size_t pix; float depth; bool ok; };
+
+__device__ __forceinline__ Elem decode(const TrainArgs& a)
+{
+    Elem e;
+    const size_t HW = (size_t)a.H * a.W;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    e.ok = idx < (size_t)a.B * a.D * HW;
+    const size_t i = e.ok ? idx : 0;
+    e.x = (int)(i % a.W);
+    e.y = (int)((i / a.W) % a.H);
+    e.d = (int)((i / HW) % a.D);
+    e.b = (int)(i / (HW * a.D));
+    e.pix = (size_t)e.y * a.W + e.x;
+    e.depth = a.per_pixel ? __ldg(a.hypos + ((size_t)e.b * a.D + e.d) * HW + e.pix) : __ldg(a.hypos + (size_t)e.b * a.D + e.d);
+    return e;
+}
+
+__device__ __forceinline__ Taps taps_of(const TrainArgs& a, const Elem& e, int v, const GridNorm& gn)
+{
+    const float* rt = a.rt + ((size_t)v * a.B + e.b) * 12;
+    float ix, iy;
+    sample_position(rot_xyz(rt, (float)e.x, (float)e.y), rt, e.depth, gn, ix, iy);
+    return make_taps(ix, iy, gn);
+}
+
+// z_v of one element (and optionally A'_v = sum_g gout_g sim_vg)
+template <int G>
+__device__ __forceinline__ float view_z(const TrainArgs& a, const Elem& e, int v, const Taps& t, const float4* __restrict__ q4,
+                                        const float* __restrict__ gout /* registers or nullptr */, float* aprime)
+{
+    constexpr int J = G / 4;
+    const size_t HW = (size_t)a.H * a.W;
+    const float4* Sv = a.S4 + ((size_t)v * a.B + e.b) * J * HW;
+    float z = 0.0f, ap = 0.0f;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        float4 tt = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t.valid) tt = sample4(Sv + (size_t)j * HW, a.H, a.W, t);
+        const float4 q = q4[j];
+        const float s0 = fmaf(q.x, sigm2(tt.x) - 0.5f, 0.5f), s1 = fmaf(q.y, sigm2(tt.y) - 0.5f, 0.5f);
+        const float s2 = fmaf(q.z, sigm2(tt.z) - 0.5f, 0.5f), s3 = fmaf(q.w, sigm2(tt.w) - 0.5f, 0.5f);
+        z = fmaf(__ldg(a.cw + 4 * j + 0), s0, z); z = fmaf(__ldg(a.cw + 4 * j + 1), s1, z);
+        z = fmaf(__ldg(a.cw + 4 * j + 2), s2, z); z = fmaf(__ldg(a.cw + 4 * j + 3), s3, z);
+        if (gout) {
+            ap = fmaf(gout[4 * j + 0], s0, ap); ap = fmaf(gout[4 * j + 1], s1, ap);
+            ap = fmaf(gout[4 * j + 2], s2, ap); ap = fmaf(gout[4 * j + 3], s3, ap);
+        }
+    }
+    if (aprime) *aprime = ap;
+    return z;
+}
+
+__device__ __forceinline__ float view_weight(const TrainArgs& a, int v, float z, float* h_out)
+{
+    const float h = fmaf(z, __ldg(a.bnv + 4 * v), __ldg(a.bnv + 4 * v + 1));
+    if (h_out) *h_out = h;
+    const float act = fmaf(fmaxf(h, 0.0f), __ldg(a.fc), __ldg(a.fc + 1));
+    return 1.0f / (1.0f + expf(-act));
+}
+
+// block-wide sum of `n` doubles per thread -> atomicAdd into dst (one atomic per block and value)
+template <int N>
+__device__ __forceinline__ void block_accumulate(double (&val)[N], double* __restrict__ dst)
+{
+    __shared__ double red[32][N];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+        for (int o = 16; o > 0; o >>= 1) val[k] += __shfl_xor_sync(0xffffffffu, val[k], o);
+    if (lane == 0)
+        for (int k = 0; k < N; ++k) red[warp][k] = val[k];
+    __syncthreads();
+    if (warp == 0) {
+        for (int k = 0; k < N; ++k) {
+            double s = lane < nwarp ? red[lane][k] : 0.0;
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0 && s != 0.0) atomicAdd(dst + k, s);
+        }
+    }
+    __syncthreads();
+}
+
+// ---- forward phase 1 (train): sum z_v, sum z_v^2 per view ------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(256)
+train_stats_kernel(const TrainArgs a, double* __restrict__ stats /* [V][2] */)
+{
+    const Elem e = decode(a);
+    const GridNorm gn = make_grid_norm(a.H, a.W);
+    const size_t HW = (size_t)a.H * a.W;
+    float4 q4[G / 4];
+#pragma unroll
+    for (int j = 0; j < G / 4; ++j) q4[j] = __ldg(a.Q4 + ((size_t)e.b * (G / 4) + j) * HW + e.pix);
+    for (int v = 0; v < a.V; ++v) {
+        double s[2] = {0.0, 0.0};
+        if (e.ok) {
+            const float z = view_z<G>(a, e, v, taps_of(a, e, v, gn), q4, nullptr, nullptr);
+            s[0] = z; s[1] = (double)z * z;
+        }
+        block_accumulate<2>(s, stats + 2 * v);
+    }
+}
+
+// ---- BatchNorm constants per view (1 thread) ---------------------------------------------------------
+// training: batch statistics from `stats`; else the running statistics.  Also publishes the batch mean and
+// the unbiased variance (momentum update of the running statistics happens on the host side of the ABI).
+__global__ void bn_fold_kernel(const double* __restrict__ stats, double count, int V, int training,
+                               const float* __restrict__ bn_w, const float* __restrict__ bn_b,
+                               const float* __restrict__ bn_mean, const float* __restrict__ bn_var, float eps,
+                               const float* __restrict__ fc_w, const float* __restrict__ fc_b,
+                               float* __restrict__ bnv, float* __restrict__ fc, float* __restrict__ batch_stats)
+{
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    fc[0] = fc_w[0]; fc[1] = fc_b[0];
+    for (int v = 0; v < V; ++v) {
+        double mean = bn_mean[0], var = bn_var[0];
+        if (training) {
+            mean = stats[2 * v] / count;
+            var = stats[2 * v + 1] / count - mean * mean;
+            if (var < 0.0) var = 0.0;
+            if (batch_stats) {
+                batch_stats[2 * v] = (float)mean;
+                batch_stats[2 * v + 1] = (float)(count > 1.0 ? var * count / (count - 1.0) : var);
+            }
+        }
+        const double invstd = 1.0 / sqrt(var + (double)eps);
+        const double alpha = invstd * (double)bn_w[0];
+        bnv[4 * v + 0] = (float)alpha;
+        bnv[4 * v + 1] = (float)((double)bn_b[0] - mean * alpha);
+        bnv[4 * v + 2] = (float)invstd;
+        bnv[4 * v + 3] = (float)mean;
+    }
+}
+
+// ---- forward phase 2: the cost volume with per-view BatchNorm constants -------------------------------
+template <int G>
+__global__ void __launch_bounds__(256)
+train_forward_kernel(const TrainArgs a, float* __restrict__ out)
+{
+    constexpr int J = G / 4;
+    const Elem e = decode(a);
+    if (!e.ok) return;
+    const GridNorm gn = make_grid_norm(a.H, a.W);
+    const size_t HW = (size_t)a.H * a.W;
+    float4 q4[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) q4[j] = __ldg(a.Q4 + ((size_t)e.b * J + j) * HW + e.pix);
+    float acc[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) acc[g] = 0.0f;
+    float wsum = 0.0f;
+    for (int v = 0; v < a.V; ++v) {
+        const Taps t = taps_of(a, e, v, gn);
+        const float4* Sv = a.S4 + ((size_t)v * a.B + e.b) * J * HW;
+        float sim[G];
+        float z = 0.0f;
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            float4 tt = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t.valid) tt = sample4(Sv + (size_t)j * HW, a.H, a.W, t);
+            sim[4 * j + 0] = fmaf(q4[j].x, sigm2(tt.x) - 0.5f, 0.5f); sim[4 * j + 1] = fmaf(q4[j].y, sigm2(tt.y) - 0.5f, 0.5f);
+            sim[4 * j + 2] = fmaf(q4[j].z, sigm2(tt.z) - 0.5f, 0.5f); sim[4 * j + 3] = fmaf(q4[j].w, sigm2(tt.w) - 0.5f, 0.5f);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) z = fmaf(__ldg(a.cw + 4 * j + k), sim[4 * j + k], z);
+        }
+        const float w = view_weight(a, v, z, nullptr);
+        wsum += w;
+#pragma unroll
+        for (int g = 0; g < G; ++g) acc[g] = fmaf(w, sim[g], acc[g]);
+    }
+    float* op = out + (((size_t)e.b * G) * a.D + e.d) * HW + e.pix;
+#pragma unroll
+    for (int g = 0; g < G; ++g) op[(size_t)g * a.D * HW] = acc[g] / wsum;
+}
+
+// ---- backward ----------------------------------------------------------------------------------------
+struct BwdArgs {
+    TrainArgs t;
+    const float* out;       // saved forward output (B,G,D,H,W)
+    const float* gout;      // upstream gradient      (B,G,D,H,W)
+    const double* bsum;     // [V][2] train: sum dh_v, sum dh_v*zhat_v  (phase 1 result)
+    double count;
+    int training;
+    float4* dS4;            // [V][B][J][H][W]  zero-initialised
+    float4* dQ4;            // [B][J][H][W]     zero-initialised
+    double* gparam;         // [4 + G]: d bn_w, d bn_b, d fc_w, d fc_b, d cw[G]   zero-initialised
+};
+
+// dL/dh_v of one element given the per-view forward values
+__device__ __forceinline__ float dh_of(const BwdArgs& a, float aprime, float go, float wsum, float w, float h, float* dact_out)
+{
+    const float dw = (aprime - go) / wsum;              // d out_g / d w_v = (sim_vg - out_g) / wsum
+    const float dact = dw * w * (1.0f - w);             // sigmoid
+    if (dact_out) *dact_out = dact;
+    return h > 0.0f ? dact * __ldg(a.t.fc) : 0.0f;      // Conv3d(1,1,1) then ReLU
+}
+
+// phase 1 (train only): sum_v over elements of dh_v and dh_v * zhat_v
+template <int G>
+__global__ void __launch_bounds__(256)
+bwd_stats_kernel(const BwdArgs a, double* __restrict__ bsum)
+{
+    constexpr int J = G / 4;
+    const TrainArgs& t = a.t;
+    const Elem e = decode(t);
+    const GridNorm gn = make_grid_norm(t.H, t.W);
+    const size_t HW = (size_t)t.H * t.W;
+    float4 q4[J];
+    float gout[G];
+    float go = 0.0f;
+#pragma unroll
+    for (int j = 0; j < J; ++j) q4[j] = __ldg(t.Q4 + ((size_t)e.b * J + j) * HW + e.pix);
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        const size_t o = (((size_t)e.b * G + g) * t.D + e.d) * HW + e.pix;
+        gout[g] = e.ok ? __ldg(a.gout + o) : 0.0f;
+        go = fmaf(gout[g], e.ok ? __ldg(a.out + o) : 0.0f, go);
+    }
+    float zv[kMaxSrcViews], wv[kMaxSrcViews], hv[kMaxSrcViews], av[kMaxSrcViews];
+    float wsum = 0.0f;
+    for (int v = 0; v < t.V; ++v) {
+        zv[v] = view_z<G>(t, e, v, taps_of(t, e, v, gn), q4, gout, &av[v]);
+        wv[v] = view_weight(t, v, zv[v], &hv[v]);
+        wsum += wv[v];
+    }
+    for (int v = 0; v < t.V; ++v) {
+        double s[2] = {0.0, 0.0};
+        if (e.ok) {
+            const float dh = dh_of(a, av[v], go, wsum, wv[v], hv[v], nullptr);
+            const float zhat = (zv[v] - __ldg(t.bnv + 4 * v + 3)) * __ldg(t.bnv + 4 * v + 2);
+            s[0] = dh; s[1] = (double)dh * zhat;
+        }
+        block_accumulate<2>(s, bsum + 2 * v);
+    }
+}
+
+__device__ __forceinline__ void red_add_v4(float4* addr, float4 v)
+{
+    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                 ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// phase 2: everything else
+template <int G>
+__global__ void __launch_bounds__(256)
+bwd_main_kernel(const BwdArgs a)
+{
+    constexpr int J = G / 4;
+    const TrainArgs& t = a.t;
+    const Elem e = decode(t);
+    const GridNorm gn = make_grid_norm(t.H, t.W);
+    const size_t HW = (size_t)t.H * t.W;
+    float4 q4[J];
+    float gout[G];
+    float go = 0.0f;
+#pragma unroll
+    for (int j = 0; j < J; ++j) q4[j] = __ldg(t.Q4 + ((size_t)e.b * J + j) * HW + e.pix);
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        const size_t o = (((size_t)e.b * G + g) * t.D + e.d) * HW + e.pix;
+        gout[g] = e.ok ? __ldg(a.gout + o) : 0.0f;
+        go = fmaf(gout[g], e.ok ? __ldg(a.out + o) : 0.0f, go);
+    }
+    float zv[kMaxSrcViews], wv[kMaxSrcViews], hv[kMaxSrcViews], av[kMaxSrcViews];
+    float wsum = 0.0f;
+    for (int v = 0; v < t.V; ++v) {
+        zv[v] = view_z<G>(t, e, v, taps_of(t, e, v, gn), q4, gout, &av[v]);
+        wv[v] = view_weight(t, v, zv[v], &hv[v]);
+        wsum += wv[v];
+    }
+    float dq[G], dcw[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) { dq[g] = 0.0f; dcw[g] = 0.0f; }
+    double gp[4] = {0.0, 0.0, 0.0, 0.0};         // d bn_w, d bn_b, d fc_w, d fc_b
+    for (int v = 0; v < t.V; ++v) {
+        if (!e.ok) break;
+        float dact;
+        const float dh = dh_of(a, av[v], go, wsum, wv[v], hv[v], &dact);
+        gp[2] += (double)dact * fmaxf(hv[v], 0.0f);
+        gp[3] += dact;
+        const float invstd = __ldg(t.bnv + 4 * v + 2), mean = __ldg(t.bnv + 4 * v + 3), alpha = __ldg(t.bnv + 4 * v);
+        const float zhat = (zv[v] - mean) * invstd;
+        float dz;
+        if (a.training) {
+            // BatchNorm with batch statistics: dz = (gamma/std) * (dh - mean(dh) - zhat * mean(dh*zhat))
+            const float m1 = (float)(a.bsum[2 * v] / a.count), m2 = (float)(a.bsum[2 * v + 1] / a.count);
+            dz = alpha * (dh - m1 - zhat * m2);
+        } else {
+            dz = alpha * dh;
+        }
+        gp[0] += (double)dh * zhat;               // d gamma = sum dh * zhat   (both modes: h = gamma*zhat + beta)
+        gp[1] += dh;                              // d beta
+        const float wn = wv[v] / wsum;
+        const Taps tp = taps_of(t, e, v, gn);
+        const float4* Sv = t.S4 + ((size_t)v * t.B + e.b) * J * HW;
+        float4* dSv = a.dS4 + ((size_t)v * t.B + e.b) * J * HW;
+        const bool x0in = (unsigned)tp.x0 < (unsigned)t.W, x1in = (unsigned)(tp.x0 + 1) < (unsigned)t.W;
+        const bool y0in = (unsigned)tp.y0 < (unsigned)t.H, y1in = (unsigned)(tp.y0 + 1) < (unsigned)t.H;
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            float4 tt = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (tp.valid) tt = sample4(Sv + (size_t)j * HW, t.H, t.W, tp);
+            const float tv[4] = {tt.x, tt.y, tt.z, tt.w};
+            const float qv[4] = {q4[j].x, q4[j].y, q4[j].z, q4[j].w};
+            float dt[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int g = 4 * j + k;
+                const float p = sigm2(tv[k]);
+                const float sim = fmaf(qv[k], p - 0.5f, 0.5f);
+                const float dsim = fmaf(gout[g], wn, dz * __ldg(t.cw + g));
+                dcw[g] = fmaf(dz, sim, dcw[g]);
+                dq[g] = fmaf(dsim, p - 0.5f, dq[g]);
+                dt[k] = -kLn2 * p * (1.0f - p) * (dsim * qv[k]);      // dp/dt = -ln2 p (1-p)
+            }
+            if (tp.valid) {
+                float4* d = dSv + (size_t)j * HW + (ptrdiff_t)tp.y0 * t.W + tp.x0;
+                if (x0in && y0in) red_add_v4(d, make_float4(dt[0] * tp.wnw, dt[1] * tp.wnw, dt[2] * tp.wnw, dt[3] * tp.wnw));
+                if (x1in && y0in) red_add_v4(d + 1, make_float4(dt[0] * tp.wne, dt[1] * tp.wne, dt[2] * tp.wne, dt[3] * tp.wne));
+                if (x0in && y1in) red_add_v4(d + t.W, make_float4(dt[0] * tp.wsw, dt[1] * tp.wsw, dt[2] * tp.wsw, dt[3] * tp.wsw));
+                if (x1in && y1in) red_add_v4(d + t.W + 1, make_float4(dt[0] * tp.wse, dt[1] * tp.wse, dt[2] * tp.wse, dt[3] * tp.wse));
+            }
+        }
+    }
+    if (e.ok) {
+        float4* dqp = a.dQ4 + (size_t)e.b * J * HW + e.pix;
+#pragma unroll
+        for (int j = 0; j < J; ++j) red_add_v4(dqp + (size_t)j * HW, make_float4(dq[4 * j], dq[4 * j + 1], dq[4 * j + 2], dq[4 * j + 3]));
+    }
+    block_accumulate<4>(gp, a.gparam);
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        double c[4] = {dcw[4 * j], dcw[4 * j + 1], dcw[4 * j + 2], dcw[4 * j + 3]};
+        block_accumulate<4>(c, a.gparam + 4 + 4 * j);
+    }
+}
+
+// dS4 / dQ4 -> NCHW feature gradients.  One thread per pixel per view; blockIdx.y = view * B + b.
+struct GradPtrs { float* p[MDF_MAX_VIEWS]; };
+
+__global__ void __launch_bounds__(256)
+bwd_finish_kernel(GradPtrs grads, int B, int G, int HW, const float4* __restrict__ Q4, const float4* __restrict__ dQ4,
+                  const float4* __restrict__ dS4)
+{
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= HW) return;
+    const int v = blockIdx.y / B, b = blockIdx.y % B;
+    float* __restrict__ g = grads.p[v];
+    if (g == nullptr) return;
+    g += (size_t)b * 2 * G * HW + pix;
+    const int J = G / 4;
+    for (int j = 0; j < J; ++j) {
+        float d[4];
+        if (v == 0) {
+            // q = 2*sigmoid(r0 - r1) - 1:  dq/dr0 = (1 - q^2)/2 = -dq/dr1
+            const float4 q = __ldg(Q4 + ((size_t)b * J + j) * HW + pix), dq = __ldg(dQ4 + ((size_t)b * J + j) * HW + pix);
+            d[0] = dq.x * 0.5f * (1.0f - q.x * q.x); d[1] = dq.y * 0.5f * (1.0f - q.y * q.y);
+            d[2] = dq.z * 0.5f * (1.0f - q.z * q.z); d[3] = dq.w * 0.5f * (1.0f - q.w * q.w);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { g[(size_t)(8 * j + 2 * k) * HW] = d[k]; g[(size_t)(8 * j + 2 * k + 1) * HW] = -d[k]; }
+        } else {
+            // S = (f[2g+1] - f[2g]) * log2e
+            const float4 ds = __ldg(dS4 + (((size_t)(v - 1) * B + b) * J + j) * HW + pix);
+            d[0] = ds.x * kLog2e; d[1] = ds.y * kLog2e; d[2] = ds.z * kLog2e; d[3] = ds.w * kLog2e;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { g[(size_t)(8 * j + 2 * k) * HW] = -d[k]; g[(size_t)(8 * j + 2 * k + 1) * HW] = d[k]; }
+        }
+    }
+}
+
+__global__ void gparam_to_float_kernel(const double* __restrict__ src, float* __restrict__ dst, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = (float)src[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// workspace
+// ------------------------------------------------------------------------------------------------
+struct TrainWorkspace {
+    size_t rt, dwp, q, s, cq, ks, bnv, fc, stats, bsum, gparam, dq, ds, total;
+};
+
+static TrainWorkspace make_train_workspace(int B, int N, int G, int H, int W)
+{
+    TrainWorkspace w;
+    const size_t V = (size_t)(N - 1), plane = (size_t)B * G * H * W * sizeof(float);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off = align_up(off + bytes, 256); return o; };
+    w.rt = take(V * B * 12 * sizeof(float));
+    w.dwp = take(64 * sizeof(float));
+    w.q = take(plane);
+    w.s = take(V * plane);
+    w.cq = take(plane);
+    w.ks = take((size_t)B * H * W * sizeof(float));
+    w.bnv = take(kMaxSrcViews * 4 * sizeof(float));
+    w.fc = take(2 * sizeof(float));
+    w.stats = take(kMaxSrcViews * 2 * sizeof(double));      // stats | bsum | gparam are contiguous: one memset
+    w.bsum = take(kMaxSrcViews * 2 * sizeof(double));
+    w.gparam = take((4 + 32) * sizeof(double));
+    w.dq = take(plane);
+    w.ds = take(V * plane);
+    w.total = off;
+    return w;
+}
+
+struct TrainCall {
+    const float* const* features; int N; const float* ref_proj; const float* const* src_projs;
+    const float* hypos; int per_pixel;
+    const float *conv_w, *bn_w, *bn_b, *bn_mean, *bn_var; float bn_eps; const float *fc_w, *fc_b;
+    int training, B, C, G, D, H, W;
+};
+
+static int validate(const TrainCall& c, const void* out, void* workspace, size_t workspace_bytes, TrainWorkspace* ws, int* dev_out)
+{
+    if (c.B < 0 || c.C <= 0 || c.G <= 0 || c.D < 0 || c.H < 0 || c.W < 0 || c.N < 2 || c.C % c.G != 0) return MDF_ERR_INVALID_SHAPE;
+    if (c.N > MDF_MAX_VIEWS || c.C != 2 * c.G || !(c.G == 8 || c.G == 16 || c.G == 32)) return MDF_ERR_UNSUPPORTED;
+    if ((long long)c.H * c.W > INT_MAX - 256 || (long long)c.N * c.B > 65535 || (long long)(c.N - 1) * c.B > 256) return MDF_ERR_UNSUPPORTED;
+    if (!c.features || !c.src_projs || !c.ref_proj || !c.hypos || !c.conv_w || !c.bn_w || !c.bn_b || !c.bn_mean || !c.bn_var ||
+        !c.fc_w || !c.fc_b || !out)
+        return MDF_ERR_NULL_POINTER;
+    *ws = make_train_workspace(c.B, c.N, c.G, c.H, c.W);
+    if (!workspace || ((uintptr_t)workspace & 255) != 0 || workspace_bytes < ws->total) return MDF_ERR_WORKSPACE;
+    const int dev = device_of(out);
+    if (dev < 0) return dev;
+    const void* ptrs[MDF_MAX_VIEWS * 2 + 16];
+    int n = 0;
+    for (int i = 0; i < c.N; ++i) ptrs[n++] = c.features[i];
+    for (int i = 0; i < c.N - 1; ++i) ptrs[n++] = c.src_projs[i];
+    const void* more[] = {c.ref_proj, c.hypos, c.conv_w, c.bn_w, c.bn_b, c.bn_mean, c.bn_var, c.fc_w, c.fc_b, workspace};
+    for (const void* p : more) ptrs[n++] = p;
+    const int st = check_on_device(dev, ptrs, n);
+    if (st != MDF_OK) return st;
+    *dev_out = dev;
+    return MDF_OK;
+}
+
+// prep (S4, Q4, rt) + BatchNorm constants; returns the TrainArgs for the sweeps
+template <int G>
+static int prepare(const TrainCall& c, uint8_t* wsb, const TrainWorkspace& ws, float* batch_stats, cudaStream_t stream, TrainArgs* out)
+{
+    const int V = c.N - 1;
+    float* rt = reinterpret_cast<float*>(wsb + ws.rt);
+    float* dwp = reinterpret_cast<float*>(wsb + ws.dwp);
+    float4* Q4 = reinterpret_cast<float4*>(wsb + ws.q);
+    float4* S4 = reinterpret_cast<float4*>(wsb + ws.s);
+    FeaPtrs fp;
+    for (int i = 0; i < MDF_MAX_VIEWS; ++i) fp.p[i] = i < c.N ? c.features[i] : nullptr;
+    PrepSetup su;
+    for (int v = 0; v < kMaxSrcViews; ++v) su.src_projs.p[v] = v < V ? c.src_projs[v] : nullptr;
+    su.ref_proj = c.ref_proj; su.V = V; su.rt = rt; su.dwp = dwp;
+    su.dw = {c.conv_w, c.bn_w, c.bn_b, c.bn_mean, c.bn_var, c.fc_w, c.fc_b, c.bn_eps};
+    const int HW = c.H * c.W;
+    prep_kernel<<<dim3((unsigned)((HW + 255) / 256), (unsigned)(c.N * c.B)), 256, 0, stream>>>(
+        fp, c.B, G, HW, su, Q4, reinterpret_cast<float4*>(wsb + ws.cq), reinterpret_cast<float*>(wsb + ws.ks), S4);
+    int st = launch_status();
+    if (st != MDF_OK) return st;
+    // stats, bsum and gparam are adjacent
+    MDF_CUDA_TRY(cudaMemsetAsync(wsb + ws.stats, 0, ws.dq - ws.stats, stream));
+
+    TrainArgs a;
+    a.S4 = S4; a.Q4 = Q4; a.rt = rt; a.cw = c.conv_w;
+    a.bnv = reinterpret_cast<float*>(wsb + ws.bnv); a.fc = reinterpret_cast<float*>(wsb + ws.fc);
+    a.hypos = c.hypos; a.per_pixel = c.per_pixel; a.V = V; a.B = c.B; a.D = c.D; a.H = c.H; a.W = c.W;
+    const size_t total = (size_t)c.B * c.D * c.H * c.W;
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    double* stats = reinterpret_cast<double*>(wsb + ws.stats);
+    if (c.training) {
+        train_stats_kernel<G><<<blocks, 256, 0, stream>>>(a, stats);
+        st = launch_status();
+        if (st != MDF_OK) return st;
+    }
+    bn_fold_kernel<<<1, 32, 0, stream>>>(stats, (double)total, V, c.training, c.bn_w, c.bn_b, c.bn_mean, c.bn_var, c.bn_eps,
+                                         c.fc_w, c.fc_b, reinterpret_cast<float*>(wsb + ws.bnv), reinterpret_cast<float*>(wsb + ws.fc),
+                                         batch_stats);
+    st = launch_status();
+    if (st != MDF_OK) return st;
+    *out = a;
+    return MDF_OK;
+}
+
+template <int G>
+static int train_fwd(const TrainCall& c, float* cost_volume, float* batch_stats, uint8_t* wsb, const TrainWorkspace& ws, cudaStream_t stream)
+{
+    TrainArgs a;
+    int st = prepare<G>(c, wsb, ws, batch_stats, stream, &a);
+    if (st != MDF_OK) return st;
+    const size_t total = (size_t)c.B * c.D * c.H * c.W;
+    train_forward_kernel<G><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(a, cost_volume);
+    return launch_status();
+}
+
+template <int G>
+static int train_bwd(const TrainCall& c, const float* cost_volume, const float* grad_out, float* const* grad_features,
+                     float* grad_params, uint8_t* wsb, const TrainWorkspace& ws, cudaStream_t stream)
+{
+    BwdArgs a;
+    int st = prepare<G>(c, wsb, ws, nullptr, stream, &a.t);
+    if (st != MDF_OK) return st;
+    a.out = cost_volume; a.gout = grad_out;
+    a.bsum = reinterpret_cast<double*>(wsb + ws.bsum);
+    a.count = (double)c.B * c.D * c.H * c.W;
+    a.training = c.training;
+    a.dS4 = reinterpret_cast<float4*>(wsb + ws.ds); a.dQ4 = reinterpret_cast<float4*>(wsb + ws.dq);
+    a.gparam = reinterpret_cast<double*>(wsb + ws.gparam);
+    MDF_CUDA_TRY(cudaMemsetAsync(wsb + ws.dq, 0, ws.total - ws.dq, stream));
+    const size_t total = (size_t)c.B * c.D * c.H * c.W;
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    if (c.training) {
+        bwd_stats_kernel<G><<<blocks, 256, 0, stream>>>(a, reinterpret_cast<double*>(wsb + ws.bsum));
+        st = launch_status();
+        if (st != MDF_OK) return st;
+    }
+    bwd_main_kernel<G><<<blocks, 256, 0, stream>>>(a);
+    st = launch_status();
+    if (st != MDF_OK) return st;
+    GradPtrs gp;
+    for (int i = 0; i < MDF_MAX_VIEWS; ++i) gp.p[i] = (grad_features && i < c.N) ? grad_features[i] : nullptr;
+    const int HW = c.H * c.W;
+    bwd_finish_kernel<<<dim3((unsigned)((HW + 255) / 256), (unsigned)(c.N * c.B)), 256, 0, stream>>>(
+        gp, c.B, G, HW, a.t.Q4, a.dQ4, a.dS4);
+    st = launch_status();
+    if (st != MDF_OK) return st;
+    if (grad_params) {
+        gparam_to_float_kernel<<<1, 64, 0, stream>>>(a.gparam, grad_params, 4 + G);
+        st = launch_status();
+    }
+    return st;
+}
+
+}  // namespace mdf
+
+using namespace mdf;
+
+extern "C" {
+
+size_t mdf_cost_volume_train_workspace_bytes(int B, int N, int C, int G, int D, int H, int W)
+{
+    (void)D;
+    if (B <= 0 || N < 2 || C != 2 * G || G <= 0 || H <= 0 || W <= 0) return 0;
+    return make_train_workspace(B, N, G, H, W).total;
+}
+
+int mdf_cost_volume_train_fwd(const float* const* features, int N, const float* ref_proj, const float* const* src_projs,
+                              const float* depth_hypos, int hypos_per_pixel, const float* conv_weight, const float* bn_weight,
+                              const float* bn_bias, const float* bn_mean, const float* bn_var, float bn_eps,
+                              const float* fc_weight, const float* fc_bias, int training, int B, int C, int G, int D, int H,
+                              int W, float* cost_volume, float* batch_stats, void* workspace, size_t workspace_bytes,
+                              mdf_stream_t stream)
+{
+    const TrainCall c = {features, N, ref_proj, src_projs, depth_hypos, hypos_per_pixel, conv_weight, bn_weight, bn_bias, bn_mean,
+                         bn_var, bn_eps, fc_weight, fc_bias, training, B, C, G, D, H, W};
+    if (B >= 0 && D >= 0 && H >= 0 && W >= 0 && C > 0 && G > 0 && N >= 2 && C % G == 0 && (size_t)B * D * H * W == 0) return MDF_OK;
+    TrainWorkspace ws;
+    int dev = 0;
+    int st = validate(c, cost_volume, workspace, workspace_bytes, &ws, &dev);
+    if (st != MDF_OK) return st;
+    if (training && batch_stats && device_of(batch_stats) != dev) return MDF_ERR_NOT_DEVICE;
+    DeviceGuard guard(dev);
+    uint8_t* wsb = static_cast<uint8_t*>(workspace);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (G == 32) return train_fwd<32>(c, cost_volume, batch_stats, wsb, ws, s);
+    if (G == 16) return train_fwd<16>(c, cost_volume, batch_stats, wsb, ws, s);
+    return train_fwd<8>(c, cost_volume, batch_stats, wsb, ws, s);
+}
+
+int mdf_cost_volume_bwd(const float* const* features, int N, const float* ref_proj, const float* const* src_projs,
+                        const float* depth_hypos, int hypos_per_pixel, const float* conv_weight, const float* bn_weight,
+                        const float* bn_bias, const float* bn_mean, const float* bn_var, float bn_eps, const float* fc_weight,
+                        const float* fc_bias, int training, int B, int C, int G, int D, int H, int W, const float* cost_volume,
+                        const float* grad_out, float* const* grad_features, float* grad_params, void* workspace,
+                        size_t workspace_bytes, mdf_stream_t stream)
+{
+    const TrainCall c = {features, N, ref_proj, src_projs, depth_hypos, hypos_per_pixel, conv_weight, bn_weight, bn_bias, bn_mean,
+                         bn_var, bn_eps, fc_weight, fc_bias, training, B, C, G, D, H, W};
+    if (!grad_out) return MDF_ERR_NULL_POINTER;
+    TrainWorkspace ws;
+    int dev = 0;
+    int st = validate(c, cost_volume, workspace, workspace_bytes, &ws, &dev);
+    if (st != MDF_OK) return st;
+    if ((size_t)B * D * H * W == 0) return MDF_ERR_INVALID_SHAPE;
+    {
+        const void* ptrs[MDF_MAX_VIEWS + 2];
+        int n = 0;
+        ptrs[n++] = grad_out;
+        if (grad_params) ptrs[n++] = grad_params;
+        if (grad_features)
+            for (int i = 0; i < N; ++i)
+                if (grad_features[i]) ptrs[n++] = grad_features[i];
+        st = check_on_device(dev, ptrs, n);
+        if (st != MDF_OK) return st;
+    }
+    DeviceGuard guard(dev);
+    uint8_t* wsb = static_cast<uint8_t*>(workspace);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (G == 32) return train_bwd<32>(c, cost_volume, grad_out, grad_features, grad_params, wsb, ws, s);
+    if (G == 16) return train_bwd<16>(c, cost_volume, grad_out, grad_features, grad_params, wsb, ws, s);
+    return train_bwd<8>(c, cost_volume, grad_out, grad_features, grad_params, wsb, ws, s);
+}
+
+}  // extern "C"

@@ -15,7 +15,7 @@ struct SrcPtrs { const float* p[kMaxSrcViews]; };
 // ------------------------------------------------------------------------------------------------
 // setup: projections + folded depth_weight parameters
 // ------------------------------------------------------------------------------------------------
-__device__ void compose_proj_f64(const float* __restrict__ src, const float* __restrict__ ref, float* __restrict__ out12)
+__device__ inline void compose_proj_f64(const float* __restrict__ src, const float* __restrict__ ref, float* __restrict__ out12)
 {
     // Gauss-Jordan with partial pivoting in float64, then rows 0..2 of src @ inv(ref), rounded once.
     double a[4][8];
@@ -85,7 +85,7 @@ __device__ inline void setup_work(int i, const SrcPtrs& src_projs, const float* 
     if (i == 0 && dwp != nullptr) fold_depth_weight(dw.conv_w, dw.bn_w, dw.bn_b, dw.bn_mean, dw.bn_var, dw.bn_eps, dw.fc_w, dw.fc_b, G, dwp);
 }
 
-__global__ void setup_kernel(SrcPtrs src_projs, const float* __restrict__ ref_proj, int V, int B,
+static __global__ void setup_kernel(SrcPtrs src_projs, const float* __restrict__ ref_proj, int V, int B,
                              float* __restrict__ rt_all, DepthWeightPtrs dw, int G, float* __restrict__ dwp)
 {
     setup_work(blockIdx.x * blockDim.x + threadIdx.x, src_projs, ref_proj, V, B, rt_all, dw, G, dwp);

@@ -47,7 +47,7 @@ struct PrepSetup {          // the per-call scalar work (mdf_setup.cuh) rides al
     DepthWeightPtrs dw;
 };
 
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 prep_kernel(FeaPtrs feas, int B, int G, int HW, PrepSetup su,
             float4* __restrict__ Q4, float4* __restrict__ CQ4, float* __restrict__ KS, float4* __restrict__ S4)
 {

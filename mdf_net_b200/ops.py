@@ -260,3 +260,85 @@ def confidence(prob_volume: Tensor, n: int = 4, pad_front: int = 1, pad_back: in
 def _(prob_volume, n=4, pad_front=1, pad_back=2, upsample=1):
     B, _, H, W = prob_volume.shape
     return prob_volume.new_empty((B, H * upsample, W * upsample))
+
+
+# ------------------------------------------------------------------- train-mode forward and backward
+def _train_common(features, ref_proj, src_projs, depth_hypos, conv_weight, bn_weight, bn_bias, bn_mean, bn_var,
+                  fc_weight, fc_bias, groups):
+    _check_views(features, src_projs)
+    feats = [_f32c(f, "features") for f in features]
+    B, C, H, W = feats[0].shape
+    hyp, D, per_pixel = _hypos(depth_hypos, B, H, W)
+    projs = [_f32c(p, "src_projs") for p in src_projs]
+    refp = _f32c(ref_proj, "ref_proj")
+    params = [_f32c(t, n) for t, n in ((conv_weight, "conv_weight"), (bn_weight, "bn_weight"), (bn_bias, "bn_bias"),
+                                        (bn_mean, "bn_mean"), (bn_var, "bn_var"), (fc_weight, "fc_weight"),
+                                        (fc_bias, "fc_bias"))]
+    if C != 2 * groups or groups not in (8, 16, 32):
+        raise RuntimeError(f"mdfnet_b200: training / autograd supports C == 2*G with G in (8, 16, 32), got C={C}, G={groups}")
+    return feats, refp, projs, hyp, per_pixel, params, (B, C, D, H, W)
+
+
+@torch.library.custom_op("mdfnet_b200::cost_volume_train", mutates_args=(), device_types="cuda")
+def cost_volume_train(features: List[Tensor], ref_proj: Tensor, src_projs: List[Tensor], depth_hypos: Tensor,
+                      conv_weight: Tensor, bn_weight: Tensor, bn_bias: Tensor, bn_mean: Tensor, bn_var: Tensor,
+                      bn_eps: float, fc_weight: Tensor, fc_bias: Tensor, groups: int, training: bool) -> Tuple[Tensor, Tensor]:
+    """Cost volume with batch-statistics BatchNorm (training=True) or running statistics (False), computed by the
+    kernels whose backward is `cost_volume_bwd`.  Returns (cost volume, (N-1,2) per-view batch mean / unbiased var)."""
+    feats, refp, projs, hyp, per_pixel, params, (B, C, D, H, W) = _train_common(
+        features, ref_proj, src_projs, depth_hypos, conv_weight, bn_weight, bn_bias, bn_mean, bn_var, fc_weight, fc_bias, groups)
+    lib = _cabi.lib()
+    N = len(feats)
+    dev = feats[0].device
+    out = torch.empty((B, groups, D, H, W), dtype=torch.float32, device=dev)
+    stats = torch.zeros((N - 1, 2), dtype=torch.float32, device=dev)
+    ws = _workspace(lib.mdf_cost_volume_train_workspace_bytes(B, N, C, groups, D, H, W), dev)
+    st = lib.mdf_cost_volume_train_fwd(
+        _cabi.ptr_array([f.data_ptr() for f in feats]), N, refp.data_ptr(), _cabi.ptr_array([p.data_ptr() for p in projs]),
+        hyp.data_ptr(), per_pixel, params[0].data_ptr(), params[1].data_ptr(), params[2].data_ptr(), params[3].data_ptr(),
+        params[4].data_ptr(), float(bn_eps), params[5].data_ptr(), params[6].data_ptr(), int(training),
+        B, C, groups, D, H, W, out.data_ptr(), stats.data_ptr(), ws.data_ptr(), ws.numel(), _stream(out))
+    _cabi.check("mdf_cost_volume_train_fwd", st)
+    _count(4 if training else 3)
+    return out, stats
+
+
+@cost_volume_train.register_fake
+def _(features, ref_proj, src_projs, depth_hypos, conv_weight, bn_weight, bn_bias, bn_mean, bn_var, bn_eps,
+      fc_weight, fc_bias, groups, training):
+    B, _, H, W = features[0].shape
+    return features[0].new_empty((B, groups, depth_hypos.shape[1], H, W)), features[0].new_empty((len(features) - 1, 2))
+
+
+@torch.library.custom_op("mdfnet_b200::cost_volume_bwd", mutates_args=(), device_types="cuda")
+def cost_volume_bwd(features: List[Tensor], ref_proj: Tensor, src_projs: List[Tensor], depth_hypos: Tensor,
+                    conv_weight: Tensor, bn_weight: Tensor, bn_bias: Tensor, bn_mean: Tensor, bn_var: Tensor,
+                    bn_eps: float, fc_weight: Tensor, fc_bias: Tensor, groups: int, training: bool,
+                    cost_volume: Tensor, grad_out: Tensor) -> Tuple[List[Tensor], Tensor]:
+    """Gradients of `cost_volume_train`: ([d features[i]], (4+G,) = d bn.weight, d bn.bias, d fc.weight, d fc.bias, d conv.weight)."""
+    feats, refp, projs, hyp, per_pixel, params, (B, C, D, H, W) = _train_common(
+        features, ref_proj, src_projs, depth_hypos, conv_weight, bn_weight, bn_bias, bn_mean, bn_var, fc_weight, fc_bias, groups)
+    lib = _cabi.lib()
+    N = len(feats)
+    dev = feats[0].device
+    cv, go = _f32c(cost_volume, "cost_volume"), _f32c(grad_out, "grad_out")
+    if cv.shape != (B, groups, D, H, W) or go.shape != cv.shape:
+        raise RuntimeError("mdfnet_b200: cost_volume / grad_out must be (B,G,D,H,W)")
+    gfeats = [torch.empty_like(f) for f in feats]
+    gparams = torch.empty(4 + groups, dtype=torch.float32, device=dev)
+    ws = _workspace(lib.mdf_cost_volume_train_workspace_bytes(B, N, C, groups, D, H, W), dev)
+    st = lib.mdf_cost_volume_bwd(
+        _cabi.ptr_array([f.data_ptr() for f in feats]), N, refp.data_ptr(), _cabi.ptr_array([p.data_ptr() for p in projs]),
+        hyp.data_ptr(), per_pixel, params[0].data_ptr(), params[1].data_ptr(), params[2].data_ptr(), params[3].data_ptr(),
+        params[4].data_ptr(), float(bn_eps), params[5].data_ptr(), params[6].data_ptr(), int(training),
+        B, C, groups, D, H, W, cv.data_ptr(), go.data_ptr(), _cabi.ptr_array([g.data_ptr() for g in gfeats]),
+        gparams.data_ptr(), ws.data_ptr(), ws.numel(), _stream(cv))
+    _cabi.check("mdf_cost_volume_bwd", st)
+    _count(7 if training else 5)
+    return gfeats, gparams
+
+
+@cost_volume_bwd.register_fake
+def _(features, ref_proj, src_projs, depth_hypos, conv_weight, bn_weight, bn_bias, bn_mean, bn_var, bn_eps,
+      fc_weight, fc_bias, groups, training, cost_volume, grad_out):
+    return [torch.empty_like(f) for f in features], features[0].new_empty(4 + groups)

@@ -50,8 +50,10 @@ class VectorAggregate(nn.Module):
     def forward(self, features: Sequence[Tensor], ref_proj: Tensor, src_projs: Sequence[Tensor],
                 depth_hypos: Tensor) -> Tensor:
         cbr, fc = self.depth_weight[0], self.depth_weight[1]
-        if self.training or torch.is_grad_enabled() and any(t.requires_grad for t in (*features, *self.parameters())):
-            from . import autograd  # train-mode BatchNorm (batch statistics) and the backward pass
+        needs_grad = torch.is_grad_enabled() and any(t.requires_grad for t in (*features, *self.parameters()))
+        if self.training or needs_grad:
+            # train-mode BatchNorm (batch statistics per source view) and / or autograd: csrc/mdf_backward.cu
+            from . import autograd
             return autograd.vector_aggregate_train(self, list(features), ref_proj, list(src_projs), depth_hypos)
         return ops.cost_volume(list(features), ref_proj, list(src_projs), depth_hypos,
                                cbr.conv.weight, cbr.bn.weight, cbr.bn.bias, cbr.bn.running_mean, cbr.bn.running_var,

@@ -124,6 +124,39 @@ def gen_varagg():
              src_projs=np.stack([s.numpy() for s in src_projs]), depth_hypos=hyp, cost_volume=out)
 
 
+def gen_vecagg_grad():
+    """Gradients of the unmodified reference VectorAggregate (autograd) in eval and train mode: w.r.t. every
+    feature map and the depth_weight parameters, for a fixed upstream gradient; train mode also records the
+    running statistics after the forward (BatchNorm3d updates them once per source view)."""
+    for name, B, N, C, G, D, H, W, per_pixel, seed in [
+        ("vecagg_grad_s0", 2, 3, 64, 32, 6, 6, 8, False, 71),
+        ("vecagg_grad_s2", 1, 4, 16, 8, 8, 10, 12, True, 72),
+    ]:
+        ref_proj, src_projs = op_rig(B, N, H, W, seed)
+        feats = syn.smooth_features(B, N, C, H, W, seed=seed)
+        hyp = syn.pixel_hypos(B, D, H, W, seed=seed) if per_pixel else syn.uniform_hypos(B, D)
+        p = syn.depth_weight_params(G, seed=seed)
+        gout = np.random.default_rng(seed).standard_normal((B, G, D, H, W)).astype(np.float32)
+        out = {}
+        for mode in ("eval", "train"):
+            mod = VectorAggregate(G)
+            set_depth_weight(mod, p)
+            mod.train(mode == "train")
+            fs = [T(f).clone().requires_grad_(True) for f in feats]
+            cv = mod(fs, ref_proj, src_projs, T(hyp))
+            cv.backward(T(gout))
+            out[f"{mode}_cost_volume"] = cv.detach().numpy()
+            out[f"{mode}_grad_features"] = np.stack([f.grad.numpy() for f in fs])
+            dw = mod.depth_weight
+            out[f"{mode}_grad_cw"] = dw[0].conv.weight.grad.numpy().reshape(-1)
+            out[f"{mode}_grad_bn"] = np.array([dw[0].bn.weight.grad.item(), dw[0].bn.bias.grad.item()], np.float32)
+            out[f"{mode}_grad_fc"] = np.array([dw[1].weight.grad.item(), dw[1].bias.grad.item()], np.float32)
+            out[f"{mode}_running"] = np.array([dw[0].bn.running_mean.item(), dw[0].bn.running_var.item(),
+                                               float(dw[0].bn.num_batches_tracked.item())], np.float64)
+        save(name, features=np.stack(feats), ref_proj=ref_proj.numpy(), src_projs=np.stack([s.numpy() for s in src_projs]),
+             depth_hypos=hyp, groups=G, grad_out=gout, **{"p_" + k: v for k, v in p.items()}, **out)
+
+
 # ------------------------------------------------------------------------------------ head
 def gen_head():
     for name, B, D, H, W, seed in [("head_d48", 1, 48, 8, 12, 41), ("head_d24", 2, 24, 8, 12, 42), ("head_d8", 2, 8, 12, 16, 43)]:
@@ -243,6 +276,6 @@ def gen_corenet():
 
 if __name__ == "__main__":
     only = sys.argv[1:]
-    for fn in (gen_warp, gen_vecagg, gen_varagg, gen_head, gen_scale, gen_corenet):
+    for fn in (gen_warp, gen_vecagg, gen_vecagg_grad, gen_varagg, gen_head, gen_scale, gen_corenet):
         if not only or fn.__name__ in only:
             fn()

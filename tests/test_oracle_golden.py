@@ -131,3 +131,35 @@ def test_corenet_stages_teacher_forced():
         assert np.abs(d - z[f"s{s}_depth"]).max() < 1e-3 * (935.0 - 425.0) / 47.0
     conf = co.confidence_regress(z["s2_prob"], upsample=2)
     assert np.array_equal(conf, z["confidence"])
+
+
+@pytest.mark.parametrize("name", ["vecagg_grad_s0", "vecagg_grad_s2"])
+@pytest.mark.parametrize("mode", ["eval", "train"])
+def test_torch_restatement_gradients(name, mode):
+    """tests/torch_ref.py (the autograd reference of the CUDA backward) reproduces the unmodified reference's
+    forward and gradients, eval and train mode, and its batch statistics reproduce the running-stat updates."""
+    import torch
+    import torch_ref
+    z = load_golden(name)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    feats = [T(f).clone().requires_grad_(True) for f in z["features"]]
+    P = {k: T(np.asarray(z["p_" + k], np.float32).reshape(-1)).clone().requires_grad_(True)
+         for k in ("cw", "bn_weight", "bn_bias", "fc_weight", "fc_bias")}
+    cv, stats = torch_ref.vector_aggregate(feats, T(z["ref_proj"]), [T(s) for s in z["src_projs"]], T(z["depth_hypos"]),
+                                           P["cw"], P["bn_weight"], P["bn_bias"], float(z["p_bn_mean"]), float(z["p_bn_var"]),
+                                           float(z["p_bn_eps"]), P["fc_weight"], P["fc_bias"], int(z["groups"]),
+                                           training=(mode == "train"))
+    cv.backward(T(z["grad_out"]))
+    assert rel_l2(cv.detach().numpy(), z[f"{mode}_cost_volume"]) < 2e-6
+    assert rel_l2(np.stack([f.grad.numpy() for f in feats]), z[f"{mode}_grad_features"]) < 2e-5
+    assert rel_l2(P["cw"].grad.numpy(), z[f"{mode}_grad_cw"]) < 1e-4
+    got_bn = np.array([P["bn_weight"].grad.item(), P["bn_bias"].grad.item()])
+    got_fc = np.array([P["fc_weight"].grad.item(), P["fc_bias"].grad.item()])
+    assert np.allclose(got_bn, z[f"{mode}_grad_bn"], rtol=2e-4, atol=1e-5)
+    assert np.allclose(got_fc, z[f"{mode}_grad_fc"], rtol=2e-4, atol=1e-5)
+    if mode == "train":
+        rm, rv = float(z["p_bn_mean"]), float(z["p_bn_var"])
+        for mean, var in stats:                      # momentum 0.1, unbiased variance, once per source view
+            rm, rv = 0.9 * rm + 0.1 * float(mean), 0.9 * rv + 0.1 * float(var)
+        assert np.allclose([rm, rv], z["train_running"][:2], rtol=1e-5)
+        assert int(z["train_running"][2]) == len(stats)
