@@ -438,7 +438,7 @@ __global__ void gparam_to_float_kernel(const double* __restrict__ src, float* __
 // workspace
 // ------------------------------------------------------------------------------------------------
 struct TrainWorkspace {
-    size_t rt, dwp, q, s, cq, ks, bnv, fc, stats, bsum, gparam, dq, ds, total;
+    size_t rt, dwp, q, s, cq, bnv, fc, stats, bsum, gparam, dq, ds, total;
 };
 
 static TrainWorkspace make_train_workspace(int B, int N, int G, int H, int W)
@@ -452,7 +452,6 @@ static TrainWorkspace make_train_workspace(int B, int N, int G, int H, int W)
     w.q = take(plane);
     w.s = take(V * plane);
     w.cq = take(plane);
-    w.ks = take((size_t)B * H * W * sizeof(float));
     w.bnv = take(kMaxSrcViews * 4 * sizeof(float));
     w.fc = take(2 * sizeof(float));
     w.stats = take(kMaxSrcViews * 2 * sizeof(double));      // stats | bsum | gparam are contiguous: one memset
@@ -511,9 +510,7 @@ static int prepare(const TrainCall& c, uint8_t* wsb, const TrainWorkspace& ws, f
     su.ref_proj = c.ref_proj; su.V = V; su.rt = rt; su.dwp = dwp;
     su.dw = {c.conv_w, c.bn_w, c.bn_b, c.bn_mean, c.bn_var, c.fc_w, c.fc_b, c.bn_eps};
     const int HW = c.H * c.W;
-    prep_kernel<<<dim3((unsigned)((HW + 255) / 256), (unsigned)(c.N * c.B)), 256, 0, stream>>>(
-        fp, c.B, G, HW, su, Q4, reinterpret_cast<float4*>(wsb + ws.cq), reinterpret_cast<float*>(wsb + ws.ks), S4);
-    int st = launch_status();
+    int st = launch_setup_and_prep(su, fp, c.N, c.B, G, HW, Q4, reinterpret_cast<float4*>(wsb + ws.cq), S4, stream);
     if (st != MDF_OK) return st;
     // stats, bsum and gparam are adjacent
     MDF_CUDA_TRY(cudaMemsetAsync(wsb + ws.stats, 0, ws.dq - ws.stats, stream));

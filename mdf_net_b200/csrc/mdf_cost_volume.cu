@@ -35,7 +35,6 @@ struct Workspace {
     size_t q_off;     // [B][G/4][H][W] float4 reference q maps           (staged path)
     size_t s_off;     // [V][B][G/4][H][W] float4 source difference maps  (staged path)
     size_t cq_off;    // [B][G/4][H][W] float4 conv_w * q                 (staged path)
-    size_t ks_off;    // [B][H][W] float 0.5 * sum_g cq_g                 (staged path)
     size_t total;
 };
 
@@ -52,8 +51,6 @@ static Workspace make_workspace(int B, int N, int G, int H, int W, bool staged)
     if (staged) off = align_up(off + V * B * (size_t)H * W * G * sizeof(float), 256);
     w.cq_off = off;
     if (staged) off = align_up(off + (size_t)B * G * H * W * sizeof(float), 256);
-    w.ks_off = off;
-    if (staged) off = align_up(off + (size_t)B * H * W * sizeof(float), 256);
     w.total = off;
     return w;
 }
@@ -356,7 +353,6 @@ int mdf_cost_volume_fwd_ex(const float* const* features, int N, const float* ref
     float4* Q4 = reinterpret_cast<float4*>(wsb + ws.q_off);
     float4* S4 = reinterpret_cast<float4*>(wsb + ws.s_off);
     float4* CQ4 = reinterpret_cast<float4*>(wsb + ws.cq_off);
-    float* KS = reinterpret_cast<float*>(wsb + ws.ks_off);
     {
         FeaPtrs fp;
         for (int i = 0; i < MDF_MAX_VIEWS; ++i) fp.p[i] = i < N ? features[i] : nullptr;
@@ -366,12 +362,11 @@ int mdf_cost_volume_fwd_ex(const float* const* features, int N, const float* ref
         for (int v = 0; v < kMaxSrcViews; ++v) su.src_projs.p[v] = v < V ? src_projs[v] : nullptr;
         su.ref_proj = ref_proj; su.V = V; su.rt = rt; su.dwp = dwp;
         su.dw = {conv_weight, bn_weight, bn_bias, bn_mean, bn_var, fc_weight, fc_bias, bn_eps};
-        prep_kernel<<<dim3((unsigned)((HW + 255) / 256), (unsigned)(N * B)), 256, 0, stream>>>(fp, B, G, (int)HW, su, Q4, CQ4, KS, S4);
-        st = launch_status();
+        st = launch_setup_and_prep(su, fp, N, B, G, (int)HW, Q4, CQ4, S4, stream);
         if (st != MDF_OK) return st;
     }
     StagedArgs a;
-    a.rt = rt; a.dwp = dwp; a.ks = KS; a.hypos = depth_hypos; a.out = cost_volume;
+    a.rt = rt; a.dwp = dwp; a.hypos = depth_hypos; a.out = cost_volume;
     a.per_pixel = hypos_per_pixel; a.V = V; a.B = B; a.D = D; a.H = H; a.W = W;
     a.gn = make_grid_norm(H, W);
     a.tiles_x = a.tiles_y = a.slabs = 0;

@@ -5,6 +5,9 @@
 //   depth_regression             net/unit/regress.py:5-7
 //   confidence_regress           net/unit/regress.py:9-25  (+ nearest x2 upsample, net/core.py:75-77)
 //
+// Two kernels: softmax_regress_reg_kernel<D> for the configured depths 8 / 24 / 48 (column in registers) and the
+// generic softmax_regress_kernel<DS> below for any other D.
+//
 // Layout: logits / prob are (B,D,H,W) with W fastest, so for a fixed depth plane consecutive lanes
 // read consecutive pixels.  A warp owns 32/DS consecutive pixels and DS interleaved slices of the
 // depth axis (lane = slice * (32/DS) + pixel): every load instruction covers DS full 32-byte
@@ -129,6 +132,86 @@ softmax_regress_kernel(const HeadArgs a)
 }
 
 // ------------------------------------------------------------------------------------------------
+// Register-resident variant for the configured depths (D = 8, 24, 48; config.py:199).  A warp owns 32/DS
+// pixels x DS slices of the depth axis (lane = slice * (32/DS) + pixel); every lane keeps its D/DS logits in
+// registers (independent loads in flight, logits read exactly once), max / sum / expectations finish with
+// shfl.xor across the slices.  DS = 1 (one thread per pixel, the reference's sequential summation order) is
+// used whenever the confidence -- a discrete decision on trunc(sum p*d) -- is produced; DS = 4 gives the deep,
+// small stages (D = 48 / 24: 29 K / 115 K pixels) four times the threads.
+// ------------------------------------------------------------------------------------------------
+template <int D, int DS>
+__global__ void __launch_bounds__(128)
+softmax_regress_reg_kernel(const HeadArgs a)
+{
+    constexpr int PW = 32 / DS, DQ = D / DS;
+    static_assert(D % DS == 0, "slices must divide the depth");
+    const int lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int slice = lane / PW;
+    const size_t HW = (size_t)a.H * a.W;
+    const size_t pix = warp * PW + (lane % PW);
+    const bool ok = pix < (size_t)a.B * HW;
+    const int b = ok ? (int)(pix / HW) : 0;
+    const size_t p = ok ? pix % HW : 0;
+    const int d0 = slice * DQ;
+    const float* __restrict__ col = a.logits + ((size_t)b * D + d0) * HW + p;
+    float e[DQ];
+#pragma unroll
+    for (int d = 0; d < DQ; ++d) e[d] = ok ? __ldg(col + (size_t)d * HW) : 0.0f;
+    float m = e[0];
+#pragma unroll
+    for (int d = 1; d < DQ; ++d) m = fmaxf(m, e[d]);
+#pragma unroll
+    for (int o = PW; o < 32; o <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float sum = 0.0f;
+#pragma unroll
+    for (int d = 0; d < DQ; ++d) { e[d] = expf(__fsub_rn(e[d], m)); sum = __fadd_rn(sum, e[d]); }
+#pragma unroll
+    for (int o = PW; o < 32; o <<= 1) sum = __fadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, o));
+    float* __restrict__ pcol = a.prob ? a.prob + ((size_t)b * D + d0) * HW + p : nullptr;
+    const float* __restrict__ hcol = a.per_pixel ? a.hypos + ((size_t)b * D + d0) * HW + p : a.hypos + (size_t)b * D + d0;
+    const size_t hstride = a.per_pixel ? HW : 1;
+    float acc = 0.0f, eidx = 0.0f;
+    if (ok) {
+#pragma unroll
+        for (int d = 0; d < DQ; ++d) {
+            e[d] = __fdiv_rn(e[d], sum);
+            if (pcol) pcol[(size_t)d * HW] = e[d];
+            acc = __fadd_rn(acc, __fmul_rn(e[d], __ldg(hcol + (size_t)d * hstride)));    // regress.py:7
+            eidx = __fadd_rn(eidx, __fmul_rn(e[d], (float)(d0 + d)));                    // regress.py:15-17
+        }
+    }
+#pragma unroll
+    for (int o = PW; o < 32; o <<= 1) {
+        acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+        eidx = __fadd_rn(eidx, __shfl_xor_sync(0xffffffffu, eidx, o));
+    }
+    if (!ok || slice != 0) return;
+    if (a.depth) a.depth[pix] = acc;
+    if (DS == 1 && a.conf) {
+        // window sum around trunc(eidx): the column lives in registers, so select with a compile-time loop
+        const int Dp = D + a.pad_front + a.pad_back - a.conf_n + 1;
+        const int k = max(0, min((int)eidx, Dp - 1));
+        const int lo = k - a.pad_front, hi = lo + a.conf_n;       // window [lo, hi)
+        float s = 0.0f;
+#pragma unroll
+        for (int d = 0; d < DQ; ++d)
+            if (d >= lo && d < hi) s = __fadd_rn(s, e[d]);
+        const float fn = (float)a.conf_n;
+        store_upsampled(a.conf, __fmul_rn(fn, __fdiv_rn(s, fn)), b, (int)(p / a.W), (int)(p % a.W), a.H, a.W, a.up);
+    }
+}
+
+template <int D, int DS>
+static int launch_reg(const HeadArgs& a, size_t npix, cudaStream_t stream)
+{
+    const size_t blocks = (npix * DS + 127) / 128;
+    if (blocks > 0x7fffffffu) return MDF_ERR_UNSUPPORTED;
+    softmax_regress_reg_kernel<D, DS><<<(unsigned)blocks, 128, 0, stream>>>(a);
+    return launch_status();
+}
+
+// ------------------------------------------------------------------------------------------------
 // depth_regression / confidence_regress on a given probability volume (the reference's split API).
 // One thread per pixel, sequential over D: bit-identical to the reference's accumulation order.
 // ------------------------------------------------------------------------------------------------
@@ -210,7 +293,17 @@ int mdf_softmax_regress_fwd(const float* logits, const float* depth_hypos, int h
     if (dev < 0) return dev;
     DeviceGuard guard(dev);
     cudaStream_t stream = (cudaStream_t)stream_;
-    // depth slices per warp: sequential order whenever the discrete confidence index is produced
+    if (D == 8 || D == 24 || D == 48) {
+        if (confidence) {                                    // sequential order for the discrete index
+            if (D == 8) return launch_reg<8, 1>(a, npix, stream);
+            if (D == 24) return launch_reg<24, 1>(a, npix, stream);
+            return launch_reg<48, 1>(a, npix, stream);
+        }
+        if (D == 8) return launch_reg<8, 1>(a, npix, stream);
+        if (D == 24) return launch_reg<24, 4>(a, npix, stream);
+        return launch_reg<48, 4>(a, npix, stream);
+    }
+    // other depths: depth slices per warp; sequential order whenever the discrete confidence index is produced
     const int ds = (confidence || D < 16) ? 1 : 4;
     const size_t threads = npix * ds;
     const size_t blocks = (threads + 255) / 256;

@@ -88,6 +88,9 @@ __device__ inline void setup_work(int i, const SrcPtrs& src_projs, const float* 
 static __global__ void setup_kernel(SrcPtrs src_projs, const float* __restrict__ ref_proj, int V, int B,
                              float* __restrict__ rt_all, DepthWeightPtrs dw, int G, float* __restrict__ dwp)
 {
+    // programmatic dependent launch: a kernel launched behind this one with the stream-serialization attribute
+    // (the layout pass, which does not read anything computed here) may start right away
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     setup_work(blockIdx.x * blockDim.x + threadIdx.x, src_projs, ref_proj, V, B, rt_all, dw, G, dwp);
 }
 

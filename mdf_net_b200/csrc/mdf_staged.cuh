@@ -1,6 +1,6 @@
 // mdf_staged.cuh -- the hot kernel of the plane-sweep cost volume (C/G == 2) and its layout pass.
 //
-//   prep_kernel             (also does the per-call scalar work of mdf_setup.cuh in its first block)
+//   prep_kernel             (overlaps the 1-block setup kernel of mdf_setup.cuh: programmatic dependent launch)
 //                           source features NCHW -> "pair difference" maps in planar-float4 layout
 //                           S4[v][b][j][y][x] = (f[2g+1]-f[2g])*log2(e) for g = 4j..4j+3, and the reference
 //                           view -> q = 2*sigmoid(r[2g]-r[2g+1]) - 1.  softmax([a,b]) = [sigmoid(a-b),
@@ -25,6 +25,7 @@
 #include <cuda_runtime.h>
 #include <limits.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "mdf_common.cuh"
 #include "mdf_host.cuh"
@@ -38,7 +39,7 @@ struct FeaPtrs { const float* p[MDF_MAX_VIEWS]; };
 // prep: one thread per pixel of one view; blockIdx.y = view * B + b.
 // Loads are 128-byte coalesced rows of the NCHW planes, stores are 512-byte coalesced float4 rows.
 // ------------------------------------------------------------------------------------------------
-struct PrepSetup {          // the per-call scalar work (mdf_setup.cuh) rides along in block (0,0)
+struct PrepSetup {          // the per-call scalar work (mdf_setup.cuh) of the launch that precedes the layout pass
     SrcPtrs src_projs;
     const float* ref_proj;
     int V;
@@ -47,49 +48,113 @@ struct PrepSetup {          // the per-call scalar work (mdf_setup.cuh) rides al
     DepthWeightPtrs dw;
 };
 
+// Exit path of every block: wait for the setup kernel this launch overlaps with (programmatic dependent
+// launch), so that "prep has completed" implies "setup has completed" for whatever follows in the stream.
+__device__ __forceinline__ void prep_exit() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// One thread handles PX consecutive pixels of one view (PX = 4 when the planes are 16-byte aligned: LDG.128 per
+// channel plane, four float4 texels written back to back; PX = 1 otherwise).
+template <int PX>
 static __global__ void __launch_bounds__(256)
-prep_kernel(FeaPtrs feas, int B, int G, int HW, PrepSetup su,
-            float4* __restrict__ Q4, float4* __restrict__ CQ4, float* __restrict__ KS, float4* __restrict__ S4)
+prep_kernel(FeaPtrs feas, int B, int G, int HW, const float* __restrict__ conv_w,
+            float4* __restrict__ Q4, float4* __restrict__ CQ4, float4* __restrict__ S4)
 {
-    if (blockIdx.x == 0 && blockIdx.y == 0)
-        setup_work(threadIdx.x, su.src_projs, su.ref_proj, su.V, B, su.rt, su.dw, G, su.dwp);
-    const float* __restrict__ conv_w = su.dw.conv_w;
-    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pix >= HW) return;
+    const int pix = (blockIdx.x * blockDim.x + threadIdx.x) * PX;
+    if (pix >= HW) { prep_exit(); return; }
     const int v = blockIdx.y / B, b = blockIdx.y % B;
     const float* __restrict__ f = feas.p[v] + (size_t)b * 2 * G * HW + pix;
     const int J = G / 4;
+    // channel pair (a, c) = (f[2g], f[2g+1]) of PX pixels
+    auto load_pair = [&](int g, float (&a)[PX], float (&c)[PX]) {
+        if (PX == 4) {
+            const float4 va = __ldg(reinterpret_cast<const float4*>(f + (size_t)(2 * g) * HW));
+            const float4 vc = __ldg(reinterpret_cast<const float4*>(f + (size_t)(2 * g + 1) * HW));
+            a[0] = va.x; a[PX > 1 ? 1 : 0] = va.y; a[PX > 2 ? 2 : 0] = va.z; a[PX > 3 ? 3 : 0] = va.w;
+            c[0] = vc.x; c[PX > 1 ? 1 : 0] = vc.y; c[PX > 2 ? 2 : 0] = vc.z; c[PX > 3 ? 3 : 0] = vc.w;
+        } else {
+            a[0] = __ldg(f + (size_t)(2 * g) * HW);
+            c[0] = __ldg(f + (size_t)(2 * g + 1) * HW);
+        }
+    };
     if (v == 0) {
-        // reference view: q_g = 2*sigmoid(r[2g]-r[2g+1]) - 1, cq_g = conv_w[g]*q_g, ks = 0.5*sum_g cq_g
+        // reference view: q_g = 2*sigmoid(r[2g]-r[2g+1]) - 1, cq_g = conv_w[g]*q_g
         float4* __restrict__ qd = Q4 + (size_t)b * J * HW + pix;
         float4* __restrict__ cd = CQ4 + (size_t)b * J * HW + pix;
-        float ks = 0.0f;
-        for (int j = 0; j < J; ++j) {
-            float d[4];
+        for (int j = blockIdx.z; j < J; j += gridDim.z) {
+            float d[4][PX];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const float a = __ldg(f + (size_t)(8 * j + 2 * k) * HW), c = __ldg(f + (size_t)(8 * j + 2 * k + 1) * HW);
-                d[k] = 2.0f / (1.0f + expf(c - a)) - 1.0f;
+                float a[PX], c[PX];
+                load_pair(4 * j + k, a, c);
+#pragma unroll
+                for (int x = 0; x < PX; ++x) d[k][x] = 2.0f / (1.0f + expf(c[x] - a[x])) - 1.0f;
             }
-            const float4 c = make_float4(__ldg(conv_w + 4 * j) * d[0], __ldg(conv_w + 4 * j + 1) * d[1],
-                                         __ldg(conv_w + 4 * j + 2) * d[2], __ldg(conv_w + 4 * j + 3) * d[3]);
-            qd[(size_t)j * HW] = make_float4(d[0], d[1], d[2], d[3]);
-            cd[(size_t)j * HW] = c;
-            ks += (c.x + c.y) + (c.z + c.w);
+            const float w0 = __ldg(conv_w + 4 * j), w1 = __ldg(conv_w + 4 * j + 1), w2 = __ldg(conv_w + 4 * j + 2), w3 = __ldg(conv_w + 4 * j + 3);
+#pragma unroll
+            for (int x = 0; x < PX; ++x) {
+                qd[(size_t)j * HW + x] = make_float4(d[0][x], d[1][x], d[2][x], d[3][x]);
+                cd[(size_t)j * HW + x] = make_float4(w0 * d[0][x], w1 * d[1][x], w2 * d[2][x], w3 * d[3][x]);
+            }
         }
-        KS[(size_t)b * HW + pix] = 0.5f * ks;
+        prep_exit();
         return;
     }
+    // source views: blockIdx.z strides over the float4 planes (more blocks in flight at the coarse stage)
     float4* __restrict__ dst = S4 + ((size_t)(v - 1) * B + b) * J * HW + pix;
-    for (int j = 0; j < J; ++j) {
-        float d[4];
+    for (int j = blockIdx.z; j < J; j += gridDim.z) {
+        float d[4][PX];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const float a = __ldg(f + (size_t)(8 * j + 2 * k) * HW), c = __ldg(f + (size_t)(8 * j + 2 * k + 1) * HW);
-            d[k] = (c - a) * kLog2e;
+            float a[PX], c[PX];
+            load_pair(4 * j + k, a, c);
+#pragma unroll
+            for (int x = 0; x < PX; ++x) d[k][x] = (c[x] - a[x]) * kLog2e;
         }
-        dst[(size_t)j * HW] = make_float4(d[0], d[1], d[2], d[3]);
+#pragma unroll
+        for (int x = 0; x < PX; ++x) dst[(size_t)j * HW + x] = make_float4(d[0][x], d[1][x], d[2][x], d[3][x]);
     }
+    prep_exit();
+}
+
+static inline unsigned prep_zsplit(int HW, int images, int G);
+
+// setup (1 block: float64 projections + folded depth_weight) and the layout pass, overlapped by programmatic
+// dependent launch: the layout pass reads nothing the setup kernel writes, so it starts immediately.
+static int launch_setup_and_prep(const PrepSetup& su, const FeaPtrs& fp, int N, int B, int G, int HW,
+                                 float4* Q4, float4* CQ4, float4* S4, cudaStream_t stream)
+{
+    const int n = su.V * B;
+    setup_kernel<<<(n + 63) / 64, 64, 0, stream>>>(su.src_projs, su.ref_proj, su.V, B, su.rt, su.dw, G, su.dwp);
+    int st = launch_status();
+    if (st != MDF_OK) return st;
+    // 4 pixels per thread when every feature plane is 16-byte aligned
+    bool vec = (HW % 4) == 0;
+    for (int i = 0; i < N; ++i) vec = vec && (reinterpret_cast<uintptr_t>(fp.p[i]) & 15) == 0;
+    const int px = vec ? 4 : 1;
+    const int threads_x = (HW + px - 1) / px;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((threads_x + 255) / 256), (unsigned)(N * B), prep_zsplit(threads_x, N * B, G));
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (vec) MDF_CUDA_TRY(cudaLaunchKernelEx(&cfg, prep_kernel<4>, fp, B, G, HW, su.dw.conv_w, Q4, CQ4, S4));
+    else MDF_CUDA_TRY(cudaLaunchKernelEx(&cfg, prep_kernel<1>, fp, B, G, HW, su.dw.conv_w, Q4, CQ4, S4));
+    return MDF_OK;
+}
+
+// planes per source-view block column: split until the grid holds a few waves of 148 SMs x 8 blocks
+static inline unsigned prep_zsplit(int threads_x, int images, int G)
+{
+    const long long blocks = (long long)((threads_x + 255) / 256) * images;
+    if (const char* e = getenv("MDF_PREP_Z")) return (unsigned)max(1, min(atoi(e), G / 4));   // tuning knob
+    unsigned z = 1;
+    while (z < (unsigned)(G / 4) && blocks * z < 148LL * 8 * 4) z *= 2;
+    return z;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -159,10 +224,10 @@ __device__ __forceinline__ void sts128(uint32_t addr, float4 v)
 //   MINB   CTAs per SM the register allocation aims at
 //   CQS    keep the per-pixel similarity weights cq_g = conv_w[g]*q_g in shared memory instead of registers
 // ------------------------------------------------------------------------------------------------
-template <int G_, int PT_, int TH_, int PG_, int BW_, int BH_, int MINB_, bool CQS_>
+template <int G_, int PT_, int TH_, int PG_, int BW_, int BH_, int MINB_, bool CQS_, bool EARLY_ = true>
 struct StagedCfg {
     static constexpr int G = G_, PT = PT_, TH = TH_, PG = PG_, BW = BW_, BH = BH_, MINB = MINB_;
-    static constexpr bool CQS = CQS_;
+    static constexpr bool CQS = CQS_, EARLY = EARLY_;
     static constexpr int J = G / 4;
     static constexpr int NCQ = CQS ? 1 : G;
     static constexpr int THREADS = 32 * TH * PG;
@@ -185,7 +250,6 @@ struct StagedCfg {
 struct StagedArgs {
     const float* rt;      // [V][B][12]
     const float* dwp;     // folded depth_weight
-    const float* ks;      // [B][H][W]  0.5 * sum_g cq_g
     const float* hypos;
     float* out;           // (B,G,D,H,W)
     GridNorm gn;
@@ -275,7 +339,6 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
                                    : __ldg(a.hypos + (size_t)b * D + d);
         }
     }
-    const float ksum = pix_ok ? __ldg(a.ks + (size_t)b * HW + (size_t)py * W + px) : 0.0f;
     const float alpha = __ldg(a.dwp + 0), betap = __ldg(a.dwp + 1), fcw = __ldg(a.dwp + 2), fcb = __ldg(a.dwp + 3);
 
     float2 acc[PT][G / 2];                       // pairs of groups: the core runs on packed FFMA2 / FMUL2 / FADD2
@@ -290,12 +353,14 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
     uint32_t left = 0;                           // bit v: some sample of mine did not fit view v's box
     __syncthreads();                             // rt_s, mbarriers and control words are set up
 
-    // sample positions of my planes in view v; returns the mask of samples with at least one tap in bounds
-    auto positions = [&](int v, float (&ix)[PT], float (&iy)[PT], bool count_void) -> uint32_t {
-        uint32_t todo = 0;
-        float rt[12];
+    // rot | trans of view v from shared memory (issued early, consumed by `positions`)
+    auto load_rt = [&](int v, float (&rt)[12]) {
 #pragma unroll
         for (int k = 0; k < 12; ++k) rt[k] = lds32(rt_s + (uint32_t)(v * 12 + k) * 4u);
+    };
+    // sample positions of my planes; returns the mask of samples with at least one tap in bounds
+    auto positions = [&](const float (&rt)[12], float (&ix)[PT], float (&iy)[PT], bool count_void) -> uint32_t {
+        uint32_t todo = 0;
         const RotXYZ r = rot_xyz(rt, (float)px, (float)py);
 #pragma unroll
         for (int i = 0; i < PT; ++i) {
@@ -322,6 +387,8 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
         if (lane == 0) {
             const int set = kSetStride * (v & 1);
             if (kx != kNone) { atomicMin(ctl_nv + set + kMinX, key_floor(kx)); atomicMin(ctl_nv + set + kMinY, key_floor(ky)); }
+            // the mins must be performed before the arrival becomes visible (reductions and atomics with a
+            // return value are NOT ordered with each other without it: measured, not assumed)
             __threadfence_block();
             if (atomicAdd(ctl_nv + set + kCount, 1) == Cfg::WARPS - 1) {
                 __threadfence_block();
@@ -338,6 +405,7 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
     };
 
     float cq[NCQ];
+    float ksum = 0.0f;
     // gather the samples of `todo` that lie inside the box with origin (ox, oy); returns the rest
     auto gather = [&](uint32_t box, int ox, int oy, const float (&ix)[PT], const float (&iy)[PT], uint32_t todo) -> uint32_t {
 #pragma unroll
@@ -400,24 +468,34 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
     };
 
     float ix[PT], iy[PT];
-    uint32_t todo = positions(0, ix, iy, true);
+    uint32_t todo;
+    {
+        float rt[12];
+        load_rt(0, rt);
+        todo = positions(rt, ix, iy, true);
+    }
     announce(0, ix, iy, todo);
     mbar_wait(bar0 + 24, 0);                     // q / cq tiles have landed
-    if (!Cfg::CQS) {
+    {   // ksum = 0.5 * sum_g cq_g (z accumulates sum_g cq_g (p_g - 0.5)); cq stays in registers unless CQS
+        float s4 = 0.0f;
 #pragma unroll
         for (int j = 0; j < J; ++j) {
             const float4 c = lds128(cq_s + (uint32_t)j * TJ);
-            cq[(4 * j + 0) % NCQ] = c.x; cq[(4 * j + 1) % NCQ] = c.y; cq[(4 * j + 2) % NCQ] = c.z; cq[(4 * j + 3) % NCQ] = c.w;
+            if (!Cfg::CQS) { cq[(4 * j + 0) % NCQ] = c.x; cq[(4 * j + 1) % NCQ] = c.y; cq[(4 * j + 2) % NCQ] = c.z; cq[(4 * j + 3) % NCQ] = c.w; }
+            s4 += (c.x + c.y) + (c.z + c.w);
         }
+        ksum = 0.5f * s4;
     }
 
     // ---- main loop: no block-wide barrier; warps run freely, the box of view v+1 streams in while view v
-    //      is gathered ----
+    //      is gathered (its load is issued before anybody waits for view v) ----
     for (int v = 0; v < a.V; ++v) {
         float nx[PT], ny[PT];
         uint32_t ntodo = 0;
         if (v + 1 < a.V) {
-            ntodo = positions(v + 1, nx, ny, true);
+            float rt[12];
+            load_rt(v + 1, rt);
+            ntodo = positions(rt, nx, ny, true);
             announce(v + 1, nx, ny, ntodo);
         }
         mbar_wait(bar0 + 8u * (v & 1), (uint32_t)(v >> 1) & 1u);
@@ -428,6 +506,36 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
         for (int i = 0; i < PT; ++i) { ix[i] = nx[i]; iy[i] = ny[i]; }
         todo = ntodo;
     }
+
+    // ---- volume_sum / weight_sum (homoaggregate.py:46), coalesced 128-byte rows ----
+    auto epilogue = [&]() {
+        const float w_void = __ldg(a.dwp + 5);       // view weight of a sample with no tap in bounds (similarity 0.5)
+    #pragma unroll
+        for (int i = 0; i < PT; ++i) {
+            if (!((ok_mask >> i) & 1u)) continue;
+            const float nv = (float)((unsigned)(n_void >> (8 * i)) & 255u);
+            const float ws = fmaf(nv, w_void, wsum[i]);
+            const float rw = __frcp_rn(ws);
+            // out = 0.5 + q * ((acc + 0.5*nv*w_void) / ws - 0.5); void samples have similarity 0.5 in every group
+            const float c0 = fmaf(0.5f * nv * w_void, rw, -0.5f);
+            const float2 rw2 = make_float2(rw, rw), c02 = make_float2(c0, c0), half2 = make_float2(0.5f, 0.5f);
+            float* op = a.out + (((size_t)b * G) * D + (d0 + i)) * HW + (size_t)py * W + px;
+            const size_t gstride = (size_t)D * HW;
+    #pragma unroll
+            for (int j = 0; j < J; ++j) {
+                const float4 q = lds128(q_s + (uint32_t)j * TJ);
+                const float2 o01 = __ffma2_rn(make_float2(q.x, q.y), __ffma2_rn(acc[i][2 * j], rw2, c02), half2);
+                const float2 o23 = __ffma2_rn(make_float2(q.z, q.w), __ffma2_rn(acc[i][2 * j + 1], rw2, c02), half2);
+                op[0] = o01.x; op[gstride] = o01.y; op[2 * gstride] = o23.x; op[3 * gstride] = o23.y;
+                op += 4 * gstride;
+            }
+        }
+    };
+
+    // Warps whose samples all fitted write their results before the CTA-wide vote (their stores overlap the tail
+    // of the slower warps); the others write after the retry rounds.
+    const bool early = Cfg::EARLY && __all_sync(0xffffffffu, left == 0u);
+    if (early) epilogue();
 
     // ---- samples that did not fit their view's box (rough depth maps, silhouettes): synchronous staging
     //      rounds.  x origin = min over the samples left; y origin = min over those whose column fits, so the
@@ -440,7 +548,11 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
         while (views != 0u) {
             const int v = __ffs(views) - 1;
             views &= views - 1u;
-            todo = positions(v, ix, iy, false);
+            {
+                float rt[12];
+                load_rt(v, rt);
+                todo = positions(rt, ix, iy, false);
+            }
             {   // drop what round 0 already gathered
                 const int ox0 = ctl[kOrg + 2 * v], oy0 = ctl[kOrg + 2 * v + 1];
 #pragma unroll
@@ -483,28 +595,7 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
         }
     }
 
-    // ---- volume_sum / weight_sum (homoaggregate.py:46), coalesced 128-byte rows ----
-    const float w_void = __ldg(a.dwp + 5);       // view weight of a sample with no tap in bounds (similarity 0.5)
-#pragma unroll
-    for (int i = 0; i < PT; ++i) {
-        if (!((ok_mask >> i) & 1u)) continue;
-        const float nv = (float)((unsigned)(n_void >> (8 * i)) & 255u);
-        const float ws = fmaf(nv, w_void, wsum[i]);
-        const float rw = __frcp_rn(ws);
-        // out = 0.5 + q * ((acc + 0.5*nv*w_void) / ws - 0.5); void samples have similarity 0.5 in every group
-        const float c0 = fmaf(0.5f * nv * w_void, rw, -0.5f);
-        const float2 rw2 = make_float2(rw, rw), c02 = make_float2(c0, c0), half2 = make_float2(0.5f, 0.5f);
-        float* op = a.out + (((size_t)b * G) * D + (d0 + i)) * HW + (size_t)py * W + px;
-        const size_t gstride = (size_t)D * HW;
-#pragma unroll
-        for (int j = 0; j < J; ++j) {
-            const float4 q = lds128(q_s + (uint32_t)j * TJ);
-            const float2 o01 = __ffma2_rn(make_float2(q.x, q.y), __ffma2_rn(acc[i][2 * j], rw2, c02), half2);
-            const float2 o23 = __ffma2_rn(make_float2(q.z, q.w), __ffma2_rn(acc[i][2 * j + 1], rw2, c02), half2);
-            op[0] = o01.x; op[gstride] = o01.y; op[2 * gstride] = o23.x; op[3 * gstride] = o23.y;
-            op += 4 * gstride;
-        }
-    }
+    if (!early) epilogue();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -570,19 +661,19 @@ static int launch_staged(const StagedArgs& args, const StagedBuffers& buf, cudaS
 }
 
 // Tuning variants per G (algo = 16 + k selects variant k; variant 0 is the default).
-//                         G  PT TH PG  BW  BH MINB CQS
+//                         G  PT TH PG  BW  BH MINB CQS   EARLY
 using CfgG32_0 = StagedCfg<32, 1, 4, 2, 40, 7, 2, true>;     // 256 thr x 2 CTAs; 2 x 35 KiB boxes + 2 x 16 KiB tiles
-using CfgG32_1 = StagedCfg<32, 1, 4, 2, 40, 8, 2, true>;     // 2 x 40 KiB boxes
+using CfgG32_1 = StagedCfg<32, 1, 4, 2, 40, 7, 2, true, false>;
 using CfgG32_2 = StagedCfg<32, 1, 2, 4, 40, 6, 2, true>;     // tile 32x2, slab 4 planes
-using CfgG32_3 = StagedCfg<32, 1, 4, 1, 40, 7, 4, true>;     // 128 thr x 4 CTAs
+using CfgG32_3 = StagedCfg<32, 1, 2, 4, 40, 6, 2, true, false>;
 using CfgG16_0 = StagedCfg<16, 2, 4, 2, 64, 8, 2, false>;    // 256 thr x 2 CTAs, 2 x 32 KiB boxes, slab 4 planes
-using CfgG16_1 = StagedCfg<16, 1, 4, 2, 48, 8, 3, false>;    // 3 CTAs (85 registers), slab 2 planes
-using CfgG16_2 = StagedCfg<16, 2, 4, 1, 64, 8, 4, false>;    // 128 thr x 4 CTAs, slab 2 planes
-using CfgG16_3 = StagedCfg<16, 4, 4, 2, 64, 8, 2, true>;     // slab 8 planes
+using CfgG16_1 = StagedCfg<16, 2, 4, 2, 64, 8, 2, false, false>;
+using CfgG16_2 = StagedCfg<16, 2, 4, 2, 48, 8, 2, false>;    // narrower box
+using CfgG16_3 = StagedCfg<16, 1, 4, 2, 48, 8, 3, false>;    // 3 CTAs (85 registers), slab 2 planes
 using CfgG8_0  = StagedCfg<8, 4, 4, 2, 64, 10, 2, false>;    // 256 thr x 2 CTAs, 2 x 20 KiB boxes, slab 8 planes
-using CfgG8_1  = StagedCfg<8, 2, 4, 2, 64, 10, 3, false>;    // 3 CTAs, slab 4 planes
-using CfgG8_2  = StagedCfg<8, 4, 4, 1, 64, 10, 4, false>;    // 128 thr x 4 CTAs, slab 4 planes
-using CfgG8_3  = StagedCfg<8, 8, 4, 1, 64, 10, 2, false>;    // 128 thr, slab 8 planes
+using CfgG8_1  = StagedCfg<8, 4, 4, 2, 64, 10, 2, false, false>;
+using CfgG8_2  = StagedCfg<8, 2, 4, 2, 64, 10, 3, false>;    // 3 CTAs, slab 4 planes
+using CfgG8_3  = StagedCfg<8, 4, 4, 2, 48, 8, 2, false>;     // smaller box
 
 static int launch_staged_variant(int G, int variant, const StagedArgs& a, const StagedBuffers& S, cudaStream_t stream)
 {

@@ -28,8 +28,8 @@ __all__ = ["cost_volume", "homo_warp", "variance_volume", "softmax_regress", "de
 # kernels launched through this module since the last reset (bench.py's `gpu_launches`)
 _launches = 0
 
-# kernel launches per C-ABI call (staged: prep [+ setup work] + hot kernel; direct: setup + kernel; see csrc/*.cu)
-_LAUNCHES_STAGED, _LAUNCHES_DIRECT, _LAUNCHES_SIMPLE = 2, 2, 1
+# kernel launches per C-ABI call (staged: setup + prep + hot kernel; direct: setup + kernel; see csrc/*.cu)
+_LAUNCHES_STAGED, _LAUNCHES_DIRECT, _LAUNCHES_SIMPLE = 3, 2, 1
 
 
 def launch_count() -> int:
@@ -299,7 +299,7 @@ def cost_volume_train(features: List[Tensor], ref_proj: Tensor, src_projs: List[
         params[4].data_ptr(), float(bn_eps), params[5].data_ptr(), params[6].data_ptr(), int(training),
         B, C, groups, D, H, W, out.data_ptr(), stats.data_ptr(), ws.data_ptr(), ws.numel(), _stream(out))
     _cabi.check("mdf_cost_volume_train_fwd", st)
-    _count(4 if training else 3)
+    _count(5 if training else 4)
     return out, stats
 
 
@@ -334,7 +334,7 @@ def cost_volume_bwd(features: List[Tensor], ref_proj: Tensor, src_projs: List[Te
         B, C, groups, D, H, W, cv.data_ptr(), go.data_ptr(), _cabi.ptr_array([g.data_ptr() for g in gfeats]),
         gparams.data_ptr(), ws.data_ptr(), ws.numel(), _stream(cv))
     _cabi.check("mdf_cost_volume_bwd", st)
-    _count(7 if training else 5)
+    _count(8 if training else 6)
     return gfeats, gparams
 
 

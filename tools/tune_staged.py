@@ -37,7 +37,7 @@ for s, st in enumerate(view):
             base = out.clone()
         err = float((out - base).abs().max())
         ts = []
-        for _ in range(5):
+        for _ in range(9):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); ops.cost_volume(*args, 16 + variant); e1.record()
