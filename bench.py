@@ -175,6 +175,7 @@ def cpu_sample(view, frac_rows: float):
 def cpu_baseline(view, budget_s: float, batch: int):
     from oracle import c_oracle as co
     co.build()
+    co.set_num_threads(co.host_threads())
     probe = cpu_sample(view, 1.0 / 16.0)                     # calibrate: 1/16 of the rows
     frac = min(1.0, max(1.0 / 16.0, budget_s / (probe * 16.0)))
     t = cpu_sample(view, frac)
@@ -191,6 +192,7 @@ def run_reference(args, workload):
         return
     from oracle import c_oracle as co
     co.build()
+    co.set_num_threads(co.host_threads())      # torchrun exports OMP_NUM_THREADS=1
     h0, w0, nviews, batch = WORKLOADS[workload]
     view = make_view(h0, w0, nviews, batch, seed=1)
     probe = cpu_sample(view, 1.0 / 16.0)

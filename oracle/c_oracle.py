@@ -206,3 +206,23 @@ def num_threads() -> int:
         return 1
     fn.restype = ctypes.c_int
     return int(fn())
+
+
+def set_num_threads(n: int) -> int:
+    """Use `n` OpenMP threads from now on (torchrun exports OMP_NUM_THREADS=1; the CPU baseline wants them all).
+    Returns the number in effect (1 when built without OpenMP)."""
+    lib = _lib("f32")
+    try:
+        fn = lib.omp_set_num_threads
+    except AttributeError:
+        return 1
+    fn.argtypes = [ctypes.c_int]
+    fn(int(max(1, n)))
+    return num_threads()
+
+
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1

@@ -16,6 +16,7 @@ from mdf_net_b200 import synthetic as syn
 
 pytestmark = pytest.mark.gpu
 
+FULL = dict(h0=1152, w0=1600, nviews=5)     # BASELINE.json configs[1]
 INTERVAL = (935.0 - 425.0) / 47.0     # stage-0 hypothesis interval (depthhypos.py:33, dtueval.py:47)
 COST_TOL = 1e-5
 ELEM_TOL = 5e-5
@@ -196,6 +197,30 @@ def test_rough_hypotheses_need_several_staging_rounds():
         assert_cost_close(out, ref, f"rough stage {stage}", truth=truth)
 
 
+def test_eleven_views_like_tanks_and_temples():
+    """config.py:119: EvalTanks.nviews = 11 (10 source views); also the 1920x1056 aspect ratio."""
+    from oracle import c_oracle as co
+    for stage in (0, 2):
+        c = stage_case(stage, 1056 // 4, 1920 // 4, 11, seed=900)
+        kw = dict(ref_proj=c["ref_proj"], src_projs=c["src_projs"])
+        ref = co.vector_aggregate(c["features"], c["hypos"], c["params"], c["G"], **kw)
+        truth = co.vector_aggregate(c["features"], c["hypos"], c["params"], c["G"], prec="f64", **kw)
+        out = run_cost_volume(c["features"], c["ref_proj"], c["src_projs"], c["hypos"], c["params"], c["G"], 1)
+        assert_cost_close(out, ref, f"11 views stage {stage}", truth=truth)
+
+
+def test_scene_hypotheses_full_size():
+    """The benchmark's own stage-1/2 hypotheses (synthetic.scene_hypos) at 1600x1152 N=5 against the oracle."""
+    from oracle import c_oracle as co
+    c = stage_case(1, FULL["h0"], FULL["w0"], FULL["nviews"], seed=950)
+    c["hypos"] = syn.scene_hypos(1, c["D"], c["H"], c["W"], seed=951)
+    kw = dict(ref_proj=c["ref_proj"], src_projs=c["src_projs"])
+    ref = co.vector_aggregate(c["features"], c["hypos"], c["params"], c["G"], **kw)
+    truth = co.vector_aggregate(c["features"], c["hypos"], c["params"], c["G"], prec="f64", **kw)
+    out = run_cost_volume(c["features"], c["ref_proj"], c["src_projs"], c["hypos"], c["params"], c["G"])
+    assert_cost_close(out, ref, "scene hypotheses stage 1", truth=truth)
+
+
 def test_corenet_stages_teacher_forced():
     """Replay the three stages of a whole reference CoreNet forward through the drop-in units."""
     import mdf_net_b200 as mdf
@@ -301,7 +326,6 @@ def test_head_vs_oracle_config1(stage):
 
 
 # ------------------------------------------------------------- full-size properties (BASELINE cfg 2)
-FULL = dict(h0=1152, w0=1600, nviews=5)
 
 
 @pytest.mark.parametrize("stage", [0, 1, 2])
