@@ -46,7 +46,12 @@ WORKLOADS = {
     "tanks_1920x1056_n7": (1056, 1920, 7, 1),    # configs[3]
 }
 LAUNCHES_PER_STEP = 3 * (3 + 1)   # per stage: setup + prep + staged cost-volume kernel, + the fused head kernel
-FALLBACK_HBM_GBS = 6650.0      # /opt/skills/guides/B200_PROFILING.md fallback
+FALLBACK_HBM_GBS = 6650.0
+# dram__bytes_read.sum + dram__bytes_write.sum of the three cost_volume_staged_kernel launches of one step, from
+# the ncu --set full capture summarised in profiles/r01_final_staged_ncu_full_summary.txt (154.6 + 275.4 + 178.4 MB;
+# below the algorithmic 755.7 MB because the layout pass leaves S4 in L2 and part of the volume is still dirty in
+# L2 when the kernel ends)
+NCU_DRAM_TRAFFIC = {"dtu_1600x1152_n5": 608.4e6}      # /opt/skills/guides/B200_PROFILING.md fallback
 
 
 # ----------------------------------------------------------------------------------------- workload
@@ -220,7 +225,7 @@ def run_b200(args, workload):
     import torch.distributed as dist
 
     import mdf_net_b200 as mdf
-    from mdf_net_b200 import ops
+    from mdf_net_b200 import _cabi, ops
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -259,10 +264,12 @@ def run_b200(args, workload):
     dev_views = [convert(v, pin=False) for v in host_views]
     pin_views = [convert(v, pin=True) for v in host_views] if not args.no_e2e else None
 
-    def hot_path(view, events=None):
+    def hot_path(view, events=None, kernel_events=None):
         """3 x (fused cost volume -> fused head).  Returns the per-stage depth maps and the confidence."""
         depths, conf = [], None
         for s, st in enumerate(view):
+            if kernel_events is not None:      # events around the hot kernel alone, recorded inside the library
+                _cabi.lib().mdf_debug_time_next_hot_kernel(kernel_events[s][0].cuda_event, kernel_events[s][1].cuda_event)
             if events is not None:
                 events[s][0].record()
             cv = ops.cost_volume(st["features"], st["ref_proj"], st["src_projs"], st["hypos"], *st["w"][:5], st["eps"],
@@ -328,16 +335,24 @@ def run_b200(args, workload):
         if sampler:
             sampler.start()
         # (a) instrumented eager pass: CUDA events around every fused cost-volume call -> roofline numbers
-        stage_events = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(3)]
-                        for _ in range(args.steps)]
+        def make_events():
+            evs = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(3)]
+                   for _ in range(args.steps)]
+            for step in evs:              # torch creates the CUDA event lazily: force it so the library gets a handle
+                for a, b in step:
+                    a.record(); b.record()
+            return evs
+        stage_events, kernel_events = make_events(), make_events()
+        torch.cuda.synchronize()
         t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t_start.record()
         for i in range(args.steps):
-            hot_path(dev_views[i % 2], stage_events[i])
+            hot_path(dev_views[i % 2], stage_events[i], kernel_events[i])
         t_end.record()
         barrier()
         eager_ms = t_start.elapsed_time(t_end)
         cv_ms = [statistics.mean(ev[s][0].elapsed_time(ev[s][1]) for ev in stage_events) for s in range(3)]
+        hot_ms = [statistics.mean(ev[s][0].elapsed_time(ev[s][1]) for ev in kernel_events) for s in range(3)]
 
         # (b) the timed region: the same K steps, replayed from CUDA graphs (one per input set) so that the
         #     host's launch overhead is not on the critical path; falls back to eager launches if capture fails
@@ -421,10 +436,15 @@ def run_b200(args, workload):
                                              "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback",
+                         "traffic": NCU_DRAM_TRAFFIC.get(workload), "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback",
                          "kernel": "mdf_cost_volume_fwd (setup_kernel || prep_kernel, then cost_volume_staged_kernel), 3 calls of the op per step",
                          "algorithmic_bytes_per_step": sum(cv_bytes),
-                         "per_stage": [{"bytes": b, "ms": ms, "GB/s": b / 1e9 / (ms / 1e3)} for b, ms in zip(cv_bytes, cv_ms)],
+                         "per_stage": [{"bytes": b, "ms": ms, "GB/s": b / 1e9 / (ms / 1e3), "hot_kernel_ms": hk}
+                                       for b, ms, hk in zip(cv_bytes, cv_ms, hot_ms)],
+                         "hot_kernel": "cost_volume_staged_kernel<G=32|16|8>: events recorded inside the library around the kernel alone",
+                         "hot_kernel_ms_per_step": sum(hot_ms),
+                         "hot_kernel_share_of_step": sum(hot_ms) / (eager_ms / args.steps),
+                         "hot_kernel_GBps": sum(cv_bytes) / 1e9 / (sum(hot_ms) / 1e3),
                          "timed_in": "instrumented eager pass of the same K steps (CUDA events around each call)",
                          "eager_ms_per_step": eager_ms / args.steps,
                          "share_of_step": sum(cv_ms) / (eager_ms / args.steps)},

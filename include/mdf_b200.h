@@ -172,6 +172,11 @@ MDF_API int mdf_debug_sample_positions(const float *rot_trans, const float *dept
                                        int D, int H, int W, float *ix /* (D,H,W) */, float *iy /* (D,H,W) */,
                                        mdf_stream_t stream);
 
+/* The next mdf_cost_volume_fwd[_ex] call of the calling thread that takes the staged path records the two
+ * cudaEvent_t around its hot kernel (cost_volume_staged_kernel) only -- not around the layout pass -- and
+ * then forgets them.  bench.py uses it for the live per-kernel roofline numbers.  Pass NULL, NULL to cancel. */
+MDF_API int mdf_debug_time_next_hot_kernel(void *start_event, void *stop_event);
+
 #ifdef __cplusplus
 }
 #endif

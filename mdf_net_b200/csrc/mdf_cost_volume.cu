@@ -25,6 +25,7 @@
 namespace mdf {
 
 thread_local int g_last_cuda_error = 0;
+thread_local cudaEvent_t g_time_events[2] = {nullptr, nullptr};
 
 // ------------------------------------------------------------------------------------------------
 // workspace layout (all offsets 256-byte aligned)
@@ -384,6 +385,14 @@ int mdf_cost_volume_fwd(const float* const* features, int N, const float* ref_pr
     return mdf_cost_volume_fwd_ex(features, N, ref_proj, src_projs, depth_hypos, hypos_per_pixel, conv_weight, bn_weight,
                                   bn_bias, bn_mean, bn_var, bn_eps, fc_weight, fc_bias, B, C, G, D, H, W, cost_volume,
                                   workspace, workspace_bytes, 0, stream);
+}
+
+int mdf_debug_time_next_hot_kernel(void* start_event, void* stop_event)
+{
+    if ((start_event == nullptr) != (stop_event == nullptr)) return MDF_ERR_NULL_POINTER;
+    g_time_events[0] = (cudaEvent_t)start_event;
+    g_time_events[1] = (cudaEvent_t)stop_event;
+    return MDF_OK;
 }
 
 int mdf_debug_sample_positions(const float* rot_trans, const float* depth_hypos, int hypos_per_pixel, int D, int H, int W,

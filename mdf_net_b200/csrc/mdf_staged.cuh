@@ -638,6 +638,9 @@ static int encode_planes(CUtensorMap* tmap, const float* base, int W, int H, lon
 
 struct StagedBuffers { const float* S4; const float* Q4; const float* CQ4; };
 
+// diagnostic (mdf_debug_time_next_hot_kernel): events recorded around the next hot-kernel launch of this thread
+extern thread_local cudaEvent_t g_time_events[2];
+
 template <class Cfg>
 static int launch_staged(const StagedArgs& args, const StagedBuffers& buf, cudaStream_t stream)
 {
@@ -656,7 +659,10 @@ static int launch_staged(const StagedArgs& args, const StagedBuffers& buf, cudaS
     const long long items = (long long)a.tiles_x * a.tiles_y * a.slabs * a.B;
     if (items <= 0) return MDF_OK;
     if (items > INT_MAX) return MDF_ERR_UNSUPPORTED;
+    const bool timed = g_time_events[0] != nullptr;
+    if (timed) cudaEventRecord(g_time_events[0], stream);
     kern<<<(unsigned)items, dim3(32, Cfg::TH, Cfg::PG), Cfg::SMEM, stream>>>(maps, a);
+    if (timed) { cudaEventRecord(g_time_events[1], stream); g_time_events[0] = g_time_events[1] = nullptr; }
     return launch_status();
 }
 
