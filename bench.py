@@ -87,6 +87,17 @@ def algorithmic_bytes(h0, w0, nviews, batch):
     return cv, head
 
 
+def onchip_bound(h0, w0, nviews, batch, sm_mhz, hot_ms):
+    """The gather core's own ceiling: every (source view, group, depth, pixel) evaluation reads 4 taps
+    x 4 B from shared memory; 148 SMs x 128 B/clk.  Reported next to the HBM roofline because it, not HBM, bounds
+    the kernel (ncu: l1tex data pipe 69 / 57 / 45 %, DRAM 10-16 %)."""
+    evals = sum((nviews - 1) * g * d * h * w * batch for (h, w), d, g in
+                zip(syn.stage_shapes(h0, w0), syn.STAGE_DEPTHS, syn.STAGE_GROUPS))
+    floor_ms = evals * 16.0 / (148 * 128 * sm_mhz * 1e6) * 1e3
+    return {"resource": "shared-memory gather bandwidth", "group_evaluations_per_step": evals, "bytes_per_evaluation": 16,
+            "floor_ms": floor_ms, "frac": floor_ms / hot_ms if hot_ms > 0 else None}
+
+
 def make_config(workload):
     h0, w0, nviews, batch = WORKLOADS[workload]
     stages = [f"{h}x{w} C{c} D{d} G{g}" for (h, w), c, d, g in
@@ -445,6 +456,7 @@ def run_b200(args, workload):
                          "hot_kernel_ms_per_step": sum(hot_ms),
                          "hot_kernel_share_of_step": sum(hot_ms) / (eager_ms / args.steps),
                          "hot_kernel_GBps": sum(cv_bytes) / 1e9 / (sum(hot_ms) / 1e3),
+                         "onchip_bound": onchip_bound(h0, w0, nviews, batch, (clocks or {}).get("sm_mhz") or 1965.0, sum(hot_ms)),
                          "timed_in": "instrumented eager pass of the same K steps (CUDA events around each call)",
                          "eager_ms_per_step": eager_ms / args.steps,
                          "share_of_step": sum(cv_ms) / (eager_ms / args.steps)},

@@ -155,9 +155,14 @@ softmax_regress_reg_kernel(const HeadArgs a)
     const size_t p = ok ? pix % HW : 0;
     const int d0 = slice * DQ;
     const float* __restrict__ col = a.logits + ((size_t)b * D + d0) * HW + p;
-    float e[DQ];
+    const float* __restrict__ hcol = a.per_pixel ? a.hypos + ((size_t)b * D + d0) * HW + p : a.hypos + (size_t)b * D + d0;
+    const size_t hstride = a.per_pixel ? HW : 1;
+    // logits and hypotheses of the column: 2*DQ independent loads in flight, one round trip to DRAM
+    float e[DQ], hv[DQ];
 #pragma unroll
     for (int d = 0; d < DQ; ++d) e[d] = ok ? __ldg(col + (size_t)d * HW) : 0.0f;
+#pragma unroll
+    for (int d = 0; d < DQ; ++d) hv[d] = ok ? __ldg(hcol + (size_t)d * hstride) : 0.0f;
     float m = e[0];
 #pragma unroll
     for (int d = 1; d < DQ; ++d) m = fmaxf(m, e[d]);
@@ -169,15 +174,13 @@ softmax_regress_reg_kernel(const HeadArgs a)
 #pragma unroll
     for (int o = PW; o < 32; o <<= 1) sum = __fadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, o));
     float* __restrict__ pcol = a.prob ? a.prob + ((size_t)b * D + d0) * HW + p : nullptr;
-    const float* __restrict__ hcol = a.per_pixel ? a.hypos + ((size_t)b * D + d0) * HW + p : a.hypos + (size_t)b * D + d0;
-    const size_t hstride = a.per_pixel ? HW : 1;
     float acc = 0.0f, eidx = 0.0f;
     if (ok) {
 #pragma unroll
         for (int d = 0; d < DQ; ++d) {
             e[d] = __fdiv_rn(e[d], sum);
             if (pcol) pcol[(size_t)d * HW] = e[d];
-            acc = __fadd_rn(acc, __fmul_rn(e[d], __ldg(hcol + (size_t)d * hstride)));    // regress.py:7
+            acc = __fadd_rn(acc, __fmul_rn(e[d], hv[d]));                                // regress.py:7
             eidx = __fadd_rn(eidx, __fmul_rn(e[d], (float)(d0 + d)));                    // regress.py:15-17
         }
     }

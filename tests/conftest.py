@@ -19,6 +19,22 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_sessionstart(session):
+    """The CUDA library and the oracle are built artefacts (git-ignored): build whatever is missing.  An existing
+    library is used as it is (the GPU box runs the files that travelled with the snapshot)."""
+    try:
+        from mdf_net_b200 import build
+        if not os.path.exists(build.LIB_PATH):
+            build.build_library()
+    except Exception as e:  # pragma: no cover - reported by the tests that need the library
+        print(f"[conftest] could not build libmdf_b200.so: {e}")
+    try:
+        from oracle import c_oracle
+        c_oracle.build()
+    except Exception as e:  # pragma: no cover
+        print(f"[conftest] could not build the oracle: {e}")
+
+
 def pytest_collection_modifyitems(config, items):
     try:
         import torch

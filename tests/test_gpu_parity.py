@@ -382,6 +382,15 @@ def test_full_size_head_properties():
     assert np.abs(d2.cpu().numpy() - depth).max() < 1e-3 * INTERVAL
 
 
+def test_forward_is_deterministic():
+    """No atomics on the data path of the eval forward: two runs give the same bits (also across staging variants
+    that change tile / box shapes only)."""
+    c = stage_case(2, 512, 640, 4, seed=1234)
+    a = run_cost_volume(c["features"], c["ref_proj"], c["src_projs"], c["hypos"], c["params"], c["G"], 1)
+    b = run_cost_volume(c["features"], c["ref_proj"], c["src_projs"], c["hypos"], c["params"], c["G"], 1)
+    assert np.array_equal(a, b)
+
+
 # ------------------------------------------------------------------------------------ error handling
 def test_errors_and_empty_inputs():
     import mdf_net_b200 as mdf
