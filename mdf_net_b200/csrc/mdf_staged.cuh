@@ -307,6 +307,7 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
     gf.g = a.gn;
     gf.r_half_wm1 = refine_rcp(a.gn.half_wm1);
     gf.r_half_hm1 = refine_rcp(a.gn.half_hm1);
+    const bool tiny_map = !(a.gn.half_wm1 > 0.25f && a.gn.half_hm1 > 0.25f);   // W or H == 1: the normalisation divides by 0
 
     if (tid == 0) {
         mbar_init(bar0, 1); mbar_init(bar0 + 8, 1); mbar_init(bar0 + 16, 1); mbar_init(bar0 + 24, 1);
@@ -362,9 +363,17 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
     auto positions = [&](const float (&rt)[12], float (&ix)[PT], float (&iy)[PT], bool count_void) -> uint32_t {
         uint32_t todo = 0;
         const RotXYZ r = rot_xyz(rt, (float)px, (float)py);
+        // all planes through the branch-free fast chain first (PT independent dependency chains in one basic
+        // block); the IEEE chain only if some lane of the warp met an operand the fast divisions do not cover
+        bool exact = !tiny_map;
+#pragma unroll
+        for (int i = 0; i < PT; ++i) exact = sample_position_try(r, rt, depth[i], gf, ix[i], iy[i]) && exact;
+        if (__any_sync(0xffffffffu, !exact)) {
+#pragma unroll
+            for (int i = 0; i < PT; ++i) sample_position(r, rt, depth[i], gf.g, ix[i], iy[i]);
+        }
 #pragma unroll
         for (int i = 0; i < PT; ++i) {
-            sample_position_fast(r, rt, depth[i], gf, ix[i], iy[i]);
             const bool inside = (ix[i] > -1.0f) && (ix[i] < a.gn.fw) && (iy[i] > -1.0f) && (iy[i] < a.gn.fh);
             if ((ok_mask >> i) & 1u) {
                 if (inside) todo |= 1u << i;
