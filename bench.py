@@ -48,10 +48,10 @@ WORKLOADS = {
 LAUNCHES_PER_STEP = 3 * (3 + 1)   # per stage: setup + prep + staged cost-volume kernel, + the fused head kernel
 FALLBACK_HBM_GBS = 6650.0
 # dram__bytes_read.sum + dram__bytes_write.sum of the three cost_volume_staged_kernel launches of one step, from
-# the ncu --set full capture summarised in profiles/r01_final_staged_ncu_full_summary.txt (154.6 + 275.4 + 178.4 MB;
+# the ncu --set full capture summarised in profiles/r01_final_staged_ncu_full_summary.txt (152.2 + 274.4 + 177.7 MB;
 # below the algorithmic 755.7 MB because the layout pass leaves S4 in L2 and part of the volume is still dirty in
 # L2 when the kernel ends)
-NCU_DRAM_TRAFFIC = {"dtu_1600x1152_n5": 608.4e6}      # /opt/skills/guides/B200_PROFILING.md fallback
+NCU_DRAM_TRAFFIC = {"dtu_1600x1152_n5": 604.3e6}      # /opt/skills/guides/B200_PROFILING.md fallback
 
 
 # ----------------------------------------------------------------------------------------- workload

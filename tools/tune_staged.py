@@ -21,6 +21,8 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for s, st in enumerate(view):
     if rough and s > 0:
         st["hypos"] = syn.pixel_hypos(batch, st["D"], st["H"], st["W"], seed=5, smooth="iid" not in sys.argv)
+    if "wide" in sys.argv and s > 0:     # the widest search range HyposByFit allows: 0.2 * (dmax - dmin) = 102 mm
+        st["hypos"] = syn.scene_hypos(batch, st["D"], st["H"], st["W"], seed=1, range_mm=(40.0, 102.0))
     p = st["params"]
     f32 = lambda v: cu(np.asarray(v, np.float32).reshape(-1))
     args = ([cu(f) for f in st["features"]], cu(st["ref_proj"]), [cu(q) for q in st["src_projs"]], cu(st["hypos"]),
