@@ -25,7 +25,6 @@
 #include <cuda_runtime.h>
 #include <limits.h>
 #include <stdint.h>
-#include <stdlib.h>
 
 #include "mdf_common.cuh"
 #include "mdf_host.cuh"
@@ -151,7 +150,6 @@ static int launch_setup_and_prep(const PrepSetup& su, const FeaPtrs& fp, int N, 
 static inline unsigned prep_zsplit(int threads_x, int images, int G)
 {
     const long long blocks = (long long)((threads_x + 255) / 256) * images;
-    if (const char* e = getenv("MDF_PREP_Z")) return (unsigned)max(1, min(atoi(e), G / 4));   // tuning knob
     unsigned z = 1;
     while (z < (unsigned)(G / 4) && blocks * z < 148LL * 8 * 4) z *= 2;
     return z;

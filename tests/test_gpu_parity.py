@@ -382,6 +382,24 @@ def test_full_size_head_properties():
     assert np.abs(d2.cpu().numpy() - depth).max() < 1e-3 * INTERVAL
 
 
+def test_tiny_maps_and_maximum_views():
+    """Feature maps smaller than one tile / one TMA box, a 1-pixel-wide map (the reference's normalisation divides by
+    (W-1)/2 = 0 there: every sample is invalid -> 0.5), and MDF_MAX_VIEWS = 32 views."""
+    from oracle import c_oracle as co
+    for (H, W, N) in [(2, 3, 3), (5, 33, 2), (3, 1, 3), (6, 8, 32)]:
+        C, G, D = 16, 8, 3
+        K, E = syn.camera_rig(1, N, H * 8, max(W, 2) * 8, seed=41)
+        P = syn.projection_matrices(K, E, level_div=8.0)
+        feats = syn.smooth_features(1, N, C, H, W, seed=42)
+        hyp = syn.pixel_hypos(1, D, H, W, seed=43)
+        p = syn.depth_weight_params(G, seed=44)
+        ref = co.vector_aggregate(feats, hyp, p, G, ref_proj=P[:, 0], src_projs=[P[:, v] for v in range(1, N)])
+        for algo in (1, 2):
+            out = run_cost_volume(feats, P[:, 0], [P[:, v] for v in range(1, N)], hyp, p, G, algo)
+            assert np.isfinite(out).all()
+            assert np.abs(out - np.nan_to_num(ref, nan=0.5)).max() < 2e-5, (H, W, N, algo)
+
+
 def test_forward_is_deterministic():
     """No atomics on the data path of the eval forward: two runs give the same bits (also across staging variants
     that change tile / box shapes only)."""
