@@ -163,6 +163,18 @@ MDF_API int mdf_confidence_fwd(const float *prob, int B, int D, int H, int W,
                        int n, int pad_front, int pad_back, int upsample,
                        float *confidence, mdf_stream_t stream);
 
+/* ---- next-stage depth hypotheses: HyposByFit (net/unit/depthhypos.py:27-76) -----------------
+ * curve: 1 = "gauss1" (:169-215), 2 = "laplace" (:78-125).  mdf_hypos_fit_fwd gives the fitted scale s (B,H,W) of
+ * every pixel's probability column; mdf_hypos_generate_fwd upsamples s and depth x2 (bilinear, align_corners
+ * = False) when `upsample`, derives the search range from prob_thresh, applies the reference's clamps and writes
+ * `ndepths` hypotheses (B,ndepths,2H|H,2W|W).  depth_range: (B,2) device floats (min, max).
+ * Stage 0's uniform hypotheses (:31-38) are B*ndepths numbers and stay in torch. */
+MDF_API int mdf_hypos_fit_fwd(const float *prob, const float *depth_hypos, int hypos_per_pixel, const float *depth,
+                              int curve, int B, int D, int H, int W, float *s, mdf_stream_t stream);
+MDF_API int mdf_hypos_generate_fwd(const float *depth, const float *s, const float *depth_range, int curve,
+                                   float prob_thresh, int upsample, int B, int H, int W, int ndepths,
+                                   float *depth_hypos, mdf_stream_t stream);
+
 /* ---- diagnostics --------------------------------------------------------------------------- */
 /* Sample positions (pixel units of the source map, as grid_sample uses them: base.py:102-119 +
  * ATen unnormalize) of every (d, y, x) for one precomposed projection `rot_trans` (12 floats:

@@ -93,3 +93,34 @@ def softmax_regress(logits: Tensor, depth_hypos: Tensor, want_confidence: bool =
     line): returns (prob_volume, depth[, confidence at `upsample` x resolution])."""
     prob, depth, conf = ops.softmax_regress(logits, depth_hypos, True, want_confidence, 4, 1, 2, upsample)
     return (prob, depth, conf) if want_confidence else (prob, depth)
+
+
+class HyposByFit(nn.Module):
+    """Depth hypotheses of a stage, mirroring net/unit/depthhypos.py:10-76 (same constructor and forward).
+
+    depth is None (stage 0): `ndepths` uniform hypotheses over depth_range, (B,ndepths,1,1) -- B*ndepths numbers,
+    computed with the same two torch ops as the reference (:31-38).  Otherwise: per-pixel curve fit of the previous
+    stage's probability volume ("gauss1" or "laplace"), x2 upsampling of the fitted scale and of the depth, search
+    range from prob_thresh, the reference's clamps, `ndepths` hypotheses per pixel -- two kernels of libmdf_b200.so
+    instead of ~40 ATen launches, a batched 3x3 torch.inverse and Python loops over planes and batch items.
+    No gradient flows through the reference's version either (depthhypos.py:40 is under no_grad).
+    """
+
+    def __init__(self, ndepths: int = 16, curve_calss: str = "gauss1", prob_thresh: float = 0.95):
+        super().__init__()
+        self.ndepths, self.curve_calss, self.prob_thresh = ndepths, curve_calss, torch.tensor(prob_thresh)
+
+    def forward(self, depth, depth_range, prob_volume, depth_hypos, upsample: bool = False):
+        B = depth_range.shape[0]
+        if depth is None:
+            dmin, dmax = depth_range[:, 0].float().view(B, 1), depth_range[:, 1].float().view(B, 1)
+            interval = (dmax - dmin) / (self.ndepths - 1)
+            steps = torch.arange(0, self.ndepths, device=depth_range.device).reshape(1, -1)
+            return (dmin + steps * interval).view(B, self.ndepths, 1, 1)
+        if self.curve_calss not in ("gauss1", "laplace"):
+            raise NotImplementedError(f"HyposByFit: curve {self.curve_calss!r} is not wired by the reference's config.py "
+                                      "and not implemented here")
+        with torch.no_grad():
+            s = ops.hypos_fit(prob_volume, depth_hypos, depth, self.curve_calss)
+            return ops.hypos_generate(depth, s, depth_range, self.curve_calss, float(self.prob_thresh), self.ndepths,
+                                      bool(upsample))

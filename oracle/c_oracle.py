@@ -226,3 +226,31 @@ def host_threads() -> int:
         return len(os.sched_getaffinity(0))
     except AttributeError:
         return os.cpu_count() or 1
+
+
+_FIT_MODES = {"gauss1": 1, "laplace": 2}
+
+
+def hypos_fit(prob_volume, depth_hypos, depth, curve, prec="f32"):
+    """Per-pixel curve fit of HyposByFit (depthhypos.py:78-125 'laplace', :169-215 'gauss1') -> s (B,H,W)."""
+    p = _arr(prob_volume, prec)
+    B, D, H, W = p.shape
+    h, pp = _hypos(depth_hypos, prec, B, D, H, W)
+    d = _arr(depth, prec)
+    out = np.empty((B, H, W), _dt(prec))
+    fn = getattr(_lib(prec), f"mdf_oracle_hypos_fit_{prec}")
+    _check(fn(_ptr(p), _ptr(h), pp, _ptr(d), _FIT_MODES[curve], B, D, H, W, _ptr(out)), "hypos_fit")
+    return out
+
+
+def hypos_generate(depth, s, depth_range, curve, prob_thresh, ndepths, upsample=True, prec="f32"):
+    """Next-stage hypotheses from the fitted scale (depthhypos.py:48-76) -> (B, ndepths, 2H|H, 2W|W)."""
+    d, sv = _arr(depth, prec), _arr(s, prec)
+    B, H, W = d.shape
+    dr = _arr(depth_range, prec).reshape(B, 2)
+    out = np.empty((B, ndepths, H * (2 if upsample else 1), W * (2 if upsample else 1)), _dt(prec))
+    fn = getattr(_lib(prec), f"mdf_oracle_hypos_generate_{prec}")
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, _real(prec)] + [ctypes.c_int] * 5 + [ctypes.c_void_p]
+    _check(fn(_ptr(d), _ptr(sv), _ptr(dr), _FIT_MODES[curve], float(prob_thresh), int(bool(upsample)), B, H, W, int(ndepths),
+              _ptr(out)), "hypos_generate")
+    return out

@@ -431,3 +431,110 @@ int SYM(mdf_oracle_confidence)(const REAL *prob, int B, int D, int H, int W,
             }
     return status;
 }
+
+/* ------------------------------------------------------------------------- */
+/* Depth hypotheses of the next stage: HyposByFit (net/unit/depthhypos.py).    */
+/*   stage 0     : uniform hypotheses                       depthhypos.py:31-38 */
+/*   fit         : per-pixel curve fit of the probability column               */
+/*                 "gauss1"  depthhypos.py:169-215  s = |-1/b0|, ln p ~ b0 x^2 + b1 x + b2 */
+/*                 "laplace" depthhypos.py:78-125   s = 1/|sum(x y)/sum(x x)|, x = |hypo - depth| */
+/*   generate    : bilinear x2 upsampling of s and depth (F.interpolate, align_corners=False), */
+/*                 search range from s and prob_thresh, clamps, D' hypotheses   depthhypos.py:48-76 */
+/* The gauss1 normal equations (entries up to 935^4 * 48) are hopeless in float32: the reference's */
+/* own float32 result is ~2e-4 (median) / 3e-2 (max) away from a float64 evaluation.  The restatement */
+/* therefore solves them in long double after centring x (the quadratic coefficient is invariant */
+/* under shifts), for both REAL types: it is the yardstick, not a rounding-for-rounding copy. */
+/* ------------------------------------------------------------------------- */
+int SYM(mdf_oracle_hypos_fit)(const REAL *prob, const REAL *hypos, int per_pixel, const REAL *depth,
+                              int mode /* 1 = gauss1, 2 = laplace */, int B, int D, int H, int W, REAL *s_out)
+{
+    const size_t HW = (size_t)H * W;
+    if (mode != 1 && mode != 2) return MDF_EINVAL;
+    for (int b = 0; b < B; ++b)
+#pragma omp parallel for schedule(static)
+        for (size_t p = 0; p < HW; ++p) {
+            if (mode == 2) {
+                REAL sxy = 0, sxx = 0;
+                for (int d = 0; d < D; ++d) {
+                    REAL pr = prob[((size_t)b * D + d) * HW + p];
+                    if (pr < (REAL)1e-40) pr = (REAL)1e-40;
+                    REAL h = per_pixel ? hypos[((size_t)b * D + d) * HW + p] : hypos[(size_t)b * D + d];
+                    REAL x = (REAL)fabs((double)(h - depth[(size_t)b * HW + p]));
+                    REAL y = (REAL)log((double)pr);
+                    sxy = sxy + x * y; sxx = sxx + x * x;
+                }
+                REAL bb = (REAL)fabs((double)(sxy / sxx));
+                s_out[(size_t)b * HW + p] = 1 / bb;
+            } else {
+                long double mean = 0;
+                for (int d = 0; d < D; ++d) mean += per_pixel ? hypos[((size_t)b * D + d) * HW + p] : hypos[(size_t)b * D + d];
+                mean /= D;
+                long double m[5] = {0, 0, 0, 0, 0}, r[3] = {0, 0, 0};    /* sum u^k, sum u^k z */
+                for (int d = 0; d < D; ++d) {
+                    REAL pr = prob[((size_t)b * D + d) * HW + p];
+                    if (pr < (REAL)1e-40) pr = (REAL)1e-40;
+                    long double z = logl((long double)pr);
+                    long double u = (long double)(per_pixel ? hypos[((size_t)b * D + d) * HW + p] : hypos[(size_t)b * D + d]) - mean;
+                    long double uk = 1;
+                    for (int k = 0; k < 5; ++k) { m[k] += uk; if (k < 3) r[k] += uk * z; uk *= u; }
+                }
+                /* normal equations for [c2, c1, c0]: [[m4 m3 m2][m3 m2 m1][m2 m1 m0]] c = [r2 r1 r0]; Cramer for c2 */
+                long double a11 = m[4], a12 = m[3], a13 = m[2], a22 = m[2], a23 = m[1], a33 = m[0];
+                long double det = a11 * (a22 * a33 - a23 * a23) - a12 * (a12 * a33 - a23 * a13) + a13 * (a12 * a23 - a22 * a13);
+                long double d2 = r[2] * (a22 * a33 - a23 * a23) - a12 * (r[1] * a33 - a23 * r[0]) + a13 * (r[1] * a23 - a22 * r[0]);
+                long double c2 = d2 / det;
+                s_out[(size_t)b * HW + p] = (REAL)fabsl(-1.0L / c2);
+            }
+        }
+    return MDF_OK;
+}
+
+/* F.interpolate(scale_factor=2, mode='bilinear', align_corners=False) of one (H,W) map at fine pixel (Y,X) */
+static inline REAL up2(const REAL *m, int H, int W, int Y, int X)
+{
+    REAL sy = ((REAL)Y + (REAL)0.5) * (REAL)0.5 - (REAL)0.5, sx = ((REAL)X + (REAL)0.5) * (REAL)0.5 - (REAL)0.5;
+    if (sy < 0) sy = 0;
+    if (sx < 0) sx = 0;
+    int y0 = (int)sy, x0 = (int)sx;
+    int y1 = y0 + (y0 < H - 1), x1 = x0 + (x0 < W - 1);
+    REAL ly = sy - (REAL)y0, lx = sx - (REAL)x0, hy = 1 - ly, hx = 1 - lx;
+    return hy * (hx * m[(size_t)y0 * W + x0] + lx * m[(size_t)y0 * W + x1]) + ly * (hx * m[(size_t)y1 * W + x0] + lx * m[(size_t)y1 * W + x1]);
+}
+
+/* depth (B,H,W), s (B,H,W), depth_range (B,2) -> hypotheses (B, ND, 2H, 2W) (upsample != 0) or (B, ND, H, W) */
+int SYM(mdf_oracle_hypos_generate)(const REAL *depth, const REAL *s, const REAL *depth_range, int mode, REAL prob_thresh,
+                                   int upsample, int B, int H, int W, int ND, REAL *out)
+{
+    if (mode != 1 && mode != 2) return MDF_EINVAL;
+    const int Ho = upsample ? 2 * H : H, Wo = upsample ? 2 * W : W;
+    REAL gmax = depth_range[1], gmin = depth_range[0];
+    for (int b = 1; b < B; ++b) {
+        if (depth_range[2 * b + 1] > gmax) gmax = depth_range[2 * b + 1];
+        if (depth_range[2 * b] < gmin) gmin = depth_range[2 * b];
+    }
+    const REAL cap_all = (gmax - gmin) / 2;
+    const REAL lt = (REAL)log((double)prob_thresh);
+    for (int b = 0; b < B; ++b) {
+        const REAL dmin = depth_range[2 * b], dmax = depth_range[2 * b + 1];
+        const REAL cap_b = (dmax - dmin) * (REAL)0.2;
+#pragma omp parallel for schedule(static)
+        for (int Y = 0; Y < Ho; ++Y)
+            for (int X = 0; X < Wo; ++X) {
+                REAL sv = upsample ? up2(s + (size_t)b * H * W, H, W, Y, X) : s[((size_t)b * H + Y) * W + X];
+                REAL dv = upsample ? up2(depth + (size_t)b * H * W, H, W, Y, X) : depth[((size_t)b * H + Y) * W + X];
+                REAL res = mode == 1 ? R_SQRT(-1 * sv * lt) : (REAL)fabs((double)(sv * lt));
+                if (res < (REAL)1e-6) res = (REAL)1e-6;          /* clamp(min, max): NaN propagates like torch */
+                if (res > cap_all) res = cap_all;
+                if (res > cap_b) res = cap_b;
+                const REAL interval = res / (REAL)(ND - 1);
+                const REAL base = dv - (REAL)0.5 * res;
+                for (int d = 0; d < ND; ++d) {
+                    REAL h = base + interval * (REAL)d;
+                    REAL delta = h - dmin; if (delta < 0) delta = 0; h = dmin + delta;
+                    delta = h - dmax; if (delta > 0) delta = 0; h = dmax + delta;
+                    out[(((size_t)b * ND + d) * Ho + Y) * Wo + X] = h;
+                }
+            }
+    }
+    return MDF_OK;
+}

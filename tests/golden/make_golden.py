@@ -183,6 +183,38 @@ def gen_head():
          uniform=unif, uniform_conf=regress.confidence_regress(T(unif)).numpy())
 
 
+# ------------------------------------------------------------------------------ HyposByFit
+def gen_hypos():
+    """HyposByFit (net/unit/depthhypos.py) as config.py:199-203 wires it: stage 0 uniform, stage 0 -> 1 'gauss1'
+    (prob_thresh 0.95), stage 1 -> 2 'laplace' (prob_thresh 1e-5), both with the x2 upsampling core.py:55 asks for.
+    The float64 run of the same reference code is stored next to the float32 one: the gauss1 normal equations
+    are so ill conditioned in float32 that the reference's own result is only good to ~1e-3."""
+    from net.unit.depthhypos import HyposByFit
+    B, H, W = 2, 12, 16
+    dr = np.array([[425.0, 935.0], [480.0, 900.0]], np.float32)
+    out = {"depth_range": dr}
+    m0 = HyposByFit(48, None, 0.0)
+    hyp0 = m0(None, T(dr), None, None, upsample=True)
+    out["hypos0"] = hyp0.numpy()
+    prob0 = F.softmax(T(syn.regulariser_logits(B, 48, H, W, seed=81, peak=6.0)), 1)
+    depth0 = regress.depth_regression(prob0, hyp0)
+    m1 = HyposByFit(24, "gauss1", 0.95)
+    hyp1 = m1(depth0, T(dr), prob0, hyp0, upsample=True)
+    hyp1_64 = m1(depth0.double(), T(dr).double(), prob0.double(), hyp0.double(), upsample=True)
+    out.update(prob0=prob0.numpy(), depth0=depth0.numpy(), hypos1=hyp1.numpy(), hypos1_f64=hyp1_64.numpy(),
+               s1=m1._gauss_fitting1(depth0, prob0, hyp0).numpy(),
+               s1_f64=m1._gauss_fitting1(depth0.double(), prob0.double(), hyp0.double()).numpy())
+    prob1 = F.softmax(T(syn.regulariser_logits(B, 24, 2 * H, 2 * W, seed=82, peak=6.0)), 1)
+    depth1 = regress.depth_regression(prob1, hyp1)
+    m2 = HyposByFit(8, "laplace", 1e-5)
+    hyp2 = m2(depth1, T(dr), prob1, hyp1, upsample=True)
+    hyp2_64 = m2(depth1.double(), T(dr).double(), prob1.double(), hyp1.double(), upsample=True)
+    out.update(prob1=prob1.numpy(), depth1=depth1.numpy(), hypos2=hyp2.numpy(), hypos2_f64=hyp2_64.numpy(),
+               s2=m2._laplace_fitting(depth1, prob1, hyp1).numpy(),
+               s2_f64=m2._laplace_fitting(depth1.double(), prob1.double(), hyp1.double()).numpy())
+    save("hypos_fit", **out)
+
+
 # -------------------------------------------------------------------------------- scale_cam
 def gen_scale():
     K, E = syn.camera_rig(2, 4, 64, 80, seed=51)
@@ -276,6 +308,6 @@ def gen_corenet():
 
 if __name__ == "__main__":
     only = sys.argv[1:]
-    for fn in (gen_warp, gen_vecagg, gen_vecagg_grad, gen_varagg, gen_head, gen_scale, gen_corenet):
+    for fn in (gen_warp, gen_vecagg, gen_vecagg_grad, gen_varagg, gen_head, gen_hypos, gen_scale, gen_corenet):
         if not only or fn.__name__ in only:
             fn()
