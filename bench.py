@@ -201,7 +201,7 @@ def cpu_baseline(view, budget_s: float, batch: int):
                       f"C oracle oracle/mdf_oracle.c with OpenMP"}
 
 
-def run_reference(args, workload):
+def run_reference(args, workload, out):
     """--impl reference: the reference algorithm on the host cores (CPU oracle port; the reference itself is
     PyTorch-CPU Python that cannot travel to the GPU box).  Rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
@@ -220,7 +220,7 @@ def run_reference(args, workload):
     t = sum(times) / len(times)
     value = batch * frac / t
     sample = f"each step = first {frac:.3f} of the rows of all 3 stages of one view, {t:.2f} s/step"
-    print(json.dumps({
+    out.emit(json.dumps({
         "impl": "reference", "metric": "DTU views/s (plane-sweep cost-volume path)", "value": value, "unit": "views/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / frac,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -231,7 +231,7 @@ def run_reference(args, workload):
 
 
 # ----------------------------------------------------------------------------------------- GPU arm
-def run_b200(args, workload):
+def run_b200(args, workload, out):
     import torch
     import torch.distributed as dist
 
@@ -465,9 +465,29 @@ def run_b200(args, workload):
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(host_views[0], args.cpu_budget, batch)
-        print(json.dumps(line))
+        out.emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+class quiet_stdout:
+    """Everything libraries print to stdout while the benchmark runs (NCCL's version banner, ...) goes to stderr:
+    stdout carries exactly one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, line: str):
+        sys.stdout.flush()
+        os.write(self.saved, (line + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
 
 
 def main():
@@ -482,10 +502,11 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args, args.workload)
-    else:
-        run_b200(args, args.workload)
+    with quiet_stdout() as out:
+        if args.impl == "reference":
+            run_reference(args, args.workload, out)
+        else:
+            run_b200(args, args.workload, out)
 
 
 if __name__ == "__main__":
