@@ -675,18 +675,18 @@ static int launch_staged(const StagedArgs& args, const StagedBuffers& buf, cudaS
 
 // Tuning variants per G (algo = 16 + k selects variant k; variant 0 is the default).
 //                         G  PT TH PG  BW  BH MINB CQS   EARLY
-using CfgG32_0 = StagedCfg<32, 1, 4, 2, 40, 7, 2, true>;     // 256 thr x 2 CTAs; 2 x 35 KiB boxes + 2 x 16 KiB tiles
-using CfgG32_1 = StagedCfg<32, 1, 4, 2, 40, 7, 2, true, false>;
-using CfgG32_2 = StagedCfg<32, 1, 2, 4, 40, 6, 2, true>;     // tile 32x2, slab 4 planes
-using CfgG32_3 = StagedCfg<32, 1, 2, 4, 40, 6, 2, true, false>;
-using CfgG16_0 = StagedCfg<16, 2, 4, 2, 64, 8, 2, false>;    // 256 thr x 2 CTAs, 2 x 32 KiB boxes, slab 4 planes
-using CfgG16_1 = StagedCfg<16, 2, 4, 2, 64, 8, 2, false, false>;
+using CfgG32_0 = StagedCfg<32, 1, 2, 4, 40, 6, 2, true>;     // 256 thr x 2 CTAs; tile 32x2, slab 4 planes; 2 x 30 KiB boxes + 2 x 8 KiB tiles
+using CfgG32_1 = StagedCfg<32, 1, 4, 2, 40, 7, 2, true>;     // tile 32x4, slab 2 planes
+using CfgG32_2 = StagedCfg<32, 1, 4, 2, 40, 7, 2, true, false>;
+using CfgG32_3 = StagedCfg<32, 1, 1, 8, 48, 4, 2, true>;     // tile 32x1, slab 8 planes
+using CfgG16_0 = StagedCfg<16, 2, 2, 4, 64, 6, 2, false>;    // 256 thr x 2 CTAs; tile 32x2, slab 8 planes; 2 x 24 KiB boxes
+using CfgG16_1 = StagedCfg<16, 2, 4, 2, 64, 8, 2, false>;    // tile 32x4, slab 4 planes
 using CfgG16_2 = StagedCfg<16, 2, 4, 2, 48, 8, 2, false>;    // narrower box
-using CfgG16_3 = StagedCfg<16, 1, 4, 2, 48, 8, 3, false>;    // 3 CTAs (85 registers), slab 2 planes
-using CfgG8_0  = StagedCfg<8, 4, 4, 2, 64, 10, 2, false>;    // 256 thr x 2 CTAs, 2 x 20 KiB boxes, slab 8 planes
-using CfgG8_1  = StagedCfg<8, 4, 4, 2, 64, 10, 2, false, false>;
+using CfgG16_3 = StagedCfg<16, 2, 1, 8, 80, 4, 2, false>;    // tile 32x1, slab 16 planes
+using CfgG8_0  = StagedCfg<8, 4, 4, 2, 64, 10, 2, false>;    // 256 thr x 2 CTAs; tile 32x4, slab 8 planes; 2 x 20 KiB boxes
+using CfgG8_1  = StagedCfg<8, 4, 8, 1, 64, 14, 2, false>;    // tile 32x8, slab 4 planes
 using CfgG8_2  = StagedCfg<8, 2, 4, 2, 64, 10, 3, false>;    // 3 CTAs, slab 4 planes
-using CfgG8_3  = StagedCfg<8, 4, 4, 2, 48, 8, 2, false>;     // smaller box
+using CfgG8_3  = StagedCfg<8, 2, 2, 4, 64, 6, 3, false>;     // tile 32x2, slab 8 planes, 3 CTAs
 
 static int launch_staged_variant(int G, int variant, const StagedArgs& a, const StagedBuffers& S, cudaStream_t stream)
 {
