@@ -154,6 +154,33 @@ MDF_API int mdf_softmax_regress_fwd(const float *logits,        /* (B,D,H,W) */
                             int conf_n, int conf_pad_front, int conf_pad_back, int conf_upsample,
                             mdf_stream_t stream);
 
+/* The same pass with HyposByFit's per-pixel curve fit (net/unit/depthhypos.py:78-125, :169-215; core.py:55 hands the
+ * probability volume and the regressed depth of this stage to the next stage's Depth_hypos) done on the column while
+ * it is on chip: `s` (B,H,W) receives the fitted scale that mdf_hypos_generate_fwd consumes, so the probability
+ * volume is never re-read and need not be written (prob == NULL) unless the caller wants it.  curve: 0 = no fit
+ * (s must be NULL; identical to mdf_softmax_regress_fwd), 1 = "gauss1", 2 = "laplace".  The fit uses the depth this
+ * call regresses. */
+MDF_API int mdf_softmax_regress_fit_fwd(const float *logits, const float *depth_hypos, int hypos_per_pixel,
+                                int B, int D, int H, int W, float *prob, float *depth, float *confidence,
+                                int conf_n, int conf_pad_front, int conf_pad_back, int conf_upsample,
+                                int curve, float *s, mdf_stream_t stream);
+
+/* The regulariser's last layer folded in as well: x (B,C,D,H,W) is the feature volume that
+ * net/unit/regular.py:67 / :130 feeds to `self.prob = nn.Conv3d(c0, 1, 3, stride=1, padding=1, bias=False)`
+ * (regular.py:43,110), prob_weight its (1,C,3,3,3) weight.  One launch: convolution -> softmax over D -> depth
+ * expectation (-> confidence) (-> curve fit); the logits only exist in registers unless `logits` (B,D,H,W) is
+ * given.  Any of logits / prob / depth / confidence may be NULL; s is required iff curve != 0.  D must be 8, 24 or 48
+ * (config.py:199), C <= 64. */
+MDF_API int mdf_prob_head_fwd(const float *x, const float *prob_weight, const float *depth_hypos, int hypos_per_pixel,
+                              int B, int C, int D, int H, int W, float *logits, float *prob, float *depth,
+                              float *confidence, int conf_n, int conf_pad_front, int conf_pad_back, int conf_upsample,
+                              int curve, float *s, mdf_stream_t stream);
+/* algo: 0 = default, 1.. = alternative tile / depth-slab shapes of the same kernel (tools/time_prob_head.py). */
+MDF_API int mdf_prob_head_fwd_ex(const float *x, const float *prob_weight, const float *depth_hypos, int hypos_per_pixel,
+                                 int B, int C, int D, int H, int W, float *logits, float *prob, float *depth,
+                                 float *confidence, int conf_n, int conf_pad_front, int conf_pad_back, int conf_upsample,
+                                 int curve, float *s, int algo, mdf_stream_t stream);
+
 MDF_API int mdf_depth_regression_fwd(const float *prob, const float *depth_hypos, int hypos_per_pixel,
                              int B, int D, int H, int W, float *depth, mdf_stream_t stream);
 

@@ -36,6 +36,9 @@ SIGNATURES = {
     "mdf_variance_volume_workspace_bytes": (c_size_t, [_I] * 6),
     "mdf_variance_volume_fwd": (_I, [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, c_size_t, _P]),
     "mdf_softmax_regress_fwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "mdf_softmax_regress_fit_fwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "mdf_prob_head_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "mdf_prob_head_fwd_ex": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _I, _P]),
     "mdf_depth_regression_fwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "mdf_confidence_fwd": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "mdf_cost_volume_train_workspace_bytes": (c_size_t, [_I] * 7),

@@ -24,6 +24,7 @@
 
 #include "mdf_common.cuh"
 #include "mdf_host.cuh"
+#include "mdf_tail.cuh"
 
 namespace mdf {
 
@@ -33,45 +34,15 @@ struct HeadArgs {
     float* prob;           // (B,D,H,W) or nullptr
     float* depth;          // (B,H,W)   or nullptr
     float* conf;           // (B,H*up,W*up) or nullptr
+    float* s;              // (B,H,W) fitted scale of the column (HyposByFit) or nullptr
     int per_pixel, B, D, H, W;
     int conf_n, pad_front, pad_back, up;
 };
 
-// confidence of one pixel from its probability column (regress.py:13-18):
-//   S[k] = n * avg_pool(pad_D(prob))[k] = n * ((sum_{j<n} prob[k - pad_front + j]) / n)
-template <class ProbAt>
-__device__ __forceinline__ float window_confidence(ProbAt prob_at, float expect_idx, int D, int n, int pad_front, int pad_back)
-{
-    const int Dp = D + pad_front + pad_back - n + 1;
-    int k = (int)expect_idx;                       // .long() truncates toward zero
-    k = max(0, min(k, Dp - 1));                    // torch.gather would raise; cannot happen for a softmax output
-    float s = 0.0f;
-    for (int j = 0; j < n; ++j) {
-        const int d = k - pad_front + j;
-        s = __fadd_rn(s, (d >= 0 && d < D) ? prob_at(d) : 0.0f);
-    }
-    const float fn = (float)n;
-    return __fmul_rn(fn, __fdiv_rn(s, fn));
-}
-
-__device__ __forceinline__ void store_upsampled(float* __restrict__ conf, float c, int b, int y, int x, int H, int W, int up)
-{
-    const size_t Wu = (size_t)W * up;
-    float* base = conf + ((size_t)b * H * up + (size_t)y * up) * Wu + (size_t)x * up;
-    if (up == 2 && (reinterpret_cast<uintptr_t>(base) & 7) == 0) {
-        const float2 v = make_float2(c, c);
-        *reinterpret_cast<float2*>(base) = v;           // x*2 floats: 8-byte aligned
-        *reinterpret_cast<float2*>(base + Wu) = v;
-    } else {
-        for (int uy = 0; uy < up; ++uy)
-            for (int ux = 0; ux < up; ++ux) base[(size_t)uy * Wu + ux] = c;
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // fused softmax + expectation (+ confidence).  DS = depth slices per warp (1, 2 or 4).
 // ------------------------------------------------------------------------------------------------
-template <int DS>
+template <int DS, int FIT>
 __global__ void __launch_bounds__(256)
 softmax_regress_kernel(const HeadArgs a)
 {
@@ -121,6 +92,31 @@ softmax_regress_kernel(const HeadArgs a)
         acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, o));
         eidx = __fadd_rn(eidx, __shfl_xor_sync(0xffffffffu, eidx, o));
     }
+    if (FIT != 0) {
+        // sweep 4 (the column is in L1): the curve fit of HyposByFit against the depth just regressed
+        const float* __restrict__ hcol = a.per_pixel ? a.hypos + (size_t)b * D * HW + p : a.hypos + (size_t)b * D;
+        const size_t hstride = a.per_pixel ? HW : 1;
+        auto prob_of = [&](int d) { return __fdiv_rn(expf(__fsub_rn(__ldg(col + (size_t)d * HW), m)), sum); };
+        float sv;
+        if (FIT == 2) {
+            LaplaceSums ls;
+            if (ok)
+                for (int d = d_lo; d < d_hi; ++d) ls.add(__ldg(hcol + (size_t)d * hstride), acc, prob_of(d));
+            ls.reduce_slices<PW>();
+            sv = ls.scale();
+        } else {
+            double hs = 0.0;
+            if (ok)
+                for (int d = d_lo; d < d_hi; ++d) hs += (double)__ldg(hcol + (size_t)d * hstride);
+            const double mean = reduce_slices_f64<PW>(hs) / (double)D;
+            GaussMoments gm;
+            if (ok)
+                for (int d = d_lo; d < d_hi; ++d) gm.add((double)__ldg(hcol + (size_t)d * hstride) - mean, prob_of(d));
+            gm.reduce_slices<PW>();
+            sv = gm.scale(D);
+        }
+        if (ok && slice == 0) a.s[pix] = sv;
+    }
     if (!ok || slice != 0) return;
     if (a.depth) a.depth[pix] = acc;
     if (a.conf) {
@@ -139,7 +135,7 @@ softmax_regress_kernel(const HeadArgs a)
 // used whenever the confidence -- a discrete decision on trunc(sum p*d) -- is produced; DS = 4 gives the deep,
 // small stages (D = 48 / 24: 29 K / 115 K pixels) four times the threads.
 // ------------------------------------------------------------------------------------------------
-template <int D, int DS>
+template <int D, int DS, int FIT>
 __global__ void __launch_bounds__(128)
 softmax_regress_reg_kernel(const HeadArgs a)
 {
@@ -189,6 +185,32 @@ softmax_regress_reg_kernel(const HeadArgs a)
         acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, o));
         eidx = __fadd_rn(eidx, __shfl_xor_sync(0xffffffffu, eidx, o));
     }
+    if (FIT != 0) {
+        // the curve fit of HyposByFit on the register-resident column, against the depth just regressed
+        float sv;
+        if (FIT == 2) {
+            LaplaceSums ls;
+            if (ok) {
+#pragma unroll
+                for (int d = 0; d < DQ; ++d) ls.add(hv[d], acc, e[d]);
+            }
+            ls.reduce_slices<PW>();
+            sv = ls.scale();
+        } else {
+            double hs = 0.0;
+#pragma unroll
+            for (int d = 0; d < DQ; ++d) hs += (double)hv[d];
+            const double mean = reduce_slices_f64<PW>(hs) / (double)D;
+            GaussMoments gm;
+            if (ok) {
+#pragma unroll
+                for (int d = 0; d < DQ; ++d) gm.add((double)hv[d] - mean, e[d]);
+            }
+            gm.reduce_slices<PW>();
+            sv = gm.scale(D);
+        }
+        if (ok && slice == 0) a.s[pix] = sv;
+    }
     if (!ok || slice != 0) return;
     if (a.depth) a.depth[pix] = acc;
     if (DS == 1 && a.conf) {
@@ -206,11 +228,13 @@ softmax_regress_reg_kernel(const HeadArgs a)
 }
 
 template <int D, int DS>
-static int launch_reg(const HeadArgs& a, size_t npix, cudaStream_t stream)
+static int launch_reg(const HeadArgs& a, int fit, size_t npix, cudaStream_t stream)
 {
     const size_t blocks = (npix * DS + 127) / 128;
     if (blocks > 0x7fffffffu) return MDF_ERR_UNSUPPORTED;
-    softmax_regress_reg_kernel<D, DS><<<(unsigned)blocks, 128, 0, stream>>>(a);
+    if (fit == 1) softmax_regress_reg_kernel<D, DS, 1><<<(unsigned)blocks, 128, 0, stream>>>(a);
+    else if (fit == 2) softmax_regress_reg_kernel<D, DS, 2><<<(unsigned)blocks, 128, 0, stream>>>(a);
+    else softmax_regress_reg_kernel<D, DS, 0><<<(unsigned)blocks, 128, 0, stream>>>(a);
     return launch_status();
 }
 
@@ -259,12 +283,13 @@ static int check_head(const HeadArgs& a, bool need_hypos)
 
 static int head_device(const HeadArgs& a)
 {
-    const void* out = a.depth ? (const void*)a.depth : a.conf ? (const void*)a.conf : (const void*)a.prob;
+    const void* out = a.depth ? (const void*)a.depth : a.conf ? (const void*)a.conf : a.prob ? (const void*)a.prob : (const void*)a.s;
     const int dev = device_of(out);
     if (dev < 0) return dev;
-    const void* ptrs[5];
+    const void* ptrs[6];
     int n = 0;
     ptrs[n++] = a.logits;
+    if (a.s) ptrs[n++] = a.s;
     if (a.hypos) ptrs[n++] = a.hypos;
     if (a.prob) ptrs[n++] = a.prob;
     if (a.depth) ptrs[n++] = a.depth;
@@ -279,16 +304,19 @@ using namespace mdf;
 
 extern "C" {
 
-int mdf_softmax_regress_fwd(const float* logits, const float* depth_hypos, int hypos_per_pixel, int B, int D, int H,
-                            int W, float* prob, float* depth, float* confidence, int conf_n, int conf_pad_front,
-                            int conf_pad_back, int conf_upsample, mdf_stream_t stream_)
+int mdf_softmax_regress_fit_fwd(const float* logits, const float* depth_hypos, int hypos_per_pixel, int B, int D, int H,
+                                int W, float* prob, float* depth, float* confidence, int conf_n, int conf_pad_front,
+                                int conf_pad_back, int conf_upsample, int curve, float* s, mdf_stream_t stream_)
 {
     HeadArgs a;
-    a.logits = logits; a.hypos = depth_hypos; a.prob = prob; a.depth = depth; a.conf = confidence;
+    a.logits = logits; a.hypos = depth_hypos; a.prob = prob; a.depth = depth; a.conf = confidence; a.s = s;
     a.per_pixel = hypos_per_pixel; a.B = B; a.D = D; a.H = H; a.W = W;
     a.conf_n = conf_n; a.pad_front = conf_pad_front; a.pad_back = conf_pad_back; a.up = conf_upsample;
-    if (!prob && !depth && !confidence) return MDF_ERR_NULL_POINTER;
-    int st = check_head(a, depth != nullptr);
+    if (curve < 0 || curve > 2) return MDF_ERR_UNSUPPORTED;
+    if (B >= 0 && D >= 0 && H >= 0 && W >= 0 && (size_t)B * H * W == 0) return MDF_OK;     // empty: torch hands out NULL pointers
+    if (!prob && !depth && !confidence && !s) return MDF_ERR_NULL_POINTER;
+    if ((curve != 0) != (s != nullptr)) return MDF_ERR_NULL_POINTER;      // s is produced iff a curve is named
+    int st = check_head(a, depth != nullptr || curve != 0);
     if (st != MDF_OK) return st;
     const size_t npix = (size_t)B * H * W;
     if (npix == 0) return MDF_OK;
@@ -298,22 +326,38 @@ int mdf_softmax_regress_fwd(const float* logits, const float* depth_hypos, int h
     cudaStream_t stream = (cudaStream_t)stream_;
     if (D == 8 || D == 24 || D == 48) {
         if (confidence) {                                    // sequential order for the discrete index
-            if (D == 8) return launch_reg<8, 1>(a, npix, stream);
-            if (D == 24) return launch_reg<24, 1>(a, npix, stream);
-            return launch_reg<48, 1>(a, npix, stream);
+            if (D == 8) return launch_reg<8, 1>(a, curve, npix, stream);
+            if (D == 24) return launch_reg<24, 1>(a, curve, npix, stream);
+            return launch_reg<48, 1>(a, curve, npix, stream);
         }
-        if (D == 8) return launch_reg<8, 1>(a, npix, stream);
-        if (D == 24) return launch_reg<24, 4>(a, npix, stream);
-        return launch_reg<48, 4>(a, npix, stream);
+        if (D == 8) return launch_reg<8, 1>(a, curve, npix, stream);
+        if (D == 24) return launch_reg<24, 4>(a, curve, npix, stream);
+        return launch_reg<48, 4>(a, curve, npix, stream);
     }
     // other depths: depth slices per warp; sequential order whenever the discrete confidence index is produced
     const int ds = (confidence || D < 16) ? 1 : 4;
     const size_t threads = npix * ds;
     const size_t blocks = (threads + 255) / 256;
     if (blocks > 0x7fffffffu) return MDF_ERR_UNSUPPORTED;
-    if (ds == 1) softmax_regress_kernel<1><<<(unsigned)blocks, 256, 0, stream>>>(a);
-    else softmax_regress_kernel<4><<<(unsigned)blocks, 256, 0, stream>>>(a);
+    const unsigned nb = (unsigned)blocks;
+    if (ds == 1) {
+        if (curve == 1) softmax_regress_kernel<1, 1><<<nb, 256, 0, stream>>>(a);
+        else if (curve == 2) softmax_regress_kernel<1, 2><<<nb, 256, 0, stream>>>(a);
+        else softmax_regress_kernel<1, 0><<<nb, 256, 0, stream>>>(a);
+    } else {
+        if (curve == 1) softmax_regress_kernel<4, 1><<<nb, 256, 0, stream>>>(a);
+        else if (curve == 2) softmax_regress_kernel<4, 2><<<nb, 256, 0, stream>>>(a);
+        else softmax_regress_kernel<4, 0><<<nb, 256, 0, stream>>>(a);
+    }
     return launch_status();
+}
+
+int mdf_softmax_regress_fwd(const float* logits, const float* depth_hypos, int hypos_per_pixel, int B, int D, int H,
+                            int W, float* prob, float* depth, float* confidence, int conf_n, int conf_pad_front,
+                            int conf_pad_back, int conf_upsample, mdf_stream_t stream)
+{
+    return mdf_softmax_regress_fit_fwd(logits, depth_hypos, hypos_per_pixel, B, D, H, W, prob, depth, confidence, conf_n,
+                                       conf_pad_front, conf_pad_back, conf_upsample, 0, nullptr, stream);
 }
 
 static int run_regress(HeadArgs& a, mdf_stream_t stream_)
@@ -336,7 +380,7 @@ int mdf_depth_regression_fwd(const float* prob, const float* depth_hypos, int hy
 {
     if (!depth) return MDF_ERR_NULL_POINTER;
     HeadArgs a;
-    a.logits = prob; a.hypos = depth_hypos; a.prob = nullptr; a.depth = depth; a.conf = nullptr;
+    a.logits = prob; a.hypos = depth_hypos; a.prob = nullptr; a.depth = depth; a.conf = nullptr; a.s = nullptr;
     a.per_pixel = hypos_per_pixel; a.B = B; a.D = D; a.H = H; a.W = W;
     a.conf_n = 0; a.pad_front = 0; a.pad_back = 0; a.up = 1;
     return run_regress(a, stream);
@@ -347,7 +391,7 @@ int mdf_confidence_fwd(const float* prob, int B, int D, int H, int W, int n, int
 {
     if (!confidence) return MDF_ERR_NULL_POINTER;
     HeadArgs a;
-    a.logits = prob; a.hypos = nullptr; a.prob = nullptr; a.depth = nullptr; a.conf = confidence;
+    a.logits = prob; a.hypos = nullptr; a.prob = nullptr; a.depth = nullptr; a.conf = confidence; a.s = nullptr;
     a.per_pixel = 0; a.B = B; a.D = D; a.H = H; a.W = W;
     a.conf_n = n; a.pad_front = pad_front; a.pad_back = pad_back; a.up = upsample;
     return run_regress(a, stream);

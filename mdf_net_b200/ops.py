@@ -10,6 +10,8 @@ Reference call sites replaced (file:line into the reference checkout):
   homo_warp         net/unit/base.py:85-126           homo_warping
   variance_volume   net/unit/homoaggregate.py:49-69   homo_aggregate_by_variance
   softmax_regress   net/unit/regular.py:67-69,130-133 + net/unit/regress.py:5-25
+  prob_head         net/unit/regular.py:43,67-69 / :110,130-133 (prob conv + softmax) + regress + curve fit, one launch
+  softmax_regress_fit  the same + net/unit/depthhypos.py:78-125,169-215 (the curve fit of the next stage's HyposByFit)
   depth_regression  net/unit/regress.py:5-7
   confidence        net/unit/regress.py:9-25 (+ core.py:75-77 nearest upsample)
 """
@@ -22,7 +24,8 @@ from torch import Tensor
 
 from . import _cabi
 
-__all__ = ["cost_volume", "homo_warp", "variance_volume", "softmax_regress", "depth_regression", "confidence",
+__all__ = ["cost_volume", "homo_warp", "variance_volume", "softmax_regress", "softmax_regress_fit", "prob_head", "depth_regression",
+           "confidence", "hypos_fit", "hypos_generate",
            "launch_count", "reset_launch_count"]
 
 # kernels launched through this module since the last reset (bench.py's `gpu_launches`)
@@ -180,6 +183,8 @@ def _(features, ref_proj, src_projs, depth_hypos):
 
 
 # ------------------------------------------------------------------------------------------- head
+_CURVES = {"gauss1": 1, "laplace": 2}      # depthhypos.py:44-47 (config.py:200 wires None, "gauss1", "laplace")
+
 def _prob(t: Tensor, what: str) -> Tensor:
     t = _f32c(t, what)
     if t.dim() != 4:
@@ -221,6 +226,84 @@ def _(logits, depth_hypos, want_prob=True, want_confidence=False, n=4, pad_front
     B, D, H, W = logits.shape
     return (torch.empty_like(logits) if want_prob else logits.new_empty(0), logits.new_empty((B, H, W)),
             logits.new_empty((B, H * upsample, W * upsample)) if want_confidence else logits.new_empty(0))
+
+
+@torch.library.custom_op("mdfnet_b200::softmax_regress_fit", mutates_args=(), device_types="cuda")
+def softmax_regress_fit(logits: Tensor, depth_hypos: Tensor, curve: str, want_prob: bool = False,
+                        want_confidence: bool = False, n: int = 4, pad_front: int = 1, pad_back: int = 2,
+                        upsample: int = 2) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """softmax over D + depth expectation (+ confidence) + the per-pixel curve fit of HyposByFit, one pass over the
+    logits.  Returns (prob, depth, confidence, s); outputs that were not requested are empty tensors."""
+    if curve not in _CURVES:
+        raise RuntimeError(f"mdfnet_b200: curve must be one of {sorted(_CURVES)}, got {curve!r}")
+    x = _prob(logits, "logits")
+    B, D, H, W = x.shape
+    hyp, per_pixel = _head_hypos(depth_hypos, B, D, H, W)
+    dev = x.device
+    prob = torch.empty_like(x) if want_prob else torch.empty(0, device=dev)
+    depth = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+    s = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+    conf = torch.empty((B, H * upsample, W * upsample), dtype=torch.float32, device=dev) if want_confidence \
+        else torch.empty(0, device=dev)
+    st = _cabi.lib().mdf_softmax_regress_fit_fwd(
+        x.data_ptr(), hyp.data_ptr(), per_pixel, B, D, H, W,
+        prob.data_ptr() if want_prob else None, depth.data_ptr(), conf.data_ptr() if want_confidence else None,
+        n, pad_front, pad_back, upsample, _CURVES[curve], s.data_ptr(), _stream(x))
+    _cabi.check("mdf_softmax_regress_fit_fwd", st)
+    _count(_LAUNCHES_SIMPLE)
+    return prob, depth, conf, s
+
+
+@softmax_regress_fit.register_fake
+def _(logits, depth_hypos, curve, want_prob=False, want_confidence=False, n=4, pad_front=1, pad_back=2, upsample=2):
+    B, D, H, W = logits.shape
+    return (torch.empty_like(logits) if want_prob else logits.new_empty(0), logits.new_empty((B, H, W)),
+            logits.new_empty((B, H * upsample, W * upsample)) if want_confidence else logits.new_empty(0),
+            logits.new_empty((B, H, W)))
+
+
+@torch.library.custom_op("mdfnet_b200::prob_head", mutates_args=(), device_types="cuda")
+def prob_head(x: Tensor, prob_weight: Tensor, depth_hypos: Tensor, curve: str = "", want_logits: bool = False,
+              want_prob: bool = True, want_confidence: bool = False, n: int = 4, pad_front: int = 1, pad_back: int = 2,
+              upsample: int = 2, algo: int = 0) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """Conv3d(c0,1,3,pad=1,no bias) of the regulariser's last feature volume x (B,c0,D,H,W) + softmax over D + depth
+    expectation (+ confidence) (+ curve fit, curve in {"gauss1","laplace"}), one launch.  Returns
+    (logits, prob, depth, confidence, s); outputs that were not requested are empty tensors."""
+    if curve and curve not in _CURVES:
+        raise RuntimeError(f"mdfnet_b200: curve must be '' or one of {sorted(_CURVES)}, got {curve!r}")
+    v = _f32c(x, "x")
+    if v.dim() != 5:
+        raise RuntimeError(f"mdfnet_b200: x must be (B,C,D,H,W), got {tuple(v.shape)}")
+    B, C, D, H, W = v.shape
+    w = _f32c(prob_weight, "prob_weight")
+    if w.numel() != C * 27:
+        raise RuntimeError(f"mdfnet_b200: prob_weight must be (1,{C},3,3,3), got {tuple(w.shape)}")
+    hyp, per_pixel = _head_hypos(depth_hypos, B, D, H, W)
+    dev = v.device
+    empty = lambda: torch.empty(0, device=dev)
+    logits = torch.empty((B, D, H, W), dtype=torch.float32, device=dev) if want_logits else empty()
+    prob = torch.empty((B, D, H, W), dtype=torch.float32, device=dev) if want_prob else empty()
+    depth = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+    conf = torch.empty((B, H * upsample, W * upsample), dtype=torch.float32, device=dev) if want_confidence else empty()
+    s = torch.empty((B, H, W), dtype=torch.float32, device=dev) if curve else empty()
+    st = _cabi.lib().mdf_prob_head_fwd_ex(
+        v.data_ptr(), w.data_ptr(), hyp.data_ptr(), per_pixel, B, C, D, H, W,
+        logits.data_ptr() if want_logits else None, prob.data_ptr() if want_prob else None, depth.data_ptr(),
+        conf.data_ptr() if want_confidence else None, n, pad_front, pad_back, upsample,
+        _CURVES[curve] if curve else 0, s.data_ptr() if curve else None, int(algo), _stream(v))
+    _cabi.check("mdf_prob_head_fwd", st)
+    _count(_LAUNCHES_SIMPLE)
+    return logits, prob, depth, conf, s
+
+
+@prob_head.register_fake
+def _(x, prob_weight, depth_hypos, curve="", want_logits=False, want_prob=True, want_confidence=False, n=4, pad_front=1,
+      pad_back=2, upsample=2, algo=0):
+    B, C, D, H, W = x.shape
+    e = x.new_empty(0)
+    return (x.new_empty((B, D, H, W)) if want_logits else e, x.new_empty((B, D, H, W)) if want_prob else e,
+            x.new_empty((B, H, W)), x.new_empty((B, H * upsample, W * upsample)) if want_confidence else e,
+            x.new_empty((B, H, W)) if curve else e)
 
 
 @torch.library.custom_op("mdfnet_b200::depth_regression", mutates_args=(), device_types="cuda")
@@ -345,9 +428,6 @@ def _(features, ref_proj, src_projs, depth_hypos, conv_weight, bn_weight, bn_bia
 
 
 # ------------------------------------------------------------------ next-stage hypotheses (HyposByFit)
-_CURVES = {"gauss1": 1, "laplace": 2}
-
-
 @torch.library.custom_op("mdfnet_b200::hypos_fit", mutates_args=(), device_types="cuda")
 def hypos_fit(prob_volume: Tensor, depth_hypos: Tensor, depth: Tensor, curve: str) -> Tensor:
     """Fitted scale s (B,H,W) of every pixel's probability column: depthhypos.py:78-125 ('laplace'), :169-215 ('gauss1')."""

@@ -174,6 +174,17 @@ def softmax_depth(logits, prec="f32"):
     return out
 
 
+def prob_conv(x, weight, prec="f32"):
+    """x = self.prob(x).squeeze(1): Conv3d(c0, 1, 3, padding=1, bias=False) (regular.py:43,67 / :110,130) -> logits (B,D,H,W)."""
+    v = _arr(x, prec)
+    B, C, D, H, W = v.shape
+    w = _arr(weight, prec).reshape(C, 3, 3, 3)
+    out = np.empty((B, D, H, W), _dt(prec))
+    fn = getattr(_lib(prec), f"mdf_oracle_prob_conv_{prec}")
+    _check(fn(_ptr(v), _ptr(w), B, C, D, H, W, _ptr(out)), "prob_conv")
+    return out
+
+
 def depth_regression(prob_volume, depth_hypos, prec="f32"):
     """regress.py:5-7."""
     p = _arr(prob_volume, prec)

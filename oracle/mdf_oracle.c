@@ -15,6 +15,7 @@
  *   softmax tail of the 3-D CNN  net/unit/regular.py:67-69,130-133
  *   depth_regression             net/unit/regress.py:5-7
  *   confidence_regress           net/unit/regress.py:9-25 (+ nearest x2, net/core.py:75-77)
+ *   prob conv of the 3-D CNN     net/unit/regular.py:43,67 / :110,130 (Conv3d(c0,1,3,pad=1,bias=False))
  *
  * The arithmetic of the reference lives in PyTorch (third party; the reference
  * pins torch==1.7.1, this image has 2.11.0).  The pieces of ATen that are
@@ -536,5 +537,40 @@ int SYM(mdf_oracle_hypos_generate)(const REAL *depth, const REAL *s, const REAL 
                 }
             }
     }
+    return MDF_OK;
+}
+
+/* ---- last layer of the regulariser: x = self.prob(x).squeeze(1)  (net/unit/regular.py:43,67 and :110,130) --------
+ * nn.Conv3d(c0, 1, 3, stride=1, padding=1, bias=False): cross-correlation with zero padding,
+ *   logits[b][d][y][x] = sum_{c,kd,ky,kx} w[c][kd][ky][kx] * x[b][c][d+kd-1][y+ky-1][x+kx-1].
+ * torch's CPU convolution (oneDNN / slow_conv3d) does not document its summation order; this restatement sums in
+ * (c, kd, ky, kx) order with one rounding per multiply-add pair (separate mul and add), and the float64 build is the
+ * yardstick for what any float32 order can claim. */
+int SYM(mdf_oracle_prob_conv)(const REAL *x, const REAL *w, int B, int C, int D, int H, int W, REAL *logits)
+{
+    if (B < 0 || C < 1 || D < 0 || H < 0 || W < 0) return MDF_EINVAL;
+    const size_t HW = (size_t)H * W;
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int b = 0; b < B; ++b)
+        for (int d = 0; d < D; ++d)
+            for (int y = 0; y < H; ++y)
+                for (int xx = 0; xx < W; ++xx) {
+                    REAL acc = 0;
+                    for (int c = 0; c < C; ++c)
+                        for (int kd = 0; kd < 3; ++kd) {
+                            const int dz = d + kd - 1;
+                            if (dz < 0 || dz >= D) continue;
+                            for (int ky = 0; ky < 3; ++ky) {
+                                const int yy = y + ky - 1;
+                                if (yy < 0 || yy >= H) continue;
+                                for (int kx = 0; kx < 3; ++kx) {
+                                    const int xs = xx + kx - 1;
+                                    if (xs < 0 || xs >= W) continue;
+                                    acc += w[((c * 3 + kd) * 3 + ky) * 3 + kx] * x[(((size_t)b * C + c) * D + dz) * HW + (size_t)yy * W + xs];
+                                }
+                            }
+                        }
+                    logits[((size_t)b * D + d) * HW + (size_t)y * W + xx] = acc;
+                }
     return MDF_OK;
 }

@@ -8,7 +8,8 @@ The reference ships no tests, golden vectors or checkpoints, so p
 pinned on outputs of the reference's own functions imported as-is:
   net.unit.base.homo_warping, net.unit.homoaggregate.{VectorAggregate,
   homo_aggregate_by_variance}, net.unit.regress.{depth_regression, confidence_regress},
-  net.unit.scale.scale_cam, F.softmax tail of net.unit.regular, and a whole
+  net.unit.scale.scale_cam, net.unit.regular.RegularNet_{3,4}Scales (input / output of their last layer `.prob`),
+  net.unit.depthhypos.HyposByFit, and a whole
   config.model (CoreNet) forward with per-stage tensors captured by hooks.
 Inputs come from mdf_net_b200.synthetic (seeded); each .npz stores inputs and outputs so the
 GPU box (which has no /root/reference) can replay them.
@@ -215,6 +216,53 @@ def gen_hypos():
     save("hypos_fit", **out)
 
 
+# ------------------------------------------------------ regulariser tail: prob conv + softmax + head + fit
+def gen_prob_head():
+    """The last layer of the reference's regularisers (net/unit/regular.py:43,67-69 and :110,130-133) with what follows
+    it in CoreNet.forward: `self.prob` (Conv3d(c0,1,3,pad=1,no bias)) -> softmax -> depth_regression (-> confidence on the
+    last stage) (-> the curve fit of the next stage's HyposByFit).  The unmodified modules run on a random cost volume;
+    hooks capture the input and output of `.prob`."""
+    from net.unit.depthhypos import HyposByFit
+    from net.unit.regular import RegularNet_3Scales, RegularNet_4Scales
+    g = torch.Generator().manual_seed(97)
+    for name, net, B, G, D, H, W, curve, seed in [
+        ("prob_head_s0", RegularNet_3Scales(32), 1, 32, 48, 8, 12, "gauss1", 101),
+        ("prob_head_s1", RegularNet_4Scales(16), 2, 16, 24, 16, 24, "laplace", 102),
+        ("prob_head_s2", RegularNet_4Scales(8), 1, 8, 8, 16, 24, None, 103),
+    ]:
+        net = net.eval()
+        with torch.no_grad():
+            for m in net.modules():
+                if isinstance(m, torch.nn.BatchNorm3d):
+                    m.running_mean.copy_(0.1 * torch.randn(m.running_mean.shape, generator=g))
+                    m.running_var.copy_(0.5 + torch.rand(m.running_var.shape, generator=g))
+                    m.weight.copy_(0.8 + 0.4 * torch.rand(m.weight.shape, generator=g))
+                    m.bias.copy_(0.1 * torch.randn(m.bias.shape, generator=g))
+        cv = T(np.random.default_rng(seed).uniform(0.2, 0.8, (B, G, D, H, W)).astype(np.float32))
+        cap = {}
+        h1 = net.prob.register_forward_pre_hook(lambda mod, args: cap.__setitem__("x", args[0].numpy().copy()))
+        h2 = net.prob.register_forward_hook(lambda mod, args, out: cap.__setitem__("logits", out.squeeze(1).numpy().copy()))
+        with torch.no_grad():
+            net(cv)
+            net.prob.weight.mul_(2.0 / float(np.std(cap["logits"])))       # useful logits (default init gives ~1e-2)
+            prob = net(cv)
+        h1.remove(); h2.remove()
+        hyp = syn.uniform_hypos(B, D) if name.endswith("s0") else syn.pixel_hypos(B, D, H, W, seed=seed)
+        depth = regress.depth_regression(prob, T(hyp))
+        out = dict(x=cap["x"], weight=net.prob.weight.detach().numpy(), logits=cap["logits"], prob=prob.numpy(),
+                   depth_hypos=hyp, depth=depth.numpy())
+        if curve is None:
+            conf = regress.confidence_regress(prob)
+            out["confidence_up"] = F.interpolate(conf.unsqueeze(1), size=None, scale_factor=2, mode="nearest",
+                                                 align_corners=None).squeeze(1).numpy()       # core.py:76-77
+        else:
+            m = HyposByFit(8, curve, 0.95)
+            fit = m._gauss_fitting1 if curve == "gauss1" else m._laplace_fitting
+            out["s"] = fit(depth, prob, T(hyp)).numpy()
+            out["s_f64"] = fit(depth.double(), prob.double(), T(hyp).double()).numpy()
+        save(name, **out)
+
+
 # -------------------------------------------------------------------------------- scale_cam
 def gen_scale():
     K, E = syn.camera_rig(2, 4, 64, 80, seed=51)
@@ -308,6 +356,6 @@ def gen_corenet():
 
 if __name__ == "__main__":
     only = sys.argv[1:]
-    for fn in (gen_warp, gen_vecagg, gen_vecagg_grad, gen_varagg, gen_head, gen_hypos, gen_scale, gen_corenet):
+    for fn in (gen_warp, gen_vecagg, gen_vecagg_grad, gen_varagg, gen_head, gen_hypos, gen_prob_head, gen_scale, gen_corenet):
         if not only or fn.__name__ in only:
             fn()

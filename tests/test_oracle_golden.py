@@ -183,3 +183,27 @@ def test_hypos_by_fit():
     h2 = co.hypos_generate(z["depth1"], s2, z["depth_range"], "laplace", 1e-5, 8)
     assert np.abs(h2 - z["hypos2"]).max() < 2.5e-4
     assert h2.shape == z["hypos2"].shape == (2, 8, 48, 64)
+
+
+@pytest.mark.parametrize("name", ["prob_head_s0", "prob_head_s1", "prob_head_s2"])
+def test_prob_conv_and_tail(name):
+    """Last layer of the reference's regularisers (input / output of `.prob` captured by hooks) and what CoreNet does
+    with it: the conv restatement against the reference's logits, then the chained tail against the reference's."""
+    z = load_golden(name)
+    logits = co.prob_conv(z["x"], z["weight"])
+    logits64 = co.prob_conv(z["x"], z["weight"], prec="f64")
+    ref_noise = np.abs(z["logits"] - logits64).max()            # the reference's own float32 distance to float64
+    assert np.abs(logits - logits64).max() < 4 * max(ref_noise, 1e-6)
+    assert np.abs(logits - z["logits"]).max() < 2e-5            # logits are O(1-10): a few float32 ulps of the sums
+    prob = co.softmax_depth(logits)
+    assert np.abs(prob - z["prob"]).max() < 2e-5
+    depth = co.depth_regression(prob, z["depth_hypos"])
+    assert np.abs(depth - z["depth"]).max() < 1e-3 * (935.0 - 425.0) / 47.0
+    if "confidence_up" in z.files:
+        conf = co.confidence_regress(prob, upsample=2)
+        assert (np.abs(conf - z["confidence_up"]) < 1e-4).mean() >= 0.995
+    else:
+        curve = "gauss1" if name.endswith("s0") else "laplace"
+        s = co.hypos_fit(z["prob"], z["depth_hypos"], z["depth"], curve)
+        ref = z["s_f64"] if curve == "gauss1" else z["s"]
+        assert (np.abs(s - ref) / np.abs(ref)).max() < (5e-3 if curve == "gauss1" else 1e-5)
