@@ -5,8 +5,9 @@ net/unit/base.py, net/unit/regress.py), backed by hand-written CUDA kernels behi
 (include/mdf_b200.h, mdf_net_b200/libmdf_b200.so).  Importing the package does not need a GPU;
 calling an op without the built library or with CPU tensors raises.
 """
+from .core import CoreNet
 from .units import (HyposByFit, VectorAggregate, confidence_regress, depth_regression, homo_aggregate_by_variance,
                     homo_warping, softmax_regress)
 
 __all__ = ["VectorAggregate", "homo_warping", "homo_aggregate_by_variance", "depth_regression", "confidence_regress",
-           "softmax_regress", "HyposByFit"]
+           "softmax_regress", "HyposByFit", "CoreNet"]
