@@ -26,6 +26,7 @@
 #include "mdf_common.cuh"
 #include "mdf_host.cuh"
 #include "mdf_tail.cuh"
+#include "mdf_tma.cuh"
 
 namespace mdf {
 
@@ -79,7 +80,12 @@ struct ProbCfg {
 template <int D, int S, int FIT>
 __device__ __forceinline__ void column_tail(float* __restrict__ cs, const ProbHeadArgs& a, int b, int y, int x)
 {
+    constexpr int CH = 8;                           // planes per batch: their hypotheses are requested together
+    static_assert(D % CH == 0, "the configured depths are multiples of 8");
     const size_t HW = (size_t)a.H * a.W, p = (size_t)y * a.W + x;
+    const float* __restrict__ hcol = a.per_pixel ? a.hypos + (size_t)b * D * HW + p : a.hypos + (size_t)b * D;
+    const size_t hstride = a.per_pixel ? HW : 1;
+    const bool need_h = a.depth != nullptr || FIT != 0;
     float m = cs[0];
 #pragma unroll 8
     for (int d = 1; d < D; ++d) m = fmaxf(m, cs[d * S]);
@@ -90,35 +96,44 @@ __device__ __forceinline__ void column_tail(float* __restrict__ cs, const ProbHe
         cs[d * S] = e;
         sum = __fadd_rn(sum, e);
     }
-    const float* __restrict__ hcol = a.per_pixel ? a.hypos + (size_t)b * D * HW + p : a.hypos + (size_t)b * D;
-    const size_t hstride = a.per_pixel ? HW : 1;
-    const bool need_h = a.depth != nullptr || FIT != 0;
     float* __restrict__ pc = a.prob ? a.prob + (size_t)b * D * HW + p : nullptr;
     float acc = 0.0f, eidx = 0.0f;
     double hs = 0.0;
-#pragma unroll 8
-    for (int d = 0; d < D; ++d) {
-        const float pr = __fdiv_rn(cs[d * S], sum);
-        cs[d * S] = pr;
-        if (pc) pc[(size_t)d * HW] = pr;
-        eidx = __fadd_rn(eidx, __fmul_rn(pr, (float)d));                              // regress.py:15-17
-        if (need_h) {
-            const float hv = __ldg(hcol + (size_t)d * hstride);
-            acc = __fadd_rn(acc, __fmul_rn(pr, hv));                                  // regress.py:7
-            if (FIT == 1) hs += (double)hv;
+    for (int d0 = 0; d0 < D; d0 += CH) {
+        float hv[CH];
+#pragma unroll
+        for (int i = 0; i < CH; ++i) hv[i] = need_h ? __ldg(hcol + (size_t)(d0 + i) * hstride) : 0.0f;
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+            const float pr = __fdiv_rn(cs[(d0 + i) * S], sum);
+            cs[(d0 + i) * S] = pr;
+            if (pc) pc[(size_t)(d0 + i) * HW] = pr;
+            eidx = __fadd_rn(eidx, __fmul_rn(pr, (float)(d0 + i)));                    // regress.py:15-17
+            acc = __fadd_rn(acc, __fmul_rn(pr, hv[i]));                                // regress.py:7
+            if (FIT == 1) hs += (double)hv[i];
         }
     }
     if (a.depth) a.depth[(size_t)b * HW + p] = acc;
     if (FIT == 2) {
         LaplaceSums ls;
-#pragma unroll 4
-        for (int d = 0; d < D; ++d) ls.add(__ldg(hcol + (size_t)d * hstride), acc, cs[d * S]);      // L1 hits
+        for (int d0 = 0; d0 < D; d0 += CH) {
+            float hv[CH];
+#pragma unroll
+            for (int i = 0; i < CH; ++i) hv[i] = __ldg(hcol + (size_t)(d0 + i) * hstride);     // L1 hits
+#pragma unroll
+            for (int i = 0; i < CH; ++i) ls.add(hv[i], acc, cs[(d0 + i) * S]);
+        }
         a.s[(size_t)b * HW + p] = ls.scale();
     } else if (FIT == 1) {
         const double mean = hs / (double)D;
         GaussMoments gm;
+        for (int d0 = 0; d0 < D; d0 += CH) {
+            float hv[CH];
+#pragma unroll
+            for (int i = 0; i < CH; ++i) hv[i] = __ldg(hcol + (size_t)(d0 + i) * hstride);
 #pragma unroll 2
-        for (int d = 0; d < D; ++d) gm.add((double)__ldg(hcol + (size_t)d * hstride) - mean, cs[d * S]);
+            for (int i = 0; i < CH; ++i) gm.add((double)hv[i] - mean, cs[(d0 + i) * S]);
+        }
         a.s[(size_t)b * HW + p] = gm.scale(D);
     }
     if (a.conf) {
@@ -132,6 +147,17 @@ __device__ __forceinline__ void column_tail(float* __restrict__ cs, const ProbHe
         const float fn = (float)a.conf_n;
         store_upsampled(a.conf, __fmul_rn(fn, __fdiv_rn(sw, fn)), b, y, x, a.H, a.W, a.up);
     }
+}
+
+// The tail's per-pixel hypotheses are the only global loads after the convolution: ask L2 for them up front.
+template <int D>
+__device__ __forceinline__ void prefetch_hypotheses(const ProbHeadArgs& a, int b, int y, int x)
+{
+    if (!a.per_pixel || !(a.depth != nullptr || a.s != nullptr) || y >= a.H || x >= a.W) return;
+    const size_t HW = (size_t)a.H * a.W;
+    const float* hcol = a.hypos + (size_t)b * D * HW + (size_t)y * a.W + x;
+#pragma unroll 8
+    for (int d = 0; d < D; ++d) asm volatile("prefetch.global.L2 [%0];" ::"l"(hcol + (size_t)d * HW));
 }
 
 template <class Cfg, int FIT>
@@ -274,6 +300,188 @@ prob_head_kernel(const ProbHeadArgs a)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The fast variant (W % 4 == 0, 16-byte aligned volume): the feature volume comes in by TMA.
+//   * x is a 4-D tensor map [B*c0][D][H][W]; one pipeline stage = ONE channel of the CTA's tile with its halo:
+//     box [D (+2)][4*NT + 2][40] floats at (xt - 4, yt - 1, -1 | 0, b*c0 + c).  TMA's out-of-bounds zero fill IS the
+//     convolution's zero padding (left / right / top / bottom / first and last depth plane): the compute loop has no
+//     bounds predicate at all.
+//   * a dedicated producer warp keeps NSTAGE channels in flight (full / empty mbarriers per stage); the consumer
+//     warps -- the same 8 x 4-lane tiles and depth slabs as above -- read their rows with LDS.128 (a quarter warp reads
+//     128 contiguous bytes: conflict free), take the x-1 / x+4 neighbours from the adjacent lanes by shuffle (the two
+//     edge lanes of a row: one LDS.32 from the halo columns of the box) and issue 27*4 FFMAs per plane.
+//   * the logits meet in shared memory (the stage buffers are reused) and the column tail runs as above.
+// ------------------------------------------------------------------------------------------------
+template <int D_, int DSLAB_, int NT_, int NSTAGE_, int MINB_>
+struct ProbTmaCfg {
+    static constexpr int D = D_, DSLAB = DSLAB_, NT = NT_, NSTAGE = NSTAGE_, MINB = MINB_, PX = 4;
+    static constexpr int NWD = D / DSLAB;
+    static constexpr int CWARPS = NWD * NT, THREADS = 32 * (CWARPS + 1);       // consumers + one producer warp
+    static constexpr int TW = 32, TH = 4, TPIX = TW * TH;
+    static constexpr int DHALO = NWD > 1 ? 1 : 0;                              // one warp owns the whole column: no depth halo
+    static constexpr int BW = 40, BH = TH * NT + 2, BD = D + 2 * DHALO;
+    static constexpr int STAGE_BYTES = BD * BH * BW * 4;
+    static constexpr int STAGE_STRIDE = (STAGE_BYTES + 127) / 128 * 128;
+    static constexpr int COL_BYTES = NT * D * TPIX * 4;
+    static constexpr int OFF_W = NSTAGE * STAGE_STRIDE;
+    static constexpr int OFF_BAR = OFF_W + kMaxProbChannels * 28 * 4;
+    static constexpr size_t SMEM = OFF_BAR + 16 * NSTAGE + 128 /* alignment slack */;
+    static_assert(D % DSLAB == 0, "slabs must tile the depth axis");
+    static_assert(COL_BYTES <= NSTAGE * STAGE_STRIDE, "the logits reuse the stage buffers");
+    static_assert(BD <= 256 && BH <= 256, "TMA box dimensions are limited to 256 elements");
+};
+
+template <class Cfg, int FIT>
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB)
+prob_head_tma_kernel(const __grid_constant__ CUtensorMap xmap, const ProbHeadArgs a)
+{
+    constexpr int D = Cfg::D, DSLAB = Cfg::DSLAB, NT = Cfg::NT, NSTAGE = Cfg::NSTAGE, PX = 4, TPIX = Cfg::TPIX, TW = Cfg::TW;
+    constexpr int BW = Cfg::BW, BH = Cfg::BH, CWARPS = Cfg::CWARPS, NWD = Cfg::NWD;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t pad = (128u - (smem_u32(smem_raw) & 127u)) & 127u;
+    uint8_t* base = smem_raw + pad;
+    const uint32_t base_s = smem_u32(base);
+    float* w_s = reinterpret_cast<float*>(base + Cfg::OFF_W);
+    const uint32_t full0 = base_s + Cfg::OFF_BAR, empty0 = full0 + 8 * NSTAGE;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int H = a.H, W = a.W, C = a.C;
+    const int b = blockIdx.z;
+    const int xt = blockIdx.x * TW, yt0 = blockIdx.y * NT * Cfg::TH;
+    const size_t HW = (size_t)H * W;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, CWARPS); }
+        fence_barrier_init();
+    }
+    for (int i = tid; i < C * 28; i += Cfg::THREADS) {
+        const int c = i / 28, k = i % 28;
+        w_s[i] = k < 27 ? __ldg(a.w + c * 27 + k) : 0.0f;
+    }
+    __syncthreads();
+
+    // hypotheses of the tile's pixels -> L2, one request per 32-byte sector (they are read by the tail, much later)
+    for (int col = tid * 8; col < NT * TPIX; col += Cfg::THREADS * 8)
+        prefetch_hypotheses<D>(a, b, yt0 + (col / TPIX) * Cfg::TH + (col % TPIX) / TW, xt + (col % TPIX) % TW);
+
+    float lg[DSLAB][PX];
+#pragma unroll
+    for (int j = 0; j < DSLAB; ++j)
+#pragma unroll
+        for (int k = 0; k < PX; ++k) lg[j][k] = 0.0f;
+    const int wz = warp % NWD, t = warp / NWD;             // consumers: depth slab, tile
+    const int lx = lane & 7, ly = lane >> 3;
+    const int d0 = wz * DSLAB;
+
+    if (warp == CWARPS) {
+        // ---- producer: one lane keeps NSTAGE channels in flight ----
+        if (lane == 0) {
+            for (int c = 0; c < C; ++c) {
+                const int s = c % NSTAGE, k = c / NSTAGE;
+                if (k > 0) mbar_wait(empty0 + 8 * s, (uint32_t)(k - 1) & 1u);       // every consumer warp has left channel c - NSTAGE
+                mbar_expect_tx(full0 + 8 * s, Cfg::STAGE_BYTES);
+                tma_load_4d(base_s + s * Cfg::STAGE_STRIDE, &xmap, full0 + 8 * s, xt - 4, yt0 - 1, -Cfg::DHALO, b * C + c);
+            }
+        }
+    } else {
+        // ---- consumers ----
+        // this lane's (row y-1, column x0) of plane d0-1 (or d0) inside a stage, and the halo column of the edge lanes
+        const uint32_t lane_off = (uint32_t)((d0 * BH + t * Cfg::TH + ly) * BW + 4 + lx * PX) * 4u;
+        const uint32_t halo_off = lane_off + (lx == 0 ? (uint32_t)-4 : (uint32_t)(PX * 4));
+        const bool edge = lx == 0 || lx == 7;
+        constexpr int NP = DSLAB + 2 * Cfg::DHALO;          // input planes of a slab: local q = 0 .. NP-1, dl = q - DHALO
+        for (int c = 0; c < C; ++c) {
+            const int s = c % NSTAGE;
+            float wt[28];
+#pragma unroll
+            for (int q = 0; q < 7; ++q) {
+                const float4 v4 = *reinterpret_cast<const float4*>(w_s + c * 28 + 4 * q);
+                wt[4 * q] = v4.x; wt[4 * q + 1] = v4.y; wt[4 * q + 2] = v4.z; wt[4 * q + 3] = v4.w;
+            }
+            mbar_wait(full0 + 8 * s, (uint32_t)(c / NSTAGE) & 1u);
+            const uint32_t sb = base_s + s * Cfg::STAGE_STRIDE;
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                const int dl = q - Cfg::DHALO;
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) {
+                    const uint32_t off = (uint32_t)((q * BH + ky) * BW) * 4u;          // literal
+                    const float4 v4 = lds128(sb + lane_off + off);
+                    float hv = 0.0f;
+                    if (edge) hv = lds32(sb + halo_off + off);
+                    const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+                    const float sl = __shfl_up_sync(0xffffffffu, v4.w, 1);
+                    const float sr = __shfl_down_sync(0xffffffffu, v4.x, 1);
+                    const float left = lx != 0 ? sl : hv, right = lx != 7 ? sr : hv;
+#pragma unroll
+                    for (int kd = 0; kd < 3; ++kd) {
+                        const int j = dl - kd + 1;                                      // plane dl feeds slab-local output j
+                        if (j < 0 || j >= DSLAB) continue;
+                        const float w0 = wt[kd * 9 + ky * 3], w1 = wt[kd * 9 + ky * 3 + 1], w2 = wt[kd * 9 + ky * 3 + 2];
+#pragma unroll
+                        for (int k = 0; k < PX; ++k) {
+                            const float tl = k == 0 ? left : v[k > 0 ? k - 1 : 0];
+                            const float tr = k == PX - 1 ? right : v[k < PX - 1 ? k + 1 : 0];
+                            lg[j][k] = fmaf(w2, tr, fmaf(w1, v[k], fmaf(w0, tl, lg[j][k])));
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty0 + 8 * s);
+        }
+    }
+    __syncthreads();                                        // every stage has been consumed: the buffers become the logits' home
+
+    float* col_s = reinterpret_cast<float*>(base);
+    if (warp < CWARPS) {
+        const int x0 = xt + lx * PX, y = yt0 + t * Cfg::TH + ly;
+        float* cs = col_s + ((size_t)t * D + d0) * TPIX + ly * TW + lx * PX;
+        const bool ok = x0 < W && y < H;
+#pragma unroll
+        for (int j = 0; j < DSLAB; ++j) {
+            *reinterpret_cast<float4*>(cs + j * TPIX) = make_float4(lg[j][0], lg[j][1], lg[j][2], lg[j][3]);
+            if (a.logits && ok)
+                *reinterpret_cast<float4*>(a.logits + ((size_t)b * D + d0 + j) * HW + (size_t)y * W + x0) =
+                    make_float4(lg[j][0], lg[j][1], lg[j][2], lg[j][3]);
+        }
+    }
+    if (!a.prob && !a.depth && !a.conf && !a.s) return;     // uniform over the grid
+    __syncthreads();
+    for (int col = tid; col < NT * TPIX; col += Cfg::THREADS) {
+        const int tt = col / TPIX, pp = col % TPIX;
+        const int yy = yt0 + tt * Cfg::TH + pp / TW, xx = xt + pp % TW;
+        if (yy >= H || xx >= W) continue;
+        column_tail<D, TPIX, FIT>(col_s + (size_t)tt * D * TPIX + pp, a, b, yy, xx);
+    }
+}
+
+template <class Cfg>
+static int launch_prob_head_tma(const ProbHeadArgs& a, int fit, cudaStream_t stream)
+{
+    EncodeTiledFn encode = get_encode_fn();
+    if (encode == nullptr) return MDF_ERR_UNSUPPORTED;
+    CUtensorMap xmap;
+    const cuuint64_t dims[4] = {(cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)Cfg::D, (cuuint64_t)a.B * a.C};
+    const cuuint64_t strides[3] = {(cuuint64_t)a.W * 4, (cuuint64_t)a.H * a.W * 4, (cuuint64_t)Cfg::D * a.H * a.W * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)Cfg::BW, (cuuint32_t)Cfg::BH, (cuuint32_t)Cfg::BD, 1u};
+    const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    CUresult r = encode(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(a.x), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { g_last_cuda_error = (int)r; return MDF_ERR_CUDA; }
+    const dim3 grid((unsigned)((a.W + Cfg::TW - 1) / Cfg::TW), (unsigned)((a.H + Cfg::TH * Cfg::NT - 1) / (Cfg::TH * Cfg::NT)), (unsigned)a.B);
+    if (grid.y > 65535u || grid.z > 65535u) return MDF_ERR_UNSUPPORTED;
+    auto launch = [&](auto kern) -> int {
+        MDF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        kern<<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(xmap, a);
+        return launch_status();
+    };
+    if (fit == 1) return launch(prob_head_tma_kernel<Cfg, 1>);
+    if (fit == 2) return launch(prob_head_tma_kernel<Cfg, 2>);
+    return launch(prob_head_tma_kernel<Cfg, 0>);
+}
+
 template <class Cfg>
 static int launch_prob_head(const ProbHeadArgs& a, int fit, cudaStream_t stream)
 {
@@ -286,19 +494,20 @@ static int launch_prob_head(const ProbHeadArgs& a, int fit, cudaStream_t stream)
     return launch_status();
 }
 
-// Variants (algo k of mdf_prob_head_fwd_ex; 0 = default):        D  DSLAB NT PX
-using Prob48_0 = ProbCfg<48, 8, 1, 4>;      // 6 warps along D, tile 32x4
-using Prob48_1 = ProbCfg<48, 6, 1, 4>;      // 8 warps
-using Prob48_2 = ProbCfg<48, 4, 1, 4>;      // 12 warps
-using Prob48_s = ProbCfg<48, 8, 1, 1>;      // scalar loads (W % 4 != 0 or misaligned planes), tile 8x4
-using Prob24_0 = ProbCfg<24, 8, 2, 4>;      // 3 warps along D x 2 tiles
-using Prob24_1 = ProbCfg<24, 6, 2, 4>;      // 4 x 2
-using Prob24_2 = ProbCfg<24, 4, 1, 4>;      // 6 x 1
+// Scalar fallback of the register-pipelined kernel (W % 4 != 0 or misaligned volume):    D  DSLAB NT PX
+using Prob48_s = ProbCfg<48, 8, 1, 1>;
 using Prob24_s = ProbCfg<24, 8, 2, 1>;
-using Prob8_0 = ProbCfg<8, 8, 4, 4>;        // whole column per thread, 4 tiles
-using Prob8_1 = ProbCfg<8, 4, 2, 4>;        // 2 warps along D x 2 tiles
-using Prob8_2 = ProbCfg<8, 8, 2, 4>;
 using Prob8_s = ProbCfg<8, 8, 4, 1>;
+// TMA variants (algo k of mdf_prob_head_fwd_ex; 0 = default):   D  DSLAB NT NSTAGE MINB
+using Tma48_0 = ProbTmaCfg<48, 4, 1, 2, 2>;       // 12 + 1 warps, 2 x 48 KB stages, 2 CTAs / SM
+using Tma48_1 = ProbTmaCfg<48, 8, 1, 2, 2>;       // 6 + 1 warps
+using Tma48_2 = ProbTmaCfg<48, 6, 1, 3, 1>;       // 8 + 1 warps, 3 stages, 1 CTA / SM
+using Tma24_0 = ProbTmaCfg<24, 6, 2, 2, 2>;       // 4 x 2 + 1 warps, 2 x 41.6 KB stages
+using Tma24_1 = ProbTmaCfg<24, 4, 1, 3, 3>;       // 6 + 1 warps, tile 32x4, 3 x 25 KB
+using Tma24_2 = ProbTmaCfg<24, 8, 2, 2, 2>;       // 3 x 2 + 1 warps
+using Tma8_0 = ProbTmaCfg<8, 8, 4, 2, 3>;         // whole column per thread, 4 + 1 warps, 2 x 23 KB
+using Tma8_1 = ProbTmaCfg<8, 8, 8, 2, 2>;         // 8 + 1 warps, tile 32x32
+using Tma8_2 = ProbTmaCfg<8, 4, 4, 3, 2>;         // 2 x 4 + 1 warps, 3 stages
 
 }  // namespace mdf
 
@@ -354,20 +563,20 @@ int mdf_prob_head_fwd_ex(const float* x, const float* prob_weight, const float* 
     }
     if (D == 8) {
         if (!vec) return launch_prob_head<Prob8_s>(a, curve, stream);
-        if (algo == 1) return launch_prob_head<Prob8_1>(a, curve, stream);
-        if (algo == 2) return launch_prob_head<Prob8_2>(a, curve, stream);
-        return launch_prob_head<Prob8_0>(a, curve, stream);
+        if (algo == 1) return launch_prob_head_tma<Tma8_1>(a, curve, stream);
+        if (algo == 2) return launch_prob_head_tma<Tma8_2>(a, curve, stream);
+        return launch_prob_head_tma<Tma8_0>(a, curve, stream);
     }
     if (D == 24) {
         if (!vec) return launch_prob_head<Prob24_s>(a, curve, stream);
-        if (algo == 1) return launch_prob_head<Prob24_1>(a, curve, stream);
-        if (algo == 2) return launch_prob_head<Prob24_2>(a, curve, stream);
-        return launch_prob_head<Prob24_0>(a, curve, stream);
+        if (algo == 1) return launch_prob_head_tma<Tma24_1>(a, curve, stream);
+        if (algo == 2) return launch_prob_head_tma<Tma24_2>(a, curve, stream);
+        return launch_prob_head_tma<Tma24_0>(a, curve, stream);
     }
     if (!vec) return launch_prob_head<Prob48_s>(a, curve, stream);
-    if (algo == 1) return launch_prob_head<Prob48_1>(a, curve, stream);
-    if (algo == 2) return launch_prob_head<Prob48_2>(a, curve, stream);
-    return launch_prob_head<Prob48_0>(a, curve, stream);
+    if (algo == 1) return launch_prob_head_tma<Tma48_1>(a, curve, stream);
+    if (algo == 2) return launch_prob_head_tma<Tma48_2>(a, curve, stream);
+    return launch_prob_head_tma<Tma48_0>(a, curve, stream);
 }
 
 int mdf_prob_head_fwd(const float* x, const float* prob_weight, const float* depth_hypos, int hypos_per_pixel,

@@ -10,15 +10,29 @@ import torch.nn.functional as F
 from mdf_net_b200 import ops, synthetic as syn
 
 
-def timeit(fn, n=9, warm=3):
+def timeit(fn, n=9, warm=3, reps=10):
+    """Median over n replays of a CUDA graph holding `reps` calls (the Python / ctypes cost of a call, ~40 us, is not
+    what is being measured), in us per call."""
     for _ in range(warm):
         fn()
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fn()
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    keep = []
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            keep.append(fn())
+    g.replay()
     torch.cuda.synchronize()
     ts = []
     for _ in range(n):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); fn(); b.record(); torch.cuda.synchronize()
-        ts.append(a.elapsed_time(b))
+        a.record(); g.replay(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) / reps)
     return sorted(ts)[len(ts) // 2] * 1e3
 
 
