@@ -230,6 +230,58 @@ def run_reference(args, workload, out):
         "gpu_launches": 0}))
 
 
+
+def time_regulariser_tail(dev, h0, w0, batch, host_view):
+    """SURVEY 8f rows 1-2, reported next to the headline (not part of `value`): the fused tail of the regulariser
+    (mdf_prob_head_fwd: prob conv + softmax + depth regression + confidence / curve fit, one launch per stage) on
+    synthetic post-ReLU feature volumes of the real shapes (c0 = 16 / 8 / 8, config.py:208-212), and what the same three
+    convolutions cost through cuDNN on this GPU (the reference's path for that layer).  CUDA-graph replays, us."""
+    import torch
+    import torch.nn.functional as F
+    from mdf_net_b200 import ops
+
+    def graph_us(fn, reps=10, n=5):
+        fn(); torch.cuda.synchronize()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            fn()
+        torch.cuda.current_stream().wait_stream(side)
+        g, keep = torch.cuda.CUDAGraph(), []
+        with torch.cuda.graph(g):
+            for _ in range(reps):
+                keep.append(fn())
+        g.replay(); torch.cuda.synchronize()
+        ts = []
+        for _ in range(n):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); g.replay(); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b) / reps * 1e3)
+        return statistics.median(ts)
+
+    fused, cudnn, nbytes = [], [], []
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        for s, st in enumerate(host_view):
+            c0 = (16, 8, 8)[s]
+            gen = torch.Generator(device=dev).manual_seed(50 + s)
+            x = torch.randn((batch, c0, st["D"], st["H"], st["W"]), device=dev, generator=gen).relu_()
+            w = torch.randn((1, c0, 3, 3, 3), device=dev, generator=gen) * 0.35
+            hyp = torch.from_numpy(np.ascontiguousarray(st["hypos"])).to(dev)
+            curve = ("gauss1", "laplace", "")[s]
+            fused.append(graph_us(lambda: ops.prob_head(x, w, hyp, curve, False, False, s == 2)))
+            cudnn.append(graph_us(lambda: F.conv3d(x, w, padding=1), reps=3, n=3))
+            nbytes.append(x.numel() * 4)
+            del x
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    return {"what": "prob conv + softmax + depth regression + confidence / curve fit, one launch per stage (mdf_prob_head_fwd)",
+            "fused_us": fused, "fused_us_per_view": sum(fused), "input_bytes": nbytes,
+            "GBps": [b / 1e9 / (t / 1e6) for b, t in zip(nbytes, fused)],
+            "cudnn_conv3d_alone_us": cudnn, "not_in_value": True}
+
+
 # ----------------------------------------------------------------------------------------- GPU arm
 def run_b200(args, workload, out):
     import torch
@@ -463,6 +515,11 @@ def run_b200(args, workload, out):
             "launch_mode": mode,
             "clocks": clocks,
         }
+        if world == 1 and not args.no_tail:
+            try:
+                line["regulariser_tail"] = time_regulariser_tail(dev, h0, w0, batch, host_views[0])
+            except Exception as e:  # pragma: no cover - the headline must not depend on the extra
+                line["regulariser_tail"] = {"error": f"{type(e).__name__}: {e}"}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(host_views[0], args.cpu_budget, batch)
         out.emit(json.dumps(line))
@@ -501,6 +558,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
+    ap.add_argument("--no-tail", action="store_true", help="skip the extra timing of the fused regulariser tail")
     args = ap.parse_args()
     with quiet_stdout() as out:
         if args.impl == "reference":
