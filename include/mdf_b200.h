@@ -30,6 +30,7 @@
 #define MDF_B200_H_
 
 #include <stddef.h>
+#include <stdint.h>
 
 #ifdef __cplusplus
 extern "C" {
@@ -201,6 +202,25 @@ MDF_API int mdf_hypos_fit_fwd(const float *prob, const float *depth_hypos, int h
 MDF_API int mdf_hypos_generate_fwd(const float *depth, const float *s, const float *depth_range, int curve,
                                    float prob_thresh, int upsample, int B, int H, int W, int ndepths,
                                    float *depth_hypos, mdf_stream_t stream);
+
+/* ---- geometric-consistency filter of the post-processing --------------------
+ * Reference: tools/filter/dynamic_filter_gpu.py -- reproject_with_depth (:184-237), check_geometric_consistency
+ * (:161-182) and the per-view aggregation of filter() (:57-100), one launch per reference view instead of ~60 ATen
+ * kernels + 3 cuSOLVER / cuBLAS calls per (reference, source) pair.  All maps are (H,W) float32 at full resolution;
+ * intrinsics 3x3, extrinsics 4x4 (device memory, row major; src_* hold S of them back to back); src_depths is a HOST
+ * array of S device pointers.  Outputs (each may be NULL): src_bits (S,H,W) uint16 -- bit i-2 = the dynamic mask of
+ * threshold i = 2..10 (dist < i/thre1 px and relative depth difference < i/thre2), i.e. the `masks` list of
+ * check_geometric_consistency; depth_reprojected (S,H,W), zero where the loosest mask fails; depth_averaged (H,W);
+ * geo_mask / photo_mask / final_mask (H,W) uint8 as filter() computes them (photo_mask = confidence > photo_threshold,
+ * all ones when confidence is NULL). */
+#define MDF_MAX_FILTER_VIEWS 32
+MDF_API size_t mdf_geo_filter_workspace_bytes(int S);
+MDF_API int mdf_geo_filter_fwd(const float *ref_depth, const float *ref_intrinsics, const float *ref_extrinsics,
+                               const float *const *src_depths, const float *src_intrinsics, const float *src_extrinsics,
+                               int S, int H, int W, const float *confidence, float photo_threshold, int nconditions,
+                               float thre1, float thre2, uint16_t *src_bits, float *depth_reprojected,
+                               float *depth_averaged, uint8_t *geo_mask, uint8_t *photo_mask, uint8_t *final_mask,
+                               void *workspace, size_t workspace_bytes, mdf_stream_t stream);
 
 /* ---- diagnostics --------------------------------------------------------------------------- */
 /* Sample positions (pixel units of the source map, as grid_sample uses them: base.py:102-119 +

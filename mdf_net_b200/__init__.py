@@ -6,8 +6,8 @@ net/unit/base.py, net/unit/regress.py), backed by hand-written CUDA kernels behi
 calling an op without the built library or with CPU tensors raises.
 """
 from .core import CoreNet
-from .units import (HyposByFit, VectorAggregate, confidence_regress, depth_regression, homo_aggregate_by_variance,
+from .units import (HyposByFit, check_geometric_consistency, geometric_filter, VectorAggregate, confidence_regress, depth_regression, homo_aggregate_by_variance,
                     homo_warping, softmax_regress)
 
 __all__ = ["VectorAggregate", "homo_warping", "homo_aggregate_by_variance", "depth_regression", "confidence_regress",
-           "softmax_regress", "HyposByFit", "CoreNet"]
+           "softmax_regress", "HyposByFit", "CoreNet", "check_geometric_consistency", "geometric_filter"]

@@ -48,6 +48,9 @@ SIGNATURES = {
                                  _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, c_size_t, _P]),
     "mdf_hypos_fit_fwd": (_I, [_P, _P, _I, _P, _I, _I, _I, _I, _I, _P, _P]),
     "mdf_hypos_generate_fwd": (_I, [_P, _P, _P, _I, c_float, _I, _I, _I, _I, _I, _P, _P]),
+    "mdf_geo_filter_workspace_bytes": (c_size_t, [_I]),
+    "mdf_geo_filter_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, c_float, _I, c_float, c_float, _P, _P, _P, _P, _P, _P,
+                                _P, c_size_t, _P]),
     "mdf_debug_time_next_hot_kernel": (_I, [_P, _P]),
     "mdf_debug_sample_positions": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
 }

@@ -14,7 +14,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 INCLUDE = os.path.join(os.path.dirname(PKG), "include")
 LIB_PATH = os.path.join(PKG, "libmdf_b200.so")
-SOURCES = ("mdf_cost_volume.cu", "mdf_head.cu", "mdf_backward.cu", "mdf_hypos.cu", "mdf_prob_head.cu")
+SOURCES = ("mdf_cost_volume.cu", "mdf_head.cu", "mdf_backward.cu", "mdf_hypos.cu", "mdf_prob_head.cu", "mdf_filter.cu")
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

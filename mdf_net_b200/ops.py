@@ -14,6 +14,7 @@ Reference call sites replaced (file:line into the reference checkout):
   softmax_regress_fit  the same + net/unit/depthhypos.py:78-125,169-215 (the curve fit of the next stage's HyposByFit)
   depth_regression  net/unit/regress.py:5-7
   confidence        net/unit/regress.py:9-25 (+ core.py:75-77 nearest upsample)
+  geo_filter        tools/filter/dynamic_filter_gpu.py:57-100,161-237 (geometric-consistency filter, post-processing)
 """
 from __future__ import annotations
 
@@ -25,7 +26,7 @@ from torch import Tensor
 from . import _cabi
 
 __all__ = ["cost_volume", "homo_warp", "variance_volume", "softmax_regress", "softmax_regress_fit", "prob_head", "depth_regression",
-           "confidence", "hypos_fit", "hypos_generate",
+           "confidence", "hypos_fit", "hypos_generate", "geo_filter",
            "launch_count", "reset_launch_count"]
 
 # kernels launched through this module since the last reset (bench.py's `gpu_launches`)
@@ -478,3 +479,46 @@ def _(depth, s, depth_range, curve, prob_thresh, ndepths, upsample):
     B, H, W = depth.shape
     f = 2 if upsample else 1
     return depth.new_empty((B, ndepths, H * f, W * f))
+
+
+# ------------------------------------------------------------- post-processing: geometric-consistency filter
+def geo_filter(ref_depth: Tensor, ref_intrinsics: Tensor, ref_extrinsics: Tensor, src_depths: Sequence[Tensor],
+               src_intrinsics: Tensor, src_extrinsics: Tensor, confidence=None, photo_threshold: float = 0.8,
+               nconditions: int = 5, thre1: float = 4.0, thre2: float = 1300.0, per_source: bool = False) -> dict:
+    """One reference view of tools/filter/dynamic_filter_gpu.py:57-100,161-237 in one launch.  Returns a dict with
+    depth_averaged (H,W) float32 and geo / photo / final (H,W) bool; with per_source=True also bits (S,H,W) int16 (bit
+    i-2 = dynamic mask of threshold i) and depth_reprojected (S,H,W).  (Not a torch.library op: it returns masks of
+    several dtypes and is only ever called eagerly, from the post-processing script.)"""
+    d = _f32c(ref_depth, "ref_depth")
+    if d.dim() != 2:
+        raise RuntimeError(f"mdfnet_b200: ref_depth must be (H,W), got {tuple(d.shape)}")
+    H, W = d.shape
+    srcs = [_f32c(s, "src_depths") for s in src_depths]
+    S = len(srcs)
+    if any(s.shape != d.shape for s in srcs):
+        raise RuntimeError("mdfnet_b200: every source depth map must have the reference map's (H,W)")
+    dev = d.device
+    K, E = _f32c(ref_intrinsics, "ref_intrinsics"), _f32c(ref_extrinsics, "ref_extrinsics")
+    sK = _f32c(src_intrinsics, "src_intrinsics") if S else torch.empty(0, device=dev)
+    sE = _f32c(src_extrinsics, "src_extrinsics") if S else torch.empty(0, device=dev)
+    if K.numel() != 9 or E.numel() != 16 or sK.numel() != 9 * S or sE.numel() != 16 * S:
+        raise RuntimeError("mdfnet_b200: intrinsics must be 3x3 / (S,3,3) and extrinsics 4x4 / (S,4,4)")
+    conf = _f32c(confidence, "confidence") if confidence is not None else None
+    lib = _cabi.lib()
+    out = dict(depth_averaged=torch.empty((H, W), dtype=torch.float32, device=dev),
+               geo=torch.empty((H, W), dtype=torch.bool, device=dev), photo=torch.empty((H, W), dtype=torch.bool, device=dev),
+               final=torch.empty((H, W), dtype=torch.bool, device=dev))
+    if per_source:
+        out["bits"] = torch.empty((S, H, W), dtype=torch.int16, device=dev)
+        out["depth_reprojected"] = torch.empty((S, H, W), dtype=torch.float32, device=dev)
+    ws = _workspace(lib.mdf_geo_filter_workspace_bytes(S), dev)
+    st = lib.mdf_geo_filter_fwd(
+        d.data_ptr(), K.data_ptr(), E.data_ptr(), _cabi.ptr_array([s.data_ptr() for s in srcs]) if S else None,
+        sK.data_ptr() if S else None, sE.data_ptr() if S else None, S, H, W, conf.data_ptr() if conf is not None else None,
+        float(photo_threshold), int(nconditions), float(thre1), float(thre2),
+        out["bits"].data_ptr() if per_source else None, out["depth_reprojected"].data_ptr() if per_source else None,
+        out["depth_averaged"].data_ptr(), out["geo"].data_ptr(), out["photo"].data_ptr(), out["final"].data_ptr(),
+        ws.data_ptr(), ws.numel(), _stream(d))
+    _cabi.check("mdf_geo_filter_fwd", st)
+    _count(2)
+    return out

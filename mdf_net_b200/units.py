@@ -124,3 +124,24 @@ class HyposByFit(nn.Module):
             s = ops.hypos_fit(prob_volume, depth_hypos, depth, self.curve_calss)
             return ops.hypos_generate(depth, s, depth_range, self.curve_calss, float(self.prob_thresh), self.ndepths,
                                       bool(upsample))
+
+
+def check_geometric_consistency(depth_ref: Tensor, intrinsics_ref: Tensor, extrinsics_ref: Tensor, depth_src: Tensor,
+                                intrinsics_src: Tensor, extrinsics_src: Tensor, thre1=4, thre2=1300.0):
+    """tools/filter/dynamic_filter_gpu.py:161-182, same signature and return value: (list of the 9 dynamic masks
+    (1,H,W) bool, the loosest mask, depth_reprojected (1,H,W) zeroed outside it) for one (reference, source) pair."""
+    out = ops.geo_filter(depth_ref, intrinsics_ref, extrinsics_ref, [depth_src], intrinsics_src.reshape(1, 3, 3),
+                         extrinsics_src.reshape(1, 4, 4), None, 0.0, 1, float(thre1), float(thre2), per_source=True)
+    bits = out["bits"]
+    masks = [((bits >> i) & 1).bool() for i in range(9)]
+    return masks, masks[-1], out["depth_reprojected"]
+
+
+def geometric_filter(ref_depth: Tensor, confidence: Tensor, ref_intrinsics: Tensor, ref_extrinsics: Tensor,
+                     src_depths: Sequence[Tensor], src_intrinsics: Tensor, src_extrinsics: Tensor,
+                     photo_threshold: float = 0.8, nconditions: int = 5, thre1=4, thre2=1300.0):
+    """The per-reference-view body of filter() (tools/filter/dynamic_filter_gpu.py:57-100) in one launch: returns
+    (depth_est_averaged (H,W), geo_mask, photo_mask, final_mask (H,W) bool)."""
+    out = ops.geo_filter(ref_depth, ref_intrinsics, ref_extrinsics, list(src_depths), src_intrinsics, src_extrinsics,
+                         confidence, float(photo_threshold), int(nconditions), float(thre1), float(thre2))
+    return out["depth_averaged"], out["geo"], out["photo"], out["final"]

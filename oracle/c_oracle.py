@@ -265,3 +265,27 @@ def hypos_generate(depth, s, depth_range, curve, prob_thresh, ndepths, upsample=
     _check(fn(_ptr(d), _ptr(sv), _ptr(dr), _FIT_MODES[curve], float(prob_thresh), int(bool(upsample)), B, H, W, int(ndepths),
               _ptr(out)), "hypos_generate")
     return out
+
+
+def geo_filter(ref_depth, ref_K, ref_E, src_depths, src_K, src_E, confidence=None, photo_threshold=0.8, nconditions=5,
+               thre1=4.0, thre2=1300.0, prec="f32"):
+    """Geometric-consistency filter of one reference view (tools/filter/dynamic_filter_gpu.py:57-100,161-237).
+    Returns dict(bits (S,H,W) uint16, depth_reprojected (S,H,W), depth_averaged (H,W), geo, photo, final (H,W) uint8)."""
+    d = _arr(ref_depth, prec)
+    H, W = d.shape
+    srcs = [_arr(x, prec) for x in src_depths]
+    S = len(srcs)
+    K, E = _arr(ref_K, prec).reshape(3, 3), _arr(ref_E, prec).reshape(4, 4)
+    sK, sE = _arr(src_K, prec).reshape(S, 3, 3), _arr(src_E, prec).reshape(S, 4, 4)
+    conf = _arr(confidence, prec) if confidence is not None else None
+    out = dict(bits=np.zeros((S, H, W), np.uint16), depth_reprojected=np.zeros((S, H, W), _dt(prec)),
+               depth_averaged=np.zeros((H, W), _dt(prec)), geo=np.zeros((H, W), np.uint8), photo=np.zeros((H, W), np.uint8),
+               final=np.zeros((H, W), np.uint8))
+    fn = getattr(_lib(prec), f"mdf_oracle_geo_filter_{prec}")
+    R = _real(prec)
+    fn.argtypes = [ctypes.c_void_p] * 6 + [ctypes.c_int] * 3 + [ctypes.c_void_p, R, ctypes.c_int, R, R] + [ctypes.c_void_p] * 6
+    _check(fn(_ptr(d), _ptr(K), _ptr(E), _ptr_array(srcs), _ptr(sK), _ptr(sE), S, H, W, _ptr(conf) if conf is not None else None,
+              float(photo_threshold), int(nconditions), float(thre1), float(thre2), _ptr(out["bits"]),
+              _ptr(out["depth_reprojected"]), _ptr(out["depth_averaged"]), _ptr(out["geo"]), _ptr(out["photo"]),
+              _ptr(out["final"])), "geo_filter")
+    return out

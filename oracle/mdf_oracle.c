@@ -574,3 +574,121 @@ int SYM(mdf_oracle_prob_conv)(const REAL *x, const REAL *w, int B, int C, int D,
                 }
     return MDF_OK;
 }
+
+/* ---- geometric-consistency filter (post-processing), tools/filter/dynamic_filter_gpu.py ---------------------------
+ * reproject_with_depth (:184-237), check_geometric_consistency (:161-182), the per-view aggregation of filter() (:57-100)
+ * and bilinear_sampler (tools/filter/data_io.py:117-131: grid_sample, bilinear, zero padding, align_corners=True).
+ * Matrices: A^-1 by LU with partial pivoting (torch.inverse), products as fma chains over K = 3 / 4, every other
+ * elementwise op rounded separately.  cuBLAS / cuSOLVER (the reference runs this on the GPU) do not document their
+ * summation order; the decisions are thresholds on quantities that are smooth in the inputs, so implementations agree
+ * except within float32 noise of a threshold. */
+static int invert3(const REAL *k, REAL *inv)
+{
+    REAL a[16] = {k[0], k[1], k[2], 0, k[3], k[4], k[5], 0, k[6], k[7], k[8], 0, 0, 0, 0, 1}, o[16];
+    if (invert4(a, o) != MDF_OK) return MDF_EINVAL;
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) inv[r * 3 + c] = o[r * 4 + c];
+    return MDF_OK;
+}
+
+static void matmul4(const REAL *a, const REAL *b, REAL *o)
+{
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) {
+            REAL acc = a[r * 4 + 0] * b[0 * 4 + c];
+            for (int k = 1; k < 4; ++k) acc = R_FMA(a[r * 4 + k], b[k * 4 + c], acc);
+            o[r * 4 + c] = acc;
+        }
+}
+
+static inline void mat3v(const REAL *m, REAL x, REAL y, REAL z, REAL *o)
+{
+    for (int r = 0; r < 3; ++r) o[r] = R_FMA(m[r * 3 + 2], z, R_FMA(m[r * 3 + 1], y, m[r * 3 + 0] * x));
+}
+
+static inline void mat34v(const REAL *m, const REAL *v, REAL *o)     /* rows 0-2 of a 4x4 times [v;1] */
+{
+    for (int r = 0; r < 3; ++r) o[r] = R_FMA(m[r * 4 + 3], (REAL)1, R_FMA(m[r * 4 + 2], v[2], R_FMA(m[r * 4 + 1], v[1], m[r * 4 + 0] * v[0])));
+}
+
+/* grid_sample(bilinear, zeros, align_corners=True) of one plane at pixel coordinates (px, py) through
+ * bilinear_sampler's normalise / ATen's unnormalise pair */
+static inline REAL sample_depth_ac(const REAL *img, int H, int W, REAL px, REAL py)
+{
+    const REAL gx = (REAL)2 * px / (REAL)(W - 1) - (REAL)1, gy = (REAL)2 * py / (REAL)(H - 1) - (REAL)1;
+    const REAL ix = ((gx + (REAL)1) / (REAL)2) * (REAL)(W - 1), iy = ((gy + (REAL)1) / (REAL)2) * (REAL)(H - 1);
+    if (!(ix > (REAL)-1 && ix < (REAL)W && iy > (REAL)-1 && iy < (REAL)H)) return 0;       /* also NaN / inf */
+    const REAL fx = R_FLOOR(ix), fy = R_FLOOR(iy);
+    const int x0 = (int)fx, y0 = (int)fy;
+    const REAL ax = (fx + 1) - ix, bx = ix - fx, ay = (fy + 1) - iy, by = iy - fy;
+    const REAL nw = (x0 >= 0 && y0 >= 0 && x0 < W && y0 < H) ? img[(size_t)y0 * W + x0] : 0;
+    const REAL ne = (x0 + 1 >= 0 && y0 >= 0 && x0 + 1 < W && y0 < H) ? img[(size_t)y0 * W + x0 + 1] : 0;
+    const REAL sw = (x0 >= 0 && y0 + 1 >= 0 && x0 < W && y0 + 1 < H) ? img[(size_t)(y0 + 1) * W + x0] : 0;
+    const REAL se = (x0 + 1 >= 0 && y0 + 1 >= 0 && x0 + 1 < W && y0 + 1 < H) ? img[(size_t)(y0 + 1) * W + x0 + 1] : 0;
+    return R_FMA(se, bx * by, R_FMA(sw, ax * by, R_FMA(ne, bx * ay, nw * (ax * ay))));
+}
+
+/* Outputs (any may be NULL): per source view the 9 dynamic masks as bits 0-8 of bits[s][p] (bit i-2 <-> threshold i,
+ * :176-179) and depth_reprojected (zeroed where the last mask fails, :180); fused: depth_est_averaged (:93),
+ * geo / photo / final masks (:86-98). */
+int SYM(mdf_oracle_geo_filter)(const REAL *ref_depth, const REAL *ref_K, const REAL *ref_E, const REAL *const *src_depths,
+                               const REAL *src_K, const REAL *src_E, int S, int H, int W, const REAL *confidence,
+                               REAL photo_threshold, int nconditions, REAL thre1, REAL thre2,
+                               uint16_t *bits, REAL *depth_reprojected, REAL *depth_averaged,
+                               uint8_t *geo_mask, uint8_t *photo_mask, uint8_t *final_mask)
+{
+    if (S < 0 || H < 0 || W < 0) return MDF_EINVAL;
+    const size_t HW = (size_t)H * W;
+    REAL *mats = (REAL *)malloc(sizeof(REAL) * (size_t)(S > 0 ? S : 1) * 64);
+    REAL Ainv[9], Erinv[16];
+    if (!mats) return MDF_EINVAL;
+    if (invert3(ref_K, Ainv) != MDF_OK || invert4(ref_E, Erinv) != MDF_OK) { free(mats); return MDF_EINVAL; }
+    for (int s = 0; s < S; ++s) {
+        REAL *m = mats + 64 * s, Esinv[16];
+        if (invert4(src_E + 16 * s, Esinv) != MDF_OK || invert3(src_K + 9 * s, m + 32) != MDF_OK) { free(mats); return MDF_EINVAL; }
+        matmul4(src_E + 16 * s, Erinv, m);            /* ref camera -> src camera   (:200) */
+        matmul4(ref_E, Esinv, m + 16);                /* src camera -> ref camera   (:221) */
+    }
+#pragma omp parallel for schedule(static)
+    for (long long p = 0; p < (long long)HW; ++p) {
+        const int y = (int)(p / W), x = (int)(p % W);
+        const REAL d = ref_depth[p];
+        int counts[9] = {0};
+        int nvalid = 0;
+        REAL dsum = 0;
+        for (int s = 0; s < S; ++s) {
+            const REAL *m = mats + 64 * s;
+            REAL v[3], q[3], k[3];
+            mat3v(Ainv, (REAL)x * d, (REAL)y * d, (REAL)1 * d, v);             /* :196-198 */
+            mat34v(m, v, q);                                                   /* :200-201 */
+            mat3v(src_K + 9 * s, q[0], q[1], q[2], k);                          /* :203 */
+            const REAL xs = k[0] / k[2], ys = k[1] / k[2];                      /* :204 */
+            const REAL ds = sample_depth_ac(src_depths[s], H, W, xs, ys);      /* :212 */
+            mat3v(m + 32, xs * ds, ys * ds, (REAL)1 * ds, v);                   /* :216-217 */
+            mat34v(m + 16, v, q);                                              /* :219-220 */
+            const REAL drep = q[2];                                            /* :222 */
+            mat3v(ref_K, q[0], q[1], q[2], k);                                 /* :223 */
+            const REAL xr = k[0] / k[2], yr = k[1] / k[2];                      /* :224 */
+            const REAL dx = xr - (REAL)x, dy = yr - (REAL)y;
+            const REAL dist = R_SQRT(dx * dx + dy * dy);                        /* :170 */
+            const REAL rel = (REAL)fabs((double)(drep - d)) / d;                /* :173-174 */
+            unsigned b = 0;
+            for (int i = 2; i < 11; ++i)
+                if (dist < (REAL)i / thre1 && rel < (REAL)i / thre2) { b |= 1u << (i - 2); counts[i - 2]++; }
+            const int last = (b >> 8) & 1;
+            if (bits) bits[(size_t)s * HW + p] = (uint16_t)b;
+            if (depth_reprojected) depth_reprojected[(size_t)s * HW + p] = last ? drep : 0;
+            if (last) { nvalid++; dsum = dsum + drep; }
+        }
+        int geo = 0;
+        for (int i = 2; i < 11; ++i) geo += counts[i - 2] >= i;
+        const int g = S > 0 && geo >= nconditions;
+        const int ph = confidence ? confidence[p] > photo_threshold : 1;
+        if (depth_averaged) depth_averaged[p] = (dsum + d) / (REAL)(nvalid + 1);
+        if (geo_mask) geo_mask[p] = (uint8_t)g;
+        if (photo_mask) photo_mask[p] = (uint8_t)ph;
+        if (final_mask) final_mask[p] = (uint8_t)(g && ph);
+    }
+    free(mats);
+    return MDF_OK;
+}

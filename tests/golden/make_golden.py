@@ -263,6 +263,73 @@ def gen_prob_head():
         save(name, **out)
 
 
+# ------------------------------------------------------------------ geometric-consistency filter (post-processing)
+def filter_scene(S, H, W, seed):
+    """A tilted plane seen by S+1 cameras of the synthetic rig, with smooth multiplicative noise and a few outliers in
+    every depth map, so that every dynamic threshold of the filter gets both outcomes."""
+    rng = np.random.default_rng(seed)
+    K, E = syn.camera_rig(1, S + 1, H, W, seed=seed)
+    K, E = K[0].astype(np.float64), E[0].astype(np.float64)
+    R0, t0 = E[0, :3, :3], E[0, :3, 3]
+    p0 = R0.T @ (np.array([0.0, 0.0, 700.0]) - t0)               # 700 mm in front of the reference camera
+    n = R0.T @ np.array([0.15, -0.1, 1.0]); n /= np.linalg.norm(n)
+    c = float(n @ p0)
+    ys, xs = np.mgrid[0:H, 0:W].astype(np.float64)
+    depths = []
+    for v in range(S + 1):
+        R, t = E[v, :3, :3], E[v, :3, 3]
+        dirs = np.einsum("ij,jhw->ihw", np.linalg.inv(K[v]), np.stack([xs, ys, np.ones_like(xs)]))
+        num = c + n @ (R.T @ t)
+        den = np.einsum("i,ihw->hw", n @ R.T, dirs)
+        d = num / den
+        noise = syn._upsample2x_bilinear(syn._upsample2x_bilinear(rng.standard_normal((1, 1, H // 4, W // 4)).astype(np.float32)))[0, 0]
+        d = d * (1.0 + 0.004 * noise[:H, :W])
+        out = rng.random((H, W)) < 0.04
+        d = np.where(out, d * rng.uniform(0.8, 1.2, (H, W)), d)
+        depths.append(d.astype(np.float32))
+    conf = rng.uniform(0.5, 1.0, (H, W)).astype(np.float32)
+    return K.astype(np.float32), E.astype(np.float32), depths, conf
+
+
+def gen_geo_filter():
+    """tools/filter/dynamic_filter_gpu.py: check_geometric_consistency / reproject_with_depth imported as they are (the
+    module's `plyfile` import, only used by its PLY writer, is stubbed) and run on CPU tensors; the per-view aggregation
+    is lines 78-98 of filter() (which itself needs CUDA, the dataset on disk and plyfile)."""
+    import types
+    sys.modules.setdefault("plyfile", types.SimpleNamespace(PlyData=None, PlyElement=None))
+    sys.path.insert(0, os.path.join(REF, "tools", "filter"))
+    saved = {k: os.environ.get(k) for k in ("CUDA_VISIBLE_DEVICES", "CUDA_DEVICE_ORDER")}
+    import dynamic_filter_gpu as dfg
+    for k, v in saved.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
+    S, H, W = 4, 96, 128
+    K, E, depths, conf = filter_scene(S, H, W, seed=111)
+    thre1, thre2, photo_threshold, nconditions = 4, 1300.0, 0.8, 2
+    ref_depth = T(depths[0])
+    avg_mask, reproj, sums, bits = 0, [], None, []
+    for v in range(1, S + 1):
+        masks, mask, drep = dfg.check_geometric_consistency(ref_depth, T(K[0]), T(E[0]), T(depths[v]), T(K[v]), T(E[v]), thre1, thre2)
+        masks = [m.float() for m in masks]
+        sums = masks if sums is None else [a + b for a, b in zip(sums, masks)]
+        avg_mask = avg_mask + mask
+        reproj.append(drep)
+        bits.append(sum((m[0].numpy().astype(np.uint16) << i) for i, m in enumerate(masks)))
+    geo = 0
+    for i in range(2, 11):
+        geo = geo + (sums[i - 2] >= i)
+    averaged = (sum(reproj) + ref_depth) / (avg_mask + 1)
+    geo = geo >= nconditions
+    photo = T(conf) > photo_threshold
+    final = torch.logical_and(photo, geo)
+    save("geo_filter", intrinsics=K, extrinsics=E, depths=np.stack(depths), confidence=conf,
+         params=np.array([thre1, thre2, photo_threshold, nconditions], np.float64),
+         bits=np.stack(bits), depth_reprojected=np.stack([r[0].numpy() for r in reproj]),
+         depth_averaged=averaged[0].numpy(), geo=geo[0].numpy(), photo=photo.numpy(), final=final[0].numpy())
+
+
 # -------------------------------------------------------------------------------- scale_cam
 def gen_scale():
     K, E = syn.camera_rig(2, 4, 64, 80, seed=51)
@@ -356,6 +423,6 @@ def gen_corenet():
 
 if __name__ == "__main__":
     only = sys.argv[1:]
-    for fn in (gen_warp, gen_vecagg, gen_vecagg_grad, gen_varagg, gen_head, gen_hypos, gen_prob_head, gen_scale, gen_corenet):
+    for fn in (gen_warp, gen_vecagg, gen_vecagg_grad, gen_varagg, gen_head, gen_hypos, gen_prob_head, gen_geo_filter, gen_scale, gen_corenet):
         if not only or fn.__name__ in only:
             fn()
