@@ -69,6 +69,26 @@ def test_argument_validation_without_a_device(libpath):
                                    0, 16, 8, 8, 4, 4, None, None, 0, None) == 0             # empty batch: nothing to do
     assert lib.mdf_cost_volume_fwd(None, 40, None, None, None, 0, None, None, None, None, None, 1e-5, None, None,
                                    1, 16, 8, 8, 4, 4, None, None, 0, None) == -2            # > MDF_MAX_VIEWS
+    P = ctypes.c_void_p(256)
+    # fused tails: curve / s consistency, supported depths, empty inputs
+    assert lib.mdf_softmax_regress_fit_fwd(P, P, 0, 1, 8, 4, 4, None, P, None, 4, 1, 2, 2, 3, P, None) == -2     # unknown curve
+    assert lib.mdf_softmax_regress_fit_fwd(P, P, 0, 1, 8, 4, 4, None, P, None, 4, 1, 2, 2, 1, None, None) == -3  # curve without s
+    assert lib.mdf_softmax_regress_fit_fwd(P, P, 0, 0, 8, 4, 4, None, None, None, 4, 1, 2, 2, 0, None, None) == 0  # empty
+    assert lib.mdf_prob_head_fwd(P, P, P, 0, 1, 8, 10, 4, 4, None, None, P, None, 4, 1, 2, 2, 0, None, None) == -2   # D = 10
+    assert lib.mdf_prob_head_fwd(P, P, P, 0, 1, 65, 8, 4, 4, None, None, P, None, 4, 1, 2, 2, 0, None, None) == -2   # C > 64
+    assert lib.mdf_prob_head_fwd(P, P, P, 0, 1, 8, 8, 4, 4, None, None, None, None, 4, 1, 2, 2, 0, None, None) == -3  # no output
+    assert lib.mdf_prob_head_fwd(P, P, P, 0, 1, 8, 8, 4, 4, None, None, P, None, 4, 1, 2, 2, 2, None, None) == -3     # curve without s
+    assert lib.mdf_prob_head_fwd(None, None, None, 0, 0, 8, 8, 4, 4, None, None, None, None, 4, 1, 2, 2, 0, None, None) == 0
+    # geometric filter
+    assert lib.mdf_geo_filter_workspace_bytes(4) >= (20 + 4 * 64) * 4
+    assert lib.mdf_geo_filter_fwd(P, P, P, None, None, None, 33, 4, 4, None, 0.8, 5, 4.0, 1300.0, None, None, P, None, None, None,
+                                  P, 1 << 20, None) == -2                                   # > MDF_MAX_FILTER_VIEWS
+    assert lib.mdf_geo_filter_fwd(P, P, P, None, None, None, 0, 4, 4, None, 0.8, 5, 4.0, 1300.0, None, None, None, None, None, None,
+                                  P, 1 << 20, None) == -3                                   # no output requested
+    assert lib.mdf_geo_filter_fwd(P, P, P, None, None, None, 0, 4, 4, None, 0.8, 5, 4.0, 1300.0, None, None, P, None, None, None,
+                                  P, 16, None) == -4                                        # workspace too small
+    assert lib.mdf_geo_filter_fwd(None, None, None, None, None, None, 0, 0, 4, None, 0.8, 5, 4.0, 1300.0, None, None, None, None,
+                                  None, None, None, 0, None) == 0                           # empty map
 
 
 def test_cpu_tensors_are_a_hard_error(libpath):
