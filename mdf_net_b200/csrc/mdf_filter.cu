@@ -110,11 +110,20 @@ __device__ __forceinline__ void mat34v(const float* __restrict__ m, const float 
         o[r] = __fadd_rn(__fmaf_rn(m[r * 4 + 2], v[2], __fmaf_rn(m[r * 4 + 1], v[1], __fmul_rn(m[r * 4], v[0]))), m[r * 4 + 3]);
 }
 
-// grid_sample(bilinear, zeros, align_corners=True) through bilinear_sampler's normalisation (data_io.py:121-125)
-__device__ __forceinline__ float sample_depth_ac(const float* __restrict__ img, int H, int W, float px, float py)
+// a / b, correctly rounded: the reciprocal + residual-correction sequence of mdf_common.cuh (what nvcc emits for the
+// fast path of __fdiv_rn) when the operands are in the range where it is exact, the IEEE division otherwise.  `rb` is
+// refine_rcp(b), shared between the divisions by the same b.
+__device__ __forceinline__ float div_shared(float a, float b, float rb)
 {
-    const float gx = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, px), (float)(W - 1)), 1.0f);
-    const float gy = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, py), (float)(H - 1)), 1.0f);
+    return (range_ok(b) && fabsf(a) < 1.0e30f && fabsf(a) > 1.0e-30f) ? div_by(a, b, rb) : __fdiv_rn(a, b);
+}
+
+// grid_sample(bilinear, zeros, align_corners=True) through bilinear_sampler's normalisation (data_io.py:121-125)
+__device__ __forceinline__ float sample_depth_ac(const float* __restrict__ img, int H, int W, float px, float py,
+                                                 float r_wm1, float r_hm1)
+{
+    const float gx = __fsub_rn(div_shared(__fmul_rn(2.0f, px), (float)(W - 1), r_wm1), 1.0f);
+    const float gy = __fsub_rn(div_shared(__fmul_rn(2.0f, py), (float)(H - 1), r_hm1), 1.0f);
     const float ix = __fmul_rn(__fdiv_rn(__fadd_rn(gx, 1.0f), 2.0f), (float)(W - 1));
     const float iy = __fmul_rn(__fdiv_rn(__fadd_rn(gy, 1.0f), 2.0f), (float)(H - 1));
     if (!(ix > -1.0f && ix < (float)W && iy > -1.0f && iy < (float)H)) return 0.0f;
@@ -134,8 +143,10 @@ static __global__ void __launch_bounds__(256)
 geo_filter_kernel(const GeoArgs a)
 {
     extern __shared__ float mat_s[];                 // ref_mats[18] (+pad to 20), then S x kGeoMat
+    __shared__ float thr_s[18];                      // i / thre1, i / thre2 for i = 2..10: the same true divisions, once per CTA
     for (int i = threadIdx.x; i < 20 + a.S * kGeoMat; i += blockDim.x)
         mat_s[i] = i < 18 ? __ldg(a.ref_mats + i) : (i < 20 ? 0.0f : __ldg(a.mats + (i - 20)));
+    if (threadIdx.x < 18) thr_s[threadIdx.x] = __fdiv_rn((float)(threadIdx.x % 9 + 2), threadIdx.x < 9 ? a.thre1 : a.thre2);
     __syncthreads();
     const size_t HW = (size_t)a.H * a.W;
     const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -145,6 +156,7 @@ geo_filter_kernel(const GeoArgs a)
     const float d = __ldg(a.ref_depth + p);
     const float* Krinv = mat_s;
     const float* Kr = mat_s + 9;
+    const float r_wm1 = refine_rcp((float)(a.W - 1)), r_hm1 = refine_rcp((float)(a.H - 1)), r_d = refine_rcp(d);
     uint32_t counts = 0;                             // 9 counters of 3 bits would overflow at S > 7: use two words
     uint32_t counts_hi = 0;
     int nvalid = 0;
@@ -155,20 +167,22 @@ geo_filter_kernel(const GeoArgs a)
         mat3v(Krinv, __fmul_rn(fx, d), __fmul_rn(fy, d), d, v);                       // :196-198
         mat34v(m, v, q);                                                              // :200-201
         mat3v(m + 41, q[0], q[1], q[2], k);                                           // :203
-        const float xs = __fdiv_rn(k[0], k[2]), ys = __fdiv_rn(k[1], k[2]);           // :204
-        const float ds = sample_depth_ac(a.src.p[s], a.H, a.W, xs, ys);              // :212
+        const float rk = refine_rcp(k[2]);
+        const float xs = div_shared(k[0], k[2], rk), ys = div_shared(k[1], k[2], rk);  // :204
+        const float ds = sample_depth_ac(a.src.p[s], a.H, a.W, xs, ys, r_wm1, r_hm1);  // :212
         mat3v(m + 32, __fmul_rn(xs, ds), __fmul_rn(ys, ds), ds, v);                   // :216-217
         mat34v(m + 16, v, q);                                                         // :219-220
         const float drep = q[2];                                                      // :222
         mat3v(Kr, q[0], q[1], q[2], k);                                               // :223
-        const float xr = __fdiv_rn(k[0], k[2]), yr = __fdiv_rn(k[1], k[2]);           // :224
+        const float rk2 = refine_rcp(k[2]);
+        const float xr = div_shared(k[0], k[2], rk2), yr = div_shared(k[1], k[2], rk2); // :224
         const float dx = __fsub_rn(xr, fx), dy = __fsub_rn(yr, fy);
         const float dist = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));   // :170
-        const float rel = __fdiv_rn(fabsf(__fsub_rn(drep, d)), d);                    // :173-174
+        const float rel = div_shared(fabsf(__fsub_rn(drep, d)), d, r_d);              // :173-174
         uint32_t b = 0;
 #pragma unroll
         for (int i = 2; i < 11; ++i)
-            if (dist < __fdiv_rn((float)i, a.thre1) && rel < __fdiv_rn((float)i, a.thre2)) b |= 1u << (i - 2);
+            if (dist < thr_s[i - 2] && rel < thr_s[9 + i - 2]) b |= 1u << (i - 2);
         // per-threshold counters, 6 bits each: thresholds 2-6 in `counts`, 7-10 in `counts_hi`
 #pragma unroll
         for (int i = 0; i < 5; ++i) counts += ((b >> i) & 1u) << (6 * i);
