@@ -140,8 +140,51 @@ cost_volume_direct_kernel(const DirectArgs a)
 }
 
 // ------------------------------------------------------------------------------------------------
-// homo_warping (base.py:85-126): one thread per (b, d, y, x), loop over channels.
+// homo_warping (base.py:85-126): one thread per (b, d, y, x) computes the sample position and the four tap
+// weights once, then walks the C channel planes.  The op is bound by writing the (B,C,D,H,W) volume (354 MB per
+// call at BASELINE configs[1]): the channel loop is unrolled by 8 so that 32 independent tap loads (L1 / L2 hits:
+// neighbouring lanes read neighbouring texels) are in flight per thread and the stores -- 128-byte rows per warp,
+// written once with a streaming hint -- keep HBM busy.  Warps whose 32 footprints are all inside the source map
+// (the common case) take a path without bounds predicates.
 // ------------------------------------------------------------------------------------------------
+template <bool INTERIOR, bool SHARE>
+__device__ __forceinline__ void warp_channels(const float* __restrict__ p, float* __restrict__ o, int C, size_t HW, size_t ostride,
+                                              int W, const Taps& t, bool x0in, bool x1in, bool y0in, bool y1in, bool live)
+{
+    // SHARE (all 32 footprints inside the map, lane i+1's cell is the right-hand neighbour of lane i's): the east
+    // taps of a lane are the west taps of the next lane -- two loads + two shuffles per channel instead of four
+    // loads (the L1 data pipe is the co-limit of this kernel); lane 31 loads its own east taps.
+    constexpr int U = 8;
+    const bool last = (threadIdx.x & 31) == 31;
+    for (int c0 = 0; c0 < C; c0 += U) {
+        float nw[U], ne[U], sw[U], se[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const bool on = c0 + u < C;
+            const float* q = p + (size_t)(c0 + u) * HW;
+            nw[u] = (on && (INTERIOR || (x0in && y0in))) ? __ldg(q) : 0.0f;
+            sw[u] = (on && (INTERIOR || (x0in && y1in))) ? __ldg(q + W) : 0.0f;
+            if (SHARE) {
+                ne[u] = (on && last) ? __ldg(q + 1) : 0.0f;
+                se[u] = (on && last) ? __ldg(q + W + 1) : 0.0f;
+            } else {
+                ne[u] = (on && (INTERIOR || (x1in && y0in))) ? __ldg(q + 1) : 0.0f;
+                se[u] = (on && (INTERIOR || (x1in && y1in))) ? __ldg(q + W + 1) : 0.0f;
+            }
+        }
+        if (SHARE) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const float a = __shfl_down_sync(0xffffffffu, nw[u], 1), b = __shfl_down_sync(0xffffffffu, sw[u], 1);
+                if (!last) { ne[u] = a; se[u] = b; }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (live && c0 + u < C) __stcs(o + (size_t)(c0 + u) * ostride, blend4(nw[u], ne[u], sw[u], se[u], t));
+    }
+}
+
 __global__ void __launch_bounds__(256)
 homo_warp_kernel(const float* __restrict__ src, const float* __restrict__ rt_all, const float* __restrict__ hypos,
                  int per_pixel, int B, int C, int D, int H, int W, float* __restrict__ out)
@@ -149,19 +192,34 @@ homo_warp_kernel(const float* __restrict__ src, const float* __restrict__ rt_all
     const size_t HW = (size_t)H * W;
     const size_t total = (size_t)B * D * HW;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int x = (int)(idx % W);
-    const int y = (int)((idx / W) % H);
-    const int d = (int)((idx / HW) % D);
-    const int b = (int)(idx / (HW * D));
+    const bool live = idx < total;
+    const size_t i = live ? idx : total - 1;          // idle lanes of the last warp shadow a real sample (the votes below are warp wide)
+    const int x = (int)(i % W);
+    const int y = (int)((i / W) % H);
+    const int d = (int)((i / HW) % D);
+    const int b = (int)(i / (HW * D));
     const GridNorm gn = make_grid_norm(H, W);
     const float depth = per_pixel ? __ldg(hypos + ((size_t)b * D + d) * HW + (size_t)y * W + x) : __ldg(hypos + (size_t)b * D + d);
     const float* rt = rt_all + (size_t)b * 12;
     float ix, iy;
     sample_position(rot_xyz(rt, (float)x, (float)y), rt, depth, gn, ix, iy);
     const Taps t = make_taps(ix, iy, gn);
-    for (int c = 0; c < C; ++c)
-        out[((((size_t)b * C + c) * D + d) * H + y) * W + x] = sample_plane(src + ((size_t)b * C + c) * HW, H, W, t);
+    const bool x0in = t.valid && (unsigned)t.x0 < (unsigned)W, x1in = t.valid && (unsigned)(t.x0 + 1) < (unsigned)W;
+    const bool y0in = (unsigned)t.y0 < (unsigned)H, y1in = (unsigned)(t.y0 + 1) < (unsigned)H;
+    const bool interior = x0in && x1in && y0in && y1in;
+    const float* p = src + (size_t)b * C * HW + (ptrdiff_t)t.y0 * W + t.x0;
+    float* o = out + (((size_t)b * C * D + d) * H + y) * W + x;
+    const size_t ostride = (size_t)D * HW;
+    // is lane i+1's cell the right-hand neighbour of mine?  (lane 31 has no successor in the warp)
+    const int nx0 = __shfl_down_sync(0xffffffffu, t.x0, 1), ny0 = __shfl_down_sync(0xffffffffu, t.y0, 1);
+    const bool chained = (threadIdx.x & 31) == 31 || (nx0 == t.x0 + 1 && ny0 == t.y0);
+    if (__all_sync(0xffffffffu, interior)) {
+        // (sharing the east taps between neighbouring lanes by shuffle -- the SHARE variant -- measured slower: 192 vs 160 us)
+        (void)chained;
+        warp_channels<true, false>(p, o, C, HW, ostride, W, t, true, true, true, true, live);
+    } else {
+        warp_channels<false, false>(p, o, C, HW, ostride, W, t, x0in, x1in, y0in, y1in, live);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -177,9 +235,50 @@ struct VarArgs {
     int per_pixel, V, B, C, D, H, W;
 };
 
+// Footprint of one (sample, source view): base pointer of channel 0 (clamped into the map), weights, tap validity.
+struct VarTap {
+    const float* p;
+    Taps t;
+    bool nw, ne, sw, se;
+};
+
+__device__ __forceinline__ VarTap var_tap(const VarArgs& a, int v, int b, int x, int y, float depth, const GridNorm& gn)
+{
+    const size_t HW = (size_t)a.H * a.W;
+    const float* rt = a.rt + ((size_t)v * a.B + b) * 12;
+    float ix, iy;
+    sample_position(rot_xyz(rt, (float)x, (float)y), rt, depth, gn, ix, iy);
+    VarTap f;
+    f.t = make_taps(ix, iy, gn);
+    const bool x0in = f.t.valid && (unsigned)f.t.x0 < (unsigned)a.W, x1in = f.t.valid && (unsigned)(f.t.x0 + 1) < (unsigned)a.W;
+    const bool y0in = (unsigned)f.t.y0 < (unsigned)a.H, y1in = (unsigned)(f.t.y0 + 1) < (unsigned)a.H;
+    f.nw = x0in && y0in; f.ne = x1in && y0in; f.sw = x0in && y1in; f.se = x1in && y1in;
+    f.p = a.fea.p[v + 1] + (size_t)b * a.C * HW + (ptrdiff_t)f.t.y0 * a.W + f.t.x0;
+    return f;
+}
+
+// U consecutive channels of one footprint: 4*U independent loads in flight
+template <int U>
+__device__ __forceinline__ void var_sample(const VarTap& f, int c0, int C, size_t HW, int W, float (&out)[U])
+{
+    float nw[U], ne[U], sw[U], se[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const bool live = c0 + u < C;
+        const float* q = f.p + (size_t)(c0 + u) * HW;
+        nw[u] = (live && f.nw) ? __ldg(q) : 0.0f;
+        ne[u] = (live && f.ne) ? __ldg(q + 1) : 0.0f;
+        sw[u] = (live && f.sw) ? __ldg(q + W) : 0.0f;
+        se[u] = (live && f.se) ? __ldg(q + W + 1) : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) out[u] = blend4(nw[u], ne[u], sw[u], se[u], f.t);
+}
+
 __global__ void __launch_bounds__(256)
 variance_volume_kernel(const VarArgs a)
 {
+    constexpr int U = 8;
     const size_t HW = (size_t)a.H * a.W;
     const size_t total = (size_t)a.B * a.D * HW;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -191,37 +290,61 @@ variance_volume_kernel(const VarArgs a)
     const GridNorm gn = make_grid_norm(a.H, a.W);
     const float depth = a.per_pixel ? __ldg(a.hypos + ((size_t)b * a.D + d) * HW + (size_t)y * a.W + x)
                                     : __ldg(a.hypos + (size_t)b * a.D + d);
+    // softmax statistics of every warped view over its C channels (homoaggregate.py:60): max, then the sum of
+    // exp(v - max) in channel order; the position and the footprint are computed once per view and pass
     float vmax[kMaxSrcViews], vinv[kMaxSrcViews];
     for (int v = 0; v < a.V; ++v) {
-        const float* rt = a.rt + ((size_t)v * a.B + b) * 12;
-        float ix, iy;
-        sample_position(rot_xyz(rt, (float)x, (float)y), rt, depth, gn, ix, iy);
-        const Taps t = make_taps(ix, iy, gn);
-        const float* src = a.fea.p[v + 1] + (size_t)b * a.C * HW;
+        const VarTap f = var_tap(a, v, b, x, y, depth, gn);
         float m = -INFINITY;
-        for (int c = 0; c < a.C; ++c) m = fmaxf(m, sample_plane(src + c * HW, a.H, a.W, t));
+        for (int c0 = 0; c0 < a.C; c0 += U) {
+            float val[U];
+            var_sample<U>(f, c0, a.C, HW, a.W, val);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (c0 + u < a.C) m = fmaxf(m, val[u]);
+        }
         float s = 0.0f;
-        for (int c = 0; c < a.C; ++c) s += expf(sample_plane(src + c * HW, a.H, a.W, t) - m);
+        for (int c0 = 0; c0 < a.C; c0 += U) {
+            float val[U];
+            var_sample<U>(f, c0, a.C, HW, a.W, val);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (c0 + u < a.C) s += expf(val[u] - m);
+        }
         vmax[v] = m;
         vinv[v] = s;
     }
     const float nviews = (float)(a.V + 1);
     const float* ref = a.fea.p[0] + (size_t)b * a.C * HW + (size_t)y * a.W + x;
-    for (int c = 0; c < a.C; ++c) {
-        const float rv = __ldg(ref + c * HW);
-        float s1 = rv, s2 = rv * rv;
-        for (int v = 0; v < a.V; ++v) {
-            const float* rt = a.rt + ((size_t)v * a.B + b) * 12;
-            float ix, iy;
-            sample_position(rot_xyz(rt, (float)x, (float)y), rt, depth, gn, ix, iy);
-            const Taps t = make_taps(ix, iy, gn);
-            const float* src = a.fea.p[v + 1] + (size_t)b * a.C * HW;
-            const float p = expf(sample_plane(src + c * HW, a.H, a.W, t) - vmax[v]) / vinv[v];
-            s1 += p;
-            s2 = fmaf(p, p, s2);
+    float* o = a.out + (((size_t)b * a.C * a.D + d) * a.H + y) * a.W + x;
+    const size_t ostride = (size_t)a.D * HW;
+    // U channels at a time: sum and sum of squares over the views, in view order (homoaggregate.py:56-67)
+    for (int c0 = 0; c0 < a.C; c0 += U) {
+        float s1[U], s2[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const float rv = c0 + u < a.C ? __ldg(ref + (size_t)(c0 + u) * HW) : 0.0f;
+            s1[u] = rv;
+            s2[u] = rv * rv;
         }
-        const float mean = s1 / nviews;
-        a.out[((((size_t)b * a.C + c) * a.D + d) * a.H + y) * a.W + x] = s2 / nviews - mean * mean;
+        for (int v = 0; v < a.V; ++v) {
+            const VarTap f = var_tap(a, v, b, x, y, depth, gn);
+            float val[U];
+            var_sample<U>(f, c0, a.C, HW, a.W, val);
+            const float m = vmax[v], inv = vinv[v];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const float pr = expf(val[u] - m) / inv;
+                s1[u] += pr;
+                s2[u] = fmaf(pr, pr, s2[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (c0 + u >= a.C) break;
+            const float mean = s1[u] / nviews;
+            __stcs(o + (size_t)(c0 + u) * ostride, s2[u] / nviews - mean * mean);
+        }
     }
 }
 
