@@ -156,21 +156,46 @@ __device__ __forceinline__ void warp_channels(const float* __restrict__ p, float
     // loads (the L1 data pipe is the co-limit of this kernel); lane 31 loads its own east taps.
     constexpr int U = 8;
     const bool last = (threadIdx.x & 31) == 31;
-    for (int c0 = 0; c0 < C; c0 += U) {
+    // running pointers (north row, south row, output), advanced by one plane per channel: the loads use immediate
+    // offsets and the loop carries no 64-bit multiplications (the first version spent more issue slots on address
+    // arithmetic than on the taps)
+    const float* __restrict__ pn = p;
+    const float* __restrict__ ps = p + W;
+    float* __restrict__ po = o;
+    int c0 = 0;
+    if (INTERIOR && !SHARE) {
+        // full chunks of U channels, no predicate anywhere: 4*U loads, then U blends and stores
+        for (; c0 + U <= C; c0 += U) {
+            float nw[U], ne[U], sw[U], se[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                nw[u] = __ldg(pn); ne[u] = __ldg(pn + 1); sw[u] = __ldg(ps); se[u] = __ldg(ps + 1);
+                pn += HW;
+                ps += HW;
+            }
+            if (live) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) __stcs(po + (size_t)u * ostride, blend4(nw[u], ne[u], sw[u], se[u], t));
+            }
+            po += (size_t)U * ostride;
+        }
+    }
+    for (; c0 < C; c0 += U) {
         float nw[U], ne[U], sw[U], se[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const bool on = c0 + u < C;
-            const float* q = p + (size_t)(c0 + u) * HW;
-            nw[u] = (on && (INTERIOR || (x0in && y0in))) ? __ldg(q) : 0.0f;
-            sw[u] = (on && (INTERIOR || (x0in && y1in))) ? __ldg(q + W) : 0.0f;
+            nw[u] = (on && (INTERIOR || (x0in && y0in))) ? __ldg(pn) : 0.0f;
+            sw[u] = (on && (INTERIOR || (x0in && y1in))) ? __ldg(ps) : 0.0f;
             if (SHARE) {
-                ne[u] = (on && last) ? __ldg(q + 1) : 0.0f;
-                se[u] = (on && last) ? __ldg(q + W + 1) : 0.0f;
+                ne[u] = (on && last) ? __ldg(pn + 1) : 0.0f;
+                se[u] = (on && last) ? __ldg(ps + 1) : 0.0f;
             } else {
-                ne[u] = (on && (INTERIOR || (x1in && y0in))) ? __ldg(q + 1) : 0.0f;
-                se[u] = (on && (INTERIOR || (x1in && y1in))) ? __ldg(q + W + 1) : 0.0f;
+                ne[u] = (on && (INTERIOR || (x1in && y0in))) ? __ldg(pn + 1) : 0.0f;
+                se[u] = (on && (INTERIOR || (x1in && y1in))) ? __ldg(ps + 1) : 0.0f;
             }
+            pn += HW;
+            ps += HW;
         }
         if (SHARE) {
 #pragma unroll
@@ -180,8 +205,10 @@ __device__ __forceinline__ void warp_channels(const float* __restrict__ p, float
             }
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u)
-            if (live && c0 + u < C) __stcs(o + (size_t)(c0 + u) * ostride, blend4(nw[u], ne[u], sw[u], se[u], t));
+        for (int u = 0; u < U; ++u) {
+            if (live && c0 + u < C) __stcs(po, blend4(nw[u], ne[u], sw[u], se[u], t));
+            po += ostride;
+        }
     }
 }
 
