@@ -349,21 +349,38 @@ def run_b200(args, workload, out):
 
     copy_stream = torch.cuda.Stream(device=dev)
 
-    def stage_in(pview):
+    def pack(pview):
+        """All host tensors of one view in ONE pinned arena (256-byte aligned slots): the step's inputs then cross PCIe
+        as a single transfer instead of 36 (15 of them 64-byte matrices whose copies cost latency, not bandwidth)."""
+        slots, off = [], 0
+        def add(t):
+            nonlocal off
+            slots.append((off, t))
+            off += (t.numel() + 63) // 64 * 64
+            return len(slots) - 1
+        layout = [dict(G=st["G"], features=[add(f) for f in st["features"]], ref_proj=add(st["ref_proj"]),
+                       src_projs=[add(q) for q in st["src_projs"]], hypos=add(st["hypos"]), logits=add(st["logits"]),
+                       w=st["w"], eps=st["eps"]) for st in pview]
+        arena = torch.empty(off, dtype=torch.float32).pin_memory()
+        for o, t in slots:
+            arena[o:o + t.numel()].copy_(t.reshape(-1))
+        return arena, [(o, tuple(t.shape)) for o, t in slots], layout
+
+    packed = [pack(v) for v in pin_views] if not args.no_e2e else None
+
+    def stage_in(k):
         """H2D of everything one step reads, on the copy stream (overlaps the previous step's kernels)."""
+        arena, slots, layout = packed[k]
         compute = torch.cuda.current_stream()
-        view = []
         with torch.cuda.stream(copy_stream):
-            for st in pview:
-                def nb(t):
-                    d = t.to(dev, non_blocking=True)
-                    d.record_stream(compute)
-                    return d
-                view.append(dict(G=st["G"], features=[nb(f) for f in st["features"]], ref_proj=nb(st["ref_proj"]),
-                                 src_projs=[nb(q) for q in st["src_projs"]], hypos=nb(st["hypos"]), logits=nb(st["logits"]),
-                                 w=st["w"], eps=st["eps"]))
+            d = arena.to(dev, non_blocking=True)
+            d.record_stream(compute)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
+        get = lambda i: d[slots[i][0]:slots[i][0] + int(np.prod(slots[i][1]))].view(slots[i][1])
+        view = [dict(G=st["G"], features=[get(i) for i in st["features"]], ref_proj=get(st["ref_proj"]),
+                     src_projs=[get(i) for i in st["src_projs"]], hypos=get(st["hypos"]), logits=get(st["logits"]),
+                     w=st["w"], eps=st["eps"]) for st in layout]
         return view, ev
 
     H2s, W2s = syn.stage_shapes(h0, w0)[2]
@@ -373,11 +390,11 @@ def run_b200(args, workload, out):
     def e2e_loop(n):
         """Public-API calls with HOST (pinned) inputs: per step H2D of features / projections / hypotheses /
         logits and D2H of the depth maps + confidence; the copies of step i+1 overlap the kernels of step i."""
-        nxt = stage_in(pin_views[0])
+        nxt = stage_in(0)
         for i in range(n):
             view, ev = nxt
             if i + 1 < n:
-                nxt = stage_in(pin_views[(i + 1) % 2])
+                nxt = stage_in((i + 1) % 2)
             torch.cuda.current_stream().wait_event(ev)
             depths, conf = hot_path(view)
             for dst, src in zip(host_out[i % 2], depths + [conf]):
@@ -487,6 +504,8 @@ def run_b200(args, workload, out):
         views = world * args.steps * batch
         h2d = sum(sum(f.size for f in st["features"]) + st["ref_proj"].size + sum(q.size for q in st["src_projs"])
                   + st["hypos"].size + st["logits"].size for st in host_views[0]) * 4
+        if packed is not None:
+            h2d = packed[0][0].numel() * 4          # what actually crosses PCIe per step: the arena incl. its alignment padding
         H2, W2 = syn.stage_shapes(h0, w0)[2]
         d2h = 4 * batch * (sum(h * w for h, w in syn.stage_shapes(h0, w0)) + 4 * H2 * W2)
         achieved = sum(cv_bytes) / 1e9 / (sum(cv_ms) / 1e3)
