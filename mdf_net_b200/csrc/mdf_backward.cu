@@ -12,9 +12,10 @@
 //   sim_vg = 0.5 + q_g (p_vg - 0.5)      z_v = sum_g cw_g sim_vg     h_v = a_v z_v + b_v   (BatchNorm)
 //   w_v = sigmoid(fcw*relu(h_v) + fcb)   out_g = sum_v w_v sim_vg / sum_v w_v
 //
-// These kernels are the simple, correct version of the training path: one thread per (b,d,y,x), taps through
-// L1/L2 straight from the planar-float4 maps the prep kernel writes.  (The eval-mode forward is the tuned
-// TMA-staged kernel of mdf_staged.cuh.)  Feature gradients are scattered with 128-bit vector reductions
+// The train-mode FORWARD runs the tuned TMA-staged kernel of mdf_staged.cuh twice: in its statistics mode (sum z, sum z^2
+// per source view) and, after the per-view BatchNorm folds (bn_fold_kernel), in its per-view-fold mode.  The BACKWARD
+// kernels below are the simple, correct version: one thread per (b,d,y,x), taps through L1/L2 straight from the
+// planar-float4 maps the prep kernel writes.  Feature gradients are scattered with 128-bit vector reductions
 // (red.global.add.v4.f32) into a difference-gradient map dS4 -- half the atomics of scattering into both
 // channels of a pair -- and a finishing kernel turns dS4 / dQ4 into NCHW feature gradients.
 #include <cuda_runtime.h>
@@ -140,43 +141,31 @@ __device__ __forceinline__ void block_accumulate(double (&val)[N], double* __res
     __syncthreads();
 }
 
-// ---- forward phase 1 (train): sum z_v, sum z_v^2 per view ------------------------------------------
-template <int G>
-__global__ void __launch_bounds__(256)
-train_stats_kernel(const TrainArgs a, double* __restrict__ stats /* [V][2] */)
-{
-    const Elem e = decode(a);
-    const GridNorm gn = make_grid_norm(a.H, a.W);
-    const size_t HW = (size_t)a.H * a.W;
-    float4 q4[G / 4];
-#pragma unroll
-    for (int j = 0; j < G / 4; ++j) q4[j] = __ldg(a.Q4 + ((size_t)e.b * (G / 4) + j) * HW + e.pix);
-    for (int v = 0; v < a.V; ++v) {
-        double s[2] = {0.0, 0.0};
-        if (e.ok) {
-            const float z = view_z<G>(a, e, v, taps_of(a, e, v, gn), q4, nullptr, nullptr);
-            s[0] = z; s[1] = (double)z * z;
-        }
-        block_accumulate<2>(s, stats + 2 * v);
-    }
-}
-
 // ---- BatchNorm constants per view (1 thread) ---------------------------------------------------------
 // training: batch statistics from `stats`; else the running statistics.  Also publishes the batch mean and
 // the unbiased variance (momentum update of the running statistics happens on the host side of the ABI).
+// `stats` come from the staged kernel's statistics pass: sums of ITS z = sum_g cw_g q_g (p_g - 0.5) = true z - hcw with
+// hcw = 0.5 * sum_g cw_g (the variance does not see the shift, the mean gets it back here).  `vparams` [V][4] are the
+// folds that kernel's forward pass uses: alpha_v, beta_v + alpha_v * hcw, the weight of an out-of-image sample.
 __global__ void bn_fold_kernel(const double* __restrict__ stats, double count, int V, int training,
                                const float* __restrict__ bn_w, const float* __restrict__ bn_b,
                                const float* __restrict__ bn_mean, const float* __restrict__ bn_var, float eps,
                                const float* __restrict__ fc_w, const float* __restrict__ fc_b,
-                               float* __restrict__ bnv, float* __restrict__ fc, float* __restrict__ batch_stats)
+                               const float* __restrict__ cw, int G,
+                               float* __restrict__ bnv, float* __restrict__ fc, float* __restrict__ vparams,
+                               float* __restrict__ batch_stats)
 {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     fc[0] = fc_w[0]; fc[1] = fc_b[0];
+    double hcw = 0.0;
+    for (int g = 0; g < G; ++g) hcw += (double)cw[g];
+    hcw *= 0.5;
     for (int v = 0; v < V; ++v) {
         double mean = bn_mean[0], var = bn_var[0];
         if (training) {
-            mean = stats[2 * v] / count;
-            var = stats[2 * v + 1] / count - mean * mean;
+            const double mk = stats[2 * v] / count;
+            mean = mk + hcw;
+            var = stats[2 * v + 1] / count - mk * mk;
             if (var < 0.0) var = 0.0;
             if (batch_stats) {
                 batch_stats[2 * v] = (float)mean;
@@ -189,48 +178,13 @@ __global__ void bn_fold_kernel(const double* __restrict__ stats, double count, i
         bnv[4 * v + 1] = (float)((double)bn_b[0] - mean * alpha);
         bnv[4 * v + 2] = (float)invstd;
         bnv[4 * v + 3] = (float)mean;
+        const float betap = (float)((double)bnv[4 * v + 1] + alpha * hcw);
+        const float hv = fmaf(fmaxf(betap, 0.0f), fc_w[0], fc_b[0]);
+        vparams[4 * v + 0] = (float)alpha;
+        vparams[4 * v + 1] = betap;
+        vparams[4 * v + 2] = 1.0f / (1.0f + expf(-hv));
+        vparams[4 * v + 3] = 0.0f;
     }
-}
-
-// ---- forward phase 2: the cost volume with per-view BatchNorm constants -------------------------------
-template <int G>
-__global__ void __launch_bounds__(256)
-train_forward_kernel(const TrainArgs a, float* __restrict__ out)
-{
-    constexpr int J = G / 4;
-    const Elem e = decode(a);
-    if (!e.ok) return;
-    const GridNorm gn = make_grid_norm(a.H, a.W);
-    const size_t HW = (size_t)a.H * a.W;
-    float4 q4[J];
-#pragma unroll
-    for (int j = 0; j < J; ++j) q4[j] = __ldg(a.Q4 + ((size_t)e.b * J + j) * HW + e.pix);
-    float acc[G];
-#pragma unroll
-    for (int g = 0; g < G; ++g) acc[g] = 0.0f;
-    float wsum = 0.0f;
-    for (int v = 0; v < a.V; ++v) {
-        const Taps t = taps_of(a, e, v, gn);
-        const float4* Sv = a.S4 + ((size_t)v * a.B + e.b) * J * HW;
-        float sim[G];
-        float z = 0.0f;
-#pragma unroll
-        for (int j = 0; j < J; ++j) {
-            float4 tt = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (t.valid) tt = sample4(Sv + (size_t)j * HW, a.H, a.W, t);
-            sim[4 * j + 0] = fmaf(q4[j].x, sigm2(tt.x) - 0.5f, 0.5f); sim[4 * j + 1] = fmaf(q4[j].y, sigm2(tt.y) - 0.5f, 0.5f);
-            sim[4 * j + 2] = fmaf(q4[j].z, sigm2(tt.z) - 0.5f, 0.5f); sim[4 * j + 3] = fmaf(q4[j].w, sigm2(tt.w) - 0.5f, 0.5f);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) z = fmaf(__ldg(a.cw + 4 * j + k), sim[4 * j + k], z);
-        }
-        const float w = view_weight(a, v, z, nullptr);
-        wsum += w;
-#pragma unroll
-        for (int g = 0; g < G; ++g) acc[g] = fmaf(w, sim[g], acc[g]);
-    }
-    float* op = out + (((size_t)e.b * G) * a.D + e.d) * HW + e.pix;
-#pragma unroll
-    for (int g = 0; g < G; ++g) op[(size_t)g * a.D * HW] = acc[g] / wsum;
 }
 
 // ---- backward ----------------------------------------------------------------------------------------
@@ -438,7 +392,7 @@ __global__ void gparam_to_float_kernel(const double* __restrict__ src, float* __
 // workspace
 // ------------------------------------------------------------------------------------------------
 struct TrainWorkspace {
-    size_t rt, dwp, q, s, cq, bnv, fc, stats, bsum, gparam, dq, ds, total;
+    size_t rt, dwp, q, s, cq, bnv, vparams, fc, stats, bsum, gparam, dq, ds, total;
 };
 
 static TrainWorkspace make_train_workspace(int B, int N, int G, int H, int W)
@@ -453,6 +407,7 @@ static TrainWorkspace make_train_workspace(int B, int N, int G, int H, int W)
     w.s = take(V * plane);
     w.cq = take(plane);
     w.bnv = take(kMaxSrcViews * 4 * sizeof(float));
+    w.vparams = take(kMaxSrcViews * 4 * sizeof(float));
     w.fc = take(2 * sizeof(float));
     w.stats = take(kMaxSrcViews * 2 * sizeof(double));      // stats | bsum | gparam are contiguous: one memset
     w.bsum = take(kMaxSrcViews * 2 * sizeof(double));
@@ -494,6 +449,27 @@ static int validate(const TrainCall& c, const void* out, void* workspace, size_t
     return MDF_OK;
 }
 
+// arguments of the TMA-staged kernel (mdf_staged.cuh) over this call's workspace
+static StagedArgs staged_args(const TrainCall& c, uint8_t* wsb, const TrainWorkspace& ws, float* out)
+{
+    StagedArgs a;
+    a.rt = reinterpret_cast<const float*>(wsb + ws.rt); a.dwp = reinterpret_cast<const float*>(wsb + ws.dwp);
+    a.vparams = reinterpret_cast<const float*>(wsb + ws.vparams); a.stats = reinterpret_cast<double*>(wsb + ws.stats);
+    a.hypos = c.hypos; a.out = out;
+    a.per_pixel = c.per_pixel; a.V = c.N - 1; a.B = c.B; a.D = c.D; a.H = c.H; a.W = c.W;
+    a.gn = make_grid_norm(c.H, c.W);
+    a.tiles_x = a.tiles_y = a.slabs = 0;
+    return a;
+}
+
+static StagedBuffers staged_buffers(uint8_t* wsb, const TrainWorkspace& ws)
+{
+    StagedBuffers b;
+    b.S4 = reinterpret_cast<const float*>(wsb + ws.s); b.Q4 = reinterpret_cast<const float*>(wsb + ws.q);
+    b.CQ4 = reinterpret_cast<const float*>(wsb + ws.cq);
+    return b;
+}
+
 // prep (S4, Q4, rt) + BatchNorm constants; returns the TrainArgs for the sweeps
 template <int G>
 static int prepare(const TrainCall& c, uint8_t* wsb, const TrainWorkspace& ws, float* batch_stats, cudaStream_t stream, TrainArgs* out)
@@ -520,16 +496,15 @@ static int prepare(const TrainCall& c, uint8_t* wsb, const TrainWorkspace& ws, f
     a.bnv = reinterpret_cast<float*>(wsb + ws.bnv); a.fc = reinterpret_cast<float*>(wsb + ws.fc);
     a.hypos = c.hypos; a.per_pixel = c.per_pixel; a.V = V; a.B = c.B; a.D = c.D; a.H = c.H; a.W = c.W;
     const size_t total = (size_t)c.B * c.D * c.H * c.W;
-    const unsigned blocks = (unsigned)((total + 255) / 256);
     double* stats = reinterpret_cast<double*>(wsb + ws.stats);
     if (c.training) {
-        train_stats_kernel<G><<<blocks, 256, 0, stream>>>(a, stats);
-        st = launch_status();
+        // batch statistics of z per source view: the TMA-staged gather in its statistics mode (mdf_staged.cuh, MODE 1)
+        st = launch_staged_train<1>(G, staged_args(c, wsb, ws, nullptr), staged_buffers(wsb, ws), stream);
         if (st != MDF_OK) return st;
     }
     bn_fold_kernel<<<1, 32, 0, stream>>>(stats, (double)total, V, c.training, c.bn_w, c.bn_b, c.bn_mean, c.bn_var, c.bn_eps,
-                                         c.fc_w, c.fc_b, reinterpret_cast<float*>(wsb + ws.bnv), reinterpret_cast<float*>(wsb + ws.fc),
-                                         batch_stats);
+                                         c.fc_w, c.fc_b, c.conv_w, G, reinterpret_cast<float*>(wsb + ws.bnv),
+                                         reinterpret_cast<float*>(wsb + ws.fc), reinterpret_cast<float*>(wsb + ws.vparams), batch_stats);
     st = launch_status();
     if (st != MDF_OK) return st;
     *out = a;
@@ -542,9 +517,8 @@ static int train_fwd(const TrainCall& c, float* cost_volume, float* batch_stats,
     TrainArgs a;
     int st = prepare<G>(c, wsb, ws, batch_stats, stream, &a);
     if (st != MDF_OK) return st;
-    const size_t total = (size_t)c.B * c.D * c.H * c.W;
-    train_forward_kernel<G><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(a, cost_volume);
-    return launch_status();
+    // the forward itself: the TMA-staged kernel with per-view BatchNorm folds (MODE 2)
+    return launch_staged_train<2>(G, staged_args(c, wsb, ws, cost_volume), staged_buffers(wsb, ws), stream);
 }
 
 template <int G>

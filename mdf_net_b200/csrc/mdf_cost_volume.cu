@@ -517,7 +517,7 @@ int mdf_cost_volume_fwd_ex(const float* const* features, int N, const float* ref
         if (st != MDF_OK) return st;
     }
     StagedArgs a;
-    a.rt = rt; a.dwp = dwp; a.hypos = depth_hypos; a.out = cost_volume;
+    a.rt = rt; a.dwp = dwp; a.hypos = depth_hypos; a.out = cost_volume; a.vparams = nullptr; a.stats = nullptr;
     a.per_pixel = hypos_per_pixel; a.V = V; a.B = B; a.D = D; a.H = H; a.W = W;
     a.gn = make_grid_norm(H, W);
     a.tiles_x = a.tiles_y = a.slabs = 0;

@@ -192,6 +192,8 @@ struct StagedCfg {
 struct StagedArgs {
     const float* rt;      // [V][B][12]
     const float* dwp;     // folded depth_weight
+    const float* vparams; // MODE 2: [V][4] per-view BatchNorm fold alpha_v, beta'_v, weight of an out-of-image sample, -
+    double* stats;        // MODE 1: [V][2] sum z, sum z^2 of the kernel's z (= true z - 0.5*sum(conv_w)) over (B,D,H,W)
     const float* hypos;
     float* out;           // (B,G,D,H,W)
     GridNorm gn;
@@ -214,7 +216,10 @@ __device__ __forceinline__ int key_floor(int k) { return k < 0 ? -1 : (int)__int
 // prepared while slower warps may still be preparing view v.
 enum { kMinX = 0, kMinY = 1, kCount = 2, kSetStride = 4, kRetry = 8 /* [2][2] */, kLeft = 12, kOrg = 16 /* [V][2] */ };
 
-template <class Cfg>
+// MODE 0: eval (one BatchNorm fold for all views).  The training path (mdf_backward.cu) runs the same kernel twice:
+// MODE 1 gathers and only accumulates the batch statistics of z per source view (train-mode BatchNorm3d normalises each
+// view's z over (B,D,H,W), homoaggregate.py:40 + base.py:50-68), MODE 2 is the forward with per-view folds.
+template <class Cfg, int MODE = 0>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB)
 cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedArgs a)
 {
@@ -282,7 +287,33 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
                                    : __ldg(a.hypos + (size_t)b * D + d);
         }
     }
-    const float alpha = __ldg(a.dwp + 0), betap = __ldg(a.dwp + 1), fcw = __ldg(a.dwp + 2), fcb = __ldg(a.dwp + 3);
+    float alpha = __ldg(a.dwp + 0), betap = __ldg(a.dwp + 1);          // MODE 2: reloaded per view
+    const float fcw = __ldg(a.dwp + 2), fcb = __ldg(a.dwp + 3);
+    float w_void_view = 0.0f;                    // MODE 2: weight of an out-of-image sample of the view being prepared
+    float wvoid[MODE == 2 ? PT : 1];             // MODE 2: sum over the views of those weights, per plane
+    double zs1 = 0.0, zs2 = 0.0;                 // MODE 1: sum z, sum z^2 of the samples this thread gathered for one view
+    __shared__ double stats_s[MODE == 1 ? 2 * kMaxSrcViews : 2];
+    if (MODE == 2) {
+#pragma unroll
+        for (int i = 0; i < PT; ++i) wvoid[i] = 0.0f;
+    }
+    if (MODE == 1)
+        for (int k = tid; k < 2 * kMaxSrcViews; k += THREADS) stats_s[k] = 0.0;
+    // per-view BatchNorm fold (MODE 2) and, after a gather, the hand-over of this warp's statistics (MODE 1)
+    auto set_view = [&](int v) {
+        if (MODE == 2) { alpha = __ldg(a.vparams + 4 * v); betap = __ldg(a.vparams + 4 * v + 1); }
+    };
+    auto set_void_view = [&](int v) {
+        if (MODE == 2) w_void_view = __ldg(a.vparams + 4 * v + 2);
+    };
+    auto flush_stats = [&](int v) {
+        if (MODE == 1) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { zs1 += __shfl_xor_sync(0xffffffffu, zs1, o); zs2 += __shfl_xor_sync(0xffffffffu, zs2, o); }
+            if (lane == 0 && (zs1 != 0.0 || zs2 != 0.0)) { atomicAdd(&stats_s[2 * v], zs1); atomicAdd(&stats_s[2 * v + 1], zs2); }
+            zs1 = 0.0; zs2 = 0.0;
+        }
+    };
 
     float2 acc[PT][G / 2];                       // pairs of groups: the core runs on packed FFMA2 / FMUL2 / FADD2
     float wsum[PT];
@@ -319,7 +350,10 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
             const bool inside = (ix[i] > -1.0f) && (ix[i] < a.gn.fw) && (iy[i] > -1.0f) && (iy[i] < a.gn.fh);
             if ((ok_mask >> i) & 1u) {
                 if (inside) todo |= 1u << i;
-                else if (count_void) n_void += 1ull << (8 * i);
+                else if (count_void) {
+                    if (MODE == 2) wvoid[i] += w_void_view;
+                    else n_void += 1ull << (8 * i);
+                }
             }
         }
         return todo;
@@ -406,7 +440,8 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
                 z2 = __ffma2_rn(make_float2(c.z, c.w), p23, z2);
             }
             const float z = z2.x + z2.y;
-            float h = fmaf(z, alpha, betap);              // BatchNorm3d (eval)
+            if (MODE == 1) { zs1 += (double)z; zs2 += (double)z * (double)z; continue; }     // statistics pass: z is all it wants
+            float h = fmaf(z, alpha, betap);              // BatchNorm3d (eval fold, or this view's batch statistics)
             h = fmaxf(h, 0.0f);                           // ReLU
             h = fmaf(h, fcw, fcb);                        // Conv3d(1,1,1)
             const float w = rcp_approx(1.0f + ex2_approx(-kLog2e * h));   // Sigmoid
@@ -423,6 +458,7 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
     {
         float rt[12];
         load_rt(0, rt);
+        set_void_view(0);
         todo = positions(rt, ix, iy, true);
     }
     announce(0, ix, iy, todo);
@@ -446,12 +482,15 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
         if (v + 1 < a.V) {
             float rt[12];
             load_rt(v + 1, rt);
+            set_void_view(v + 1);
             ntodo = positions(rt, nx, ny, true);
             announce(v + 1, nx, ny, ntodo);
         }
         mbar_wait(bar0 + 8u * (v & 1), (uint32_t)(v >> 1) & 1u);
         const int ox = ctl[kOrg + 2 * v], oy = ctl[kOrg + 2 * v + 1];
+        set_view(v);
         todo = gather(box0 + (uint32_t)(v & 1) * Cfg::BOX_BYTES, ox, oy, ix, iy, todo);
+        flush_stats(v);
         if (todo != 0u) left |= 1u << v;
 #pragma unroll
         for (int i = 0; i < PT; ++i) { ix[i] = nx[i]; iy[i] = ny[i]; }
@@ -465,10 +504,12 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
         for (int i = 0; i < PT; ++i) {
             if (!((ok_mask >> i) & 1u)) continue;
             const float nv = (float)((unsigned)(n_void >> (8 * i)) & 255u);
-            const float ws = fmaf(nv, w_void, wsum[i]);
+            // weight of this plane's out-of-image samples: count * one weight (eval), or the sum of the views' own weights
+            const float wv_sum = MODE == 2 ? wvoid[MODE == 2 ? i : 0] : nv * w_void;
+            const float ws = MODE == 2 ? wv_sum + wsum[i] : fmaf(nv, w_void, wsum[i]);
             const float rw = __frcp_rn(ws);
-            // out = 0.5 + q * ((acc + 0.5*nv*w_void) / ws - 0.5); void samples have similarity 0.5 in every group
-            const float c0 = fmaf(0.5f * nv * w_void, rw, -0.5f);
+            // out = 0.5 + q * ((acc + 0.5*wv_sum) / ws - 0.5); void samples have similarity 0.5 in every group
+            const float c0 = fmaf(0.5f * wv_sum, rw, -0.5f);
             const float2 rw2 = make_float2(rw, rw), c02 = make_float2(c0, c0), half2 = make_float2(0.5f, 0.5f);
             float* op = a.out + (((size_t)b * G) * D + (d0 + i)) * HW + (size_t)py * W + px;
             const size_t gstride = (size_t)D * HW;
@@ -485,7 +526,7 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
 
     // Warps whose samples all fitted write their results before the CTA-wide vote (their stores overlap the tail
     // of the slower warps); the others write after the retry rounds.
-    const bool early = Cfg::EARLY && __all_sync(0xffffffffu, left == 0u);
+    const bool early = MODE != 1 && Cfg::EARLY && __all_sync(0xffffffffu, left == 0u);
     if (early) epilogue();
 
     // ---- samples that did not fit their view's box (rough depth maps, silhouettes): synchronous staging
@@ -504,6 +545,7 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
                 load_rt(v, rt);
                 todo = positions(rt, ix, iy, false);
             }
+            set_view(v);
             {   // drop what round 0 already gathered
                 const int ox0 = ctl[kOrg + 2 * v], oy0 = ctl[kOrg + 2 * v + 1];
 #pragma unroll
@@ -543,9 +585,15 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
                 ++riter;
                 todo = gather(box0, ox, oy, ix, iy, todo);
             }
+            flush_stats(v);
         }
     }
 
+    if (MODE == 1) {
+        __syncthreads();                             // every warp has handed its sums over
+        if (tid < 2 * a.V && stats_s[tid] != 0.0) atomicAdd(a.stats + tid, stats_s[tid]);
+        return;
+    }
     if (!early) epilogue();
 }
 
@@ -574,7 +622,7 @@ struct StagedBuffers { const float* S4; const float* Q4; const float* CQ4; };
 // diagnostic (mdf_debug_time_next_hot_kernel): events recorded around the next hot-kernel launch of this thread
 extern thread_local cudaEvent_t g_time_events[2];
 
-template <class Cfg>
+template <class Cfg, int MODE = 0>
 static int launch_staged(const StagedArgs& args, const StagedBuffers& buf, cudaStream_t stream)
 {
     StagedMaps maps;
@@ -582,7 +630,7 @@ static int launch_staged(const StagedArgs& args, const StagedBuffers& buf, cudaS
     if (st == MDF_OK) st = encode_planes(&maps.q4, buf.Q4, args.W, args.H, (long long)args.B * Cfg::J, 32, Cfg::TH, Cfg::J);
     if (st == MDF_OK) st = encode_planes(&maps.cq4, buf.CQ4, args.W, args.H, (long long)args.B * Cfg::J, 32, Cfg::TH, Cfg::J);
     if (st != MDF_OK) return st;
-    auto kern = cost_volume_staged_kernel<Cfg>;
+    auto kern = cost_volume_staged_kernel<Cfg, MODE>;
     MDF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     StagedArgs a = args;
     a.gn = make_grid_norm(a.H, a.W);
@@ -613,6 +661,16 @@ using CfgG8_0  = StagedCfg<8, 4, 4, 2, 64, 10, 2, false>;    // 256 thr x 2 CTAs
 using CfgG8_1  = StagedCfg<8, 4, 8, 1, 64, 14, 2, false>;    // tile 32x8, slab 4 planes
 using CfgG8_2  = StagedCfg<8, 2, 4, 2, 64, 10, 3, false>;    // 3 CTAs, slab 4 planes
 using CfgG8_3  = StagedCfg<8, 2, 2, 4, 64, 6, 3, false>;     // tile 32x2, slab 8 planes, 3 CTAs
+
+// the default configuration of a stage in training mode (MODE 1: batch statistics, MODE 2: per-view BatchNorm folds)
+template <int MODE>
+static int launch_staged_train(int G, const StagedArgs& a, const StagedBuffers& S, cudaStream_t stream)
+{
+    if (G == 32) return launch_staged<CfgG32_0, MODE>(a, S, stream);
+    if (G == 16) return launch_staged<CfgG16_0, MODE>(a, S, stream);
+    if (G == 8) return launch_staged<CfgG8_0, MODE>(a, S, stream);
+    return MDF_ERR_UNSUPPORTED;
+}
 
 static int launch_staged_variant(int G, int variant, const StagedArgs& a, const StagedBuffers& S, cudaStream_t stream)
 {
