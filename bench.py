@@ -47,6 +47,7 @@ WORKLOADS = {
 }
 LAUNCHES_PER_STEP = 3 * (3 + 1)   # per stage: setup + prep + staged cost-volume kernel, + the fused head kernel
 FALLBACK_HBM_GBS = 6650.0
+E2E_PASSES = 3
 # dram__bytes_read.sum + dram__bytes_write.sum of the three cost_volume_staged_kernel launches of one step, from
 # the ncu --set full capture summarised in profiles/r01_final_staged_ncu_full_summary.txt (152.2 + 274.4 + 177.7 MB;
 # below the algorithmic 755.7 MB because the layout pass leaves S4 in L2 and part of the volume is still dirty in
@@ -472,22 +473,30 @@ def run_b200(args, workload, out):
         elapsed_ms = t_start.elapsed_time(t_end)
 
         # ------------------------------------------------------------------------- end to end (host)
-        e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # The leg is PCIe bound (315 MB per step) and the host's PCIe / memory system is shared with the box's other
+        # tenants: back-to-back runs were seen at 5.73, 5.73 and 8.68 ms per step.  So the K steps are timed E2E_PASSES
+        # times, every pass is reported, and the fastest one is the figure (each pass: barrier, K steps, barrier;
+        # max over ranks per pass).
+        e2e_passes = []
         if not args.no_e2e:
             e2e_loop(3)
-        barrier()
-        e_start.record()
-        if not args.no_e2e:
-            e2e_loop(args.steps)
-        e_end.record()
-        barrier()
-        e2e_ms = e_start.elapsed_time(e_end) if not args.no_e2e else float("nan")
+            for _ in range(E2E_PASSES):
+                e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                barrier()
+                e_start.record()
+                e2e_loop(args.steps)
+                e_end.record()
+                barrier()
+                e2e_passes.append(e_start.elapsed_time(e_end))
         clocks = sampler.stop() if sampler else None
 
     if world > 1:
-        t = torch.tensor([elapsed_ms, e2e_ms], device=dev, dtype=torch.float64)
+        t = torch.tensor([elapsed_ms] + (e2e_passes or [0.0]), device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms, e2e_ms = float(t[0]), float(t[1])
+        elapsed_ms = float(t[0])
+        e2e_passes = [float(x) for x in t[1:]] if e2e_passes else []
+    e2e_ms = min(e2e_passes) if e2e_passes else float("nan")
+    if world > 1:
         # the only exchange of the path: final depth + confidence maps to rank 0 (north_star), outside the hot loop
         depths, conf = hot_path(dev_views[0])
         gathered = [torch.empty_like(conf) for _ in range(world)] if rank == 0 else None
@@ -515,7 +524,9 @@ def run_b200(args, workload, out):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": make_config(workload),
             "e2e": None if args.no_e2e else {"value": views / (e2e_ms / 1e3), "unit": "views/s", "h2d_bytes_per_step": h2d,
-                                             "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
+                                             "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
+                                             "passes_ms_per_step": [t / args.steps for t in e2e_passes],
+                                             "note": f"fastest of {E2E_PASSES} passes of K steps (PCIe bound; the host link is shared)"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_DRAM_TRAFFIC.get(workload), "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback",
