@@ -343,7 +343,9 @@ prob_head_tma_kernel(const __grid_constant__ CUtensorMap xmap, const ProbHeadArg
     const uint32_t base_s = smem_u32(base);
     float* w_s = reinterpret_cast<float*>(base + Cfg::OFF_W);
     const uint32_t full0 = base_s + Cfg::OFF_BAR, empty0 = full0 + 8 * NSTAGE;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);        // warp uniform, and the compiler knows it (no divergence
+                                                                   // handling around the consumers' shuffles)
     const int H = a.H, W = a.W, C = a.C;
     const int b = blockIdx.z;
     const int xt = blockIdx.x * TW, yt0 = blockIdx.y * NT * Cfg::TH;
@@ -387,8 +389,11 @@ prob_head_tma_kernel(const __grid_constant__ CUtensorMap xmap, const ProbHeadArg
         // ---- consumers ----
         // this lane's (row y-1, column x0) of plane d0-1 (or d0) inside a stage, and the halo column of the edge lanes
         const uint32_t lane_off = (uint32_t)((d0 * BH + t * Cfg::TH + ly) * BW + 4 + lx * PX) * 4u;
-        const uint32_t halo_off = lane_off + (lx == 0 ? (uint32_t)-4 : (uint32_t)(PX * 4));
-        const bool edge = lx == 0 || lx == 7;
+        // halo column of this lane's row: x0+4 for the last lane of a row, x-1 of the ROW'S FIRST lane for all others (lanes
+        // 1..6 never use it: they read the same word as lane 0 -- a broadcast -- so the load needs no predicate or branch;
+        // the 8 distinct words of a warp fall into 8 distinct banks)
+        const uint32_t row_off = (uint32_t)((d0 * BH + t * Cfg::TH + ly) * BW) * 4u;
+        const uint32_t halo_off = row_off + (lx == 7 ? (uint32_t)(4 + 8 * PX) * 4u : 12u);
         constexpr int NP = DSLAB + 2 * Cfg::DHALO;          // input planes of a slab: local q = 0 .. NP-1, dl = q - DHALO
         for (int c = 0; c < C; ++c) {
             const int s = c % NSTAGE;
@@ -407,8 +412,7 @@ prob_head_tma_kernel(const __grid_constant__ CUtensorMap xmap, const ProbHeadArg
                 for (int ky = 0; ky < 3; ++ky) {
                     const uint32_t off = (uint32_t)((q * BH + ky) * BW) * 4u;          // literal
                     const float4 v4 = lds128(sb + lane_off + off);
-                    float hv = 0.0f;
-                    if (edge) hv = lds32(sb + halo_off + off);
+                    const float hv = lds32(sb + halo_off + off);
                     const float v[4] = {v4.x, v4.y, v4.z, v4.w};
                     const float sl = __shfl_up_sync(0xffffffffu, v4.w, 1);
                     const float sr = __shfl_down_sync(0xffffffffu, v4.x, 1);
