@@ -40,7 +40,7 @@ def is_fresh() -> bool:
 def build_library(force: bool = False, verbose: bool = False) -> str:
     if is_fresh() and not force:
         return LIB_PATH
-    cmd = [_nvcc(), "-O3", "-std=c++17", *ARCH_FLAGS, "-lineinfo", "-shared", "-Xcompiler", "-fPIC,-fvisibility=hidden",
+    cmd = [_nvcc(), "-O3", "-std=c++17", "--threads", "0", *ARCH_FLAGS, "-lineinfo", "-shared", "-Xcompiler", "-fPIC,-fvisibility=hidden",
            "-I", INCLUDE, "-o", LIB_PATH + ".tmp", *sources()]
     if verbose:
         cmd[1:1] = ["-Xptxas", "-v"]
