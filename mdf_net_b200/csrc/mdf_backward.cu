@@ -56,7 +56,8 @@ __device__ __forceinline__ float4 sample4(const float4* __restrict__ plane, int 
                        blend4(nw.z, ne.z, sw.z, se.z, t), blend4(nw.w, ne.w, sw.w, se.w, t));
 }
 
-__device__ __forceinline__ float sigm2(float t) { return 1.0f / (1.0f + exp2f(t)); }     // 1/(1+2^t)
+// 1/(1+2^t) with the same MUFU approximations (<= 2 ulp each) as the forward kernel it differentiates
+__device__ __forceinline__ float sigm2(float t) { return rcp_approx(1.0f + ex2_approx(fminf(t, 126.0f))); }
 
 struct Elem { int x, y, d, b; size_t pix; float depth; bool ok; };
 
@@ -254,99 +255,121 @@ __device__ __forceinline__ void red_add_v4(float4* addr, float4 v)
                  ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-// phase 2: everything else
+// phase 2: everything else.  Registers decide this kernel's speed (one thread carries the gradient state of a whole
+// (b,d,y,x) element), so it is organised in two parts:
+//   A  per-view scalars z_v, A'_v, w_v, h_v -- the only place where all G groups are needed at once;
+//   B  the groups in slices of GS = 8: upstream gradients, q, d q and d conv.weight of ONE slice live in registers while
+//      the source views are walked again (the footprint is recomputed per slice: ~100 instructions against ~2000 of
+//      slice work), the tap gradients go out as vector reductions, then the slice's d q / d conv.weight are flushed.
+// G = 32 used 212 registers (1 block per SM) as one piece; sliced it fits 2-3 blocks per SM.
 template <int G>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 bwd_main_kernel(const BwdArgs a)
 {
-    constexpr int J = G / 4;
+    constexpr int J = G / 4, GS = 8, JS = GS / 4, NS = G / GS;
     const TrainArgs& t = a.t;
     const Elem e = decode(t);
     const GridNorm gn = make_grid_norm(t.H, t.W);
     const size_t HW = (size_t)t.H * t.W;
-    float4 q4[J];
-    float gout[G];
-    float go = 0.0f;
-#pragma unroll
-    for (int j = 0; j < J; ++j) q4[j] = __ldg(t.Q4 + ((size_t)e.b * J + j) * HW + e.pix);
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-        const size_t o = (((size_t)e.b * G + g) * t.D + e.d) * HW + e.pix;
-        gout[g] = e.ok ? __ldg(a.gout + o) : 0.0f;
-        go = fmaf(gout[g], e.ok ? __ldg(a.out + o) : 0.0f, go);
-    }
+    const size_t gstride = (size_t)t.D * HW;
+    const size_t o0 = ((size_t)e.b * G * t.D + e.d) * HW + e.pix;            // element of group 0 in (B,G,D,H,W)
     float zv[kMaxSrcViews], wv[kMaxSrcViews], hv[kMaxSrcViews], av[kMaxSrcViews];
-    float wsum = 0.0f;
-    for (int v = 0; v < t.V; ++v) {
-        zv[v] = view_z<G>(t, e, v, taps_of(t, e, v, gn), q4, gout, &av[v]);
-        wv[v] = view_weight(t, v, zv[v], &hv[v]);
-        wsum += wv[v];
-    }
-    float dq[G], dcw[G];
+    float wsum = 0.0f, go = 0.0f;
+    {   // ---- part A ----
+        float4 q4[J];
+        float gout[G];
 #pragma unroll
-    for (int g = 0; g < G; ++g) { dq[g] = 0.0f; dcw[g] = 0.0f; }
+        for (int j = 0; j < J; ++j) q4[j] = __ldg(t.Q4 + ((size_t)e.b * J + j) * HW + e.pix);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            gout[g] = e.ok ? __ldg(a.gout + o0 + (size_t)g * gstride) : 0.0f;
+            go = fmaf(gout[g], e.ok ? __ldg(a.out + o0 + (size_t)g * gstride) : 0.0f, go);
+        }
+        for (int v = 0; v < t.V; ++v) {
+            zv[v] = view_z<G>(t, e, v, taps_of(t, e, v, gn), q4, gout, &av[v]);
+            wv[v] = view_weight(t, v, zv[v], &hv[v]);
+            wsum += wv[v];
+        }
+    }
     double gp[4] = {0.0, 0.0, 0.0, 0.0};         // d bn_w, d bn_b, d fc_w, d fc_b
-    for (int v = 0; v < t.V; ++v) {
-        if (!e.ok) break;
-        float dact;
-        const float dh = dh_of(a, av[v], go, wsum, wv[v], hv[v], &dact);
-        gp[2] += (double)dact * fmaxf(hv[v], 0.0f);
-        gp[3] += dact;
-        const float invstd = __ldg(t.bnv + 4 * v + 2), mean = __ldg(t.bnv + 4 * v + 3), alpha = __ldg(t.bnv + 4 * v);
-        const float zhat = (zv[v] - mean) * invstd;
-        float dz;
-        if (a.training) {
-            // BatchNorm with batch statistics: dz = (gamma/std) * (dh - mean(dh) - zhat * mean(dh*zhat))
-            const float m1 = (float)(a.bsum[2 * v] / a.count), m2 = (float)(a.bsum[2 * v + 1] / a.count);
-            dz = alpha * (dh - m1 - zhat * m2);
-        } else {
-            dz = alpha * dh;
+    // ---- part B ----
+    for (int s = 0; s < NS; ++s) {
+        float4 q4[JS];
+        float gout[GS], dq[GS], dcw[GS];
+#pragma unroll
+        for (int jj = 0; jj < JS; ++jj) q4[jj] = __ldg(t.Q4 + ((size_t)e.b * J + s * JS + jj) * HW + e.pix);
+#pragma unroll
+        for (int k = 0; k < GS; ++k) {
+            gout[k] = e.ok ? __ldg(a.gout + o0 + (size_t)(s * GS + k) * gstride) : 0.0f;
+            dq[k] = 0.0f;
+            dcw[k] = 0.0f;
         }
-        gp[0] += (double)dh * zhat;               // d gamma = sum dh * zhat   (both modes: h = gamma*zhat + beta)
-        gp[1] += dh;                              // d beta
-        const float wn = wv[v] / wsum;
-        const Taps tp = taps_of(t, e, v, gn);
-        const float4* Sv = t.S4 + ((size_t)v * t.B + e.b) * J * HW;
-        float4* dSv = a.dS4 + ((size_t)v * t.B + e.b) * J * HW;
-        const bool x0in = (unsigned)tp.x0 < (unsigned)t.W, x1in = (unsigned)(tp.x0 + 1) < (unsigned)t.W;
-        const bool y0in = (unsigned)tp.y0 < (unsigned)t.H, y1in = (unsigned)(tp.y0 + 1) < (unsigned)t.H;
-#pragma unroll
-        for (int j = 0; j < J; ++j) {
-            float4 tt = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (tp.valid) tt = sample4(Sv + (size_t)j * HW, t.H, t.W, tp);
-            const float tv[4] = {tt.x, tt.y, tt.z, tt.w};
-            const float qv[4] = {q4[j].x, q4[j].y, q4[j].z, q4[j].w};
-            float dt[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int g = 4 * j + k;
-                const float p = sigm2(tv[k]);
-                const float sim = fmaf(qv[k], p - 0.5f, 0.5f);
-                const float dsim = fmaf(gout[g], wn, dz * __ldg(t.cw + g));
-                dcw[g] = fmaf(dz, sim, dcw[g]);
-                dq[g] = fmaf(dsim, p - 0.5f, dq[g]);
-                dt[k] = -kLn2 * p * (1.0f - p) * (dsim * qv[k]);      // dp/dt = -ln2 p (1-p)
+        for (int v = 0; v < t.V; ++v) {
+            if (!e.ok) break;
+            float dact;
+            const float dh = dh_of(a, av[v], go, wsum, wv[v], hv[v], &dact);
+            const float invstd = __ldg(t.bnv + 4 * v + 2), mean = __ldg(t.bnv + 4 * v + 3), alpha = __ldg(t.bnv + 4 * v);
+            const float zhat = (zv[v] - mean) * invstd;
+            float dz;
+            if (a.training) {
+                // BatchNorm with batch statistics: dz = (gamma/std) * (dh - mean(dh) - zhat * mean(dh*zhat))
+                const float m1 = (float)(a.bsum[2 * v] / a.count), m2 = (float)(a.bsum[2 * v + 1] / a.count);
+                dz = alpha * (dh - m1 - zhat * m2);
+            } else {
+                dz = alpha * dh;
             }
-            if (tp.valid) {
-                float4* d = dSv + (size_t)j * HW + (ptrdiff_t)tp.y0 * t.W + tp.x0;
-                if (x0in && y0in) red_add_v4(d, make_float4(dt[0] * tp.wnw, dt[1] * tp.wnw, dt[2] * tp.wnw, dt[3] * tp.wnw));
-                if (x1in && y0in) red_add_v4(d + 1, make_float4(dt[0] * tp.wne, dt[1] * tp.wne, dt[2] * tp.wne, dt[3] * tp.wne));
-                if (x0in && y1in) red_add_v4(d + t.W, make_float4(dt[0] * tp.wsw, dt[1] * tp.wsw, dt[2] * tp.wsw, dt[3] * tp.wsw));
-                if (x1in && y1in) red_add_v4(d + t.W + 1, make_float4(dt[0] * tp.wse, dt[1] * tp.wse, dt[2] * tp.wse, dt[3] * tp.wse));
+            if (s == 0) {
+                gp[2] += (double)dact * fmaxf(hv[v], 0.0f);
+                gp[3] += dact;
+                gp[0] += (double)dh * zhat;           // d gamma = sum dh * zhat   (both modes: h = gamma*zhat + beta)
+                gp[1] += dh;                          // d beta
+            }
+            const float wn = wv[v] / wsum;
+            const Taps tp = taps_of(t, e, v, gn);
+            const float4* Sv = t.S4 + ((size_t)v * t.B + e.b) * J * HW;
+            float4* dSv = a.dS4 + ((size_t)v * t.B + e.b) * J * HW;
+            const bool x0in = (unsigned)tp.x0 < (unsigned)t.W, x1in = (unsigned)(tp.x0 + 1) < (unsigned)t.W;
+            const bool y0in = (unsigned)tp.y0 < (unsigned)t.H, y1in = (unsigned)(tp.y0 + 1) < (unsigned)t.H;
+#pragma unroll
+            for (int jj = 0; jj < JS; ++jj) {
+                const int j = s * JS + jj;
+                float4 tt = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (tp.valid) tt = sample4(Sv + (size_t)j * HW, t.H, t.W, tp);
+                const float tv[4] = {tt.x, tt.y, tt.z, tt.w};
+                const float qv[4] = {q4[jj].x, q4[jj].y, q4[jj].z, q4[jj].w};
+                float dt[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int gl = 4 * jj + k;
+                    const float p = sigm2(tv[k]);
+                    const float sim = fmaf(qv[k], p - 0.5f, 0.5f);
+                    const float dsim = fmaf(gout[gl], wn, dz * __ldg(t.cw + 4 * j + k));
+                    dcw[gl] = fmaf(dz, sim, dcw[gl]);
+                    dq[gl] = fmaf(dsim, p - 0.5f, dq[gl]);
+                    dt[k] = -kLn2 * p * (1.0f - p) * (dsim * qv[k]);      // dp/dt = -ln2 p (1-p)
+                }
+                if (tp.valid) {
+                    float4* d = dSv + (size_t)j * HW + (ptrdiff_t)tp.y0 * t.W + tp.x0;
+                    if (x0in && y0in) red_add_v4(d, make_float4(dt[0] * tp.wnw, dt[1] * tp.wnw, dt[2] * tp.wnw, dt[3] * tp.wnw));
+                    if (x1in && y0in) red_add_v4(d + 1, make_float4(dt[0] * tp.wne, dt[1] * tp.wne, dt[2] * tp.wne, dt[3] * tp.wne));
+                    if (x0in && y1in) red_add_v4(d + t.W, make_float4(dt[0] * tp.wsw, dt[1] * tp.wsw, dt[2] * tp.wsw, dt[3] * tp.wsw));
+                    if (x1in && y1in) red_add_v4(d + t.W + 1, make_float4(dt[0] * tp.wse, dt[1] * tp.wse, dt[2] * tp.wse, dt[3] * tp.wse));
+                }
             }
         }
-    }
-    if (e.ok) {
-        float4* dqp = a.dQ4 + (size_t)e.b * J * HW + e.pix;
+        if (e.ok) {
+            float4* dqp = a.dQ4 + ((size_t)e.b * J + s * JS) * HW + e.pix;
 #pragma unroll
-        for (int j = 0; j < J; ++j) red_add_v4(dqp + (size_t)j * HW, make_float4(dq[4 * j], dq[4 * j + 1], dq[4 * j + 2], dq[4 * j + 3]));
+            for (int jj = 0; jj < JS; ++jj)
+                red_add_v4(dqp + (size_t)jj * HW, make_float4(dq[4 * jj], dq[4 * jj + 1], dq[4 * jj + 2], dq[4 * jj + 3]));
+        }
+#pragma unroll
+        for (int jj = 0; jj < JS; ++jj) {
+            double c[4] = {dcw[4 * jj], dcw[4 * jj + 1], dcw[4 * jj + 2], dcw[4 * jj + 3]};
+            block_accumulate<4>(c, a.gparam + 4 + 4 * (s * JS + jj));
+        }
     }
     block_accumulate<4>(gp, a.gparam);
-#pragma unroll
-    for (int j = 0; j < J; ++j) {
-        double c[4] = {dcw[4 * j], dcw[4 * j + 1], dcw[4 * j + 2], dcw[4 * j + 3]};
-        block_accumulate<4>(c, a.gparam + 4 + 4 * j);
-    }
 }
 
 // dS4 / dQ4 -> NCHW feature gradients.  One thread per pixel per view; blockIdx.y = view * B + b.
