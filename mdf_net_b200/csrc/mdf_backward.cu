@@ -77,12 +77,14 @@ __device__ __forceinline__ Elem decode(const TrainArgs& a)
     return e;
 }
 
-__device__ __forceinline__ Taps taps_of(const TrainArgs& a, const Elem& e, int v, const GridNorm& gn)
+// footprint of element e in source view v: the same bit-exact position as the forward (mdf_common.cuh: shared-reciprocal
+// divisions where they are exact, the IEEE chain otherwise)
+__device__ __forceinline__ Taps taps_of(const TrainArgs& a, const Elem& e, int v, const GridNormFast& gf)
 {
     const float* rt = a.rt + ((size_t)v * a.B + e.b) * 12;
     float ix, iy;
-    sample_position(rot_xyz(rt, (float)e.x, (float)e.y), rt, e.depth, gn, ix, iy);
-    return make_taps(ix, iy, gn);
+    sample_position_fast(rot_xyz(rt, (float)e.x, (float)e.y), rt, e.depth, gf, ix, iy);
+    return make_taps(ix, iy, gf.g);
 }
 
 // z_v of one element (and optionally A'_v = sum_g gout_g sim_vg)
@@ -194,6 +196,7 @@ struct BwdArgs {
     const float* out;       // saved forward output (B,G,D,H,W)
     const float* gout;      // upstream gradient      (B,G,D,H,W)
     const double* bsum;     // [V][2] train: sum dh_v, sum dh_v*zhat_v  (phase 1 result)
+    float* za;              // [V][2][B*D*H*W]: z_v and A'_v of every element, written by phase 1, read by phase 2
     double count;
     int training;
     float4* dS4;            // [V][B][J][H][W]  zero-initialised
@@ -218,7 +221,7 @@ bwd_stats_kernel(const BwdArgs a, double* __restrict__ bsum)
     constexpr int J = G / 4;
     const TrainArgs& t = a.t;
     const Elem e = decode(t);
-    const GridNorm gn = make_grid_norm(t.H, t.W);
+    const GridNormFast gn = make_grid_norm_fast(t.H, t.W);
     const size_t HW = (size_t)t.H * t.W;
     float4 q4[J];
     float gout[G];
@@ -238,6 +241,14 @@ bwd_stats_kernel(const BwdArgs a, double* __restrict__ bsum)
         wv[v] = view_weight(t, v, zv[v], &hv[v]);
         wsum += wv[v];
     }
+    // hand z_v and A'_v over to the main sweep (it would otherwise gather every view a second time just for them)
+    const size_t total = (size_t)t.B * t.D * HW, idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e.ok)
+        for (int v = 0; v < t.V; ++v) {
+            a.za[(size_t)(2 * v) * total + idx] = zv[v];
+            a.za[(size_t)(2 * v + 1) * total + idx] = av[v];
+        }
+    if (!a.training) return;                     // uniform: the batch sums only exist in train mode
     for (int v = 0; v < t.V; ++v) {
         double s[2] = {0.0, 0.0};
         if (e.ok) {
@@ -257,7 +268,7 @@ __device__ __forceinline__ void red_add_v4(float4* addr, float4 v)
 
 // phase 2: everything else.  Registers decide this kernel's speed (one thread carries the gradient state of a whole
 // (b,d,y,x) element), so it is organised in two parts:
-//   A  per-view scalars z_v, A'_v, w_v, h_v -- the only place where all G groups are needed at once;
+//   A  per-view scalars z_v, A'_v (handed over by phase 1, which needs them anyway), w_v, h_v;
 //   B  the groups in slices of GS = 8: upstream gradients, q, d q and d conv.weight of ONE slice live in registers while
 //      the source views are walked again (the footprint is recomputed per slice: ~100 instructions against ~2000 of
 //      slice work), the tap gradients go out as vector reductions, then the slice's d q / d conv.weight are flushed.
@@ -269,29 +280,28 @@ bwd_main_kernel(const BwdArgs a)
     constexpr int J = G / 4, GS = 8, JS = GS / 4, NS = G / GS;
     const TrainArgs& t = a.t;
     const Elem e = decode(t);
-    const GridNorm gn = make_grid_norm(t.H, t.W);
+    const GridNormFast gn = make_grid_norm_fast(t.H, t.W);
     const size_t HW = (size_t)t.H * t.W;
     const size_t gstride = (size_t)t.D * HW;
     const size_t o0 = ((size_t)e.b * G * t.D + e.d) * HW + e.pix;            // element of group 0 in (B,G,D,H,W)
     float zv[kMaxSrcViews], wv[kMaxSrcViews], hv[kMaxSrcViews], av[kMaxSrcViews];
     float wsum = 0.0f, go = 0.0f;
-    {   // ---- part A ----
-        float4 q4[J];
-        float gout[G];
-#pragma unroll
-        for (int j = 0; j < J; ++j) q4[j] = __ldg(t.Q4 + ((size_t)e.b * J + j) * HW + e.pix);
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-            gout[g] = e.ok ? __ldg(a.gout + o0 + (size_t)g * gstride) : 0.0f;
-            go = fmaf(gout[g], e.ok ? __ldg(a.out + o0 + (size_t)g * gstride) : 0.0f, go);
-        }
+    {   // ---- part A: z_v and A'_v come from phase 1; go = sum_g gout_g out_g is a plain sweep ----
+        const size_t total = (size_t)t.B * t.D * HW, idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll 8
+        for (int g = 0; g < G; ++g)
+            go = fmaf(e.ok ? __ldg(a.gout + o0 + (size_t)g * gstride) : 0.0f, e.ok ? __ldg(a.out + o0 + (size_t)g * gstride) : 0.0f, go);
         for (int v = 0; v < t.V; ++v) {
-            zv[v] = view_z<G>(t, e, v, taps_of(t, e, v, gn), q4, gout, &av[v]);
+            zv[v] = e.ok ? __ldg(a.za + (size_t)(2 * v) * total + idx) : 0.0f;
+            av[v] = e.ok ? __ldg(a.za + (size_t)(2 * v + 1) * total + idx) : 0.0f;
             wv[v] = view_weight(t, v, zv[v], &hv[v]);
             wsum += wv[v];
         }
     }
     double gp[4] = {0.0, 0.0, 0.0, 0.0};         // d bn_w, d bn_b, d fc_w, d fc_b
+    __shared__ double dcw_s[G];                  // d conv.weight of the block: warp sums land here, one flush at the end
+    if (threadIdx.x < G) dcw_s[threadIdx.x] = 0.0;
+    __syncthreads();
     // ---- part B ----
     for (int s = 0; s < NS; ++s) {
         float4 q4[JS];
@@ -364,12 +374,15 @@ bwd_main_kernel(const BwdArgs a)
                 red_add_v4(dqp + (size_t)jj * HW, make_float4(dq[4 * jj], dq[4 * jj + 1], dq[4 * jj + 2], dq[4 * jj + 3]));
         }
 #pragma unroll
-        for (int jj = 0; jj < JS; ++jj) {
-            double c[4] = {dcw[4 * jj], dcw[4 * jj + 1], dcw[4 * jj + 2], dcw[4 * jj + 3]};
-            block_accumulate<4>(c, a.gparam + 4 + 4 * (s * JS + jj));
+        for (int k = 0; k < GS; ++k) {
+            float c = e.ok ? dcw[k] : 0.0f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            if ((threadIdx.x & 31) == 0 && c != 0.0f) atomicAdd(&dcw_s[s * GS + k], (double)c);
         }
     }
-    block_accumulate<4>(gp, a.gparam);
+    block_accumulate<4>(gp, a.gparam);           // ends with a barrier: dcw_s is complete
+    if (threadIdx.x < G && dcw_s[threadIdx.x] != 0.0) atomicAdd(a.gparam + 4 + threadIdx.x, dcw_s[threadIdx.x]);
 }
 
 // dS4 / dQ4 -> NCHW feature gradients.  One thread per pixel per view; blockIdx.y = view * B + b.
@@ -415,10 +428,10 @@ __global__ void gparam_to_float_kernel(const double* __restrict__ src, float* __
 // workspace
 // ------------------------------------------------------------------------------------------------
 struct TrainWorkspace {
-    size_t rt, dwp, q, s, cq, bnv, vparams, fc, stats, bsum, gparam, dq, ds, total;
+    size_t rt, dwp, q, s, cq, bnv, vparams, fc, za, stats, bsum, gparam, dq, ds, total;
 };
 
-static TrainWorkspace make_train_workspace(int B, int N, int G, int H, int W)
+static TrainWorkspace make_train_workspace(int B, int N, int G, int D, int H, int W)
 {
     TrainWorkspace w;
     const size_t V = (size_t)(N - 1), plane = (size_t)B * G * H * W * sizeof(float);
@@ -432,6 +445,7 @@ static TrainWorkspace make_train_workspace(int B, int N, int G, int H, int W)
     w.bnv = take(kMaxSrcViews * 4 * sizeof(float));
     w.vparams = take(kMaxSrcViews * 4 * sizeof(float));
     w.fc = take(2 * sizeof(float));
+    w.za = take(V * 2 * (size_t)B * D * H * W * sizeof(float));      // z_v, A'_v of every element (backward phase 1 -> 2)
     w.stats = take(kMaxSrcViews * 2 * sizeof(double));      // stats | bsum | gparam are contiguous: one memset
     w.bsum = take(kMaxSrcViews * 2 * sizeof(double));
     w.gparam = take((4 + 32) * sizeof(double));
@@ -456,7 +470,7 @@ static int validate(const TrainCall& c, const void* out, void* workspace, size_t
     if (!c.features || !c.src_projs || !c.ref_proj || !c.hypos || !c.conv_w || !c.bn_w || !c.bn_b || !c.bn_mean || !c.bn_var ||
         !c.fc_w || !c.fc_b || !out)
         return MDF_ERR_NULL_POINTER;
-    *ws = make_train_workspace(c.B, c.N, c.G, c.H, c.W);
+    *ws = make_train_workspace(c.B, c.N, c.G, c.D, c.H, c.W);
     if (!workspace || ((uintptr_t)workspace & 255) != 0 || workspace_bytes < ws->total) return MDF_ERR_WORKSPACE;
     const int dev = device_of(out);
     if (dev < 0) return dev;
@@ -560,11 +574,10 @@ static int train_bwd(const TrainCall& c, const float* cost_volume, const float* 
     MDF_CUDA_TRY(cudaMemsetAsync(wsb + ws.dq, 0, ws.total - ws.dq, stream));
     const size_t total = (size_t)c.B * c.D * c.H * c.W;
     const unsigned blocks = (unsigned)((total + 255) / 256);
-    if (c.training) {
-        bwd_stats_kernel<G><<<blocks, 256, 0, stream>>>(a, reinterpret_cast<double*>(wsb + ws.bsum));
-        st = launch_status();
-        if (st != MDF_OK) return st;
-    }
+    a.za = reinterpret_cast<float*>(wsb + ws.za);
+    bwd_stats_kernel<G><<<blocks, 256, 0, stream>>>(a, reinterpret_cast<double*>(wsb + ws.bsum));      // also in eval mode: it hands z_v, A'_v over
+    st = launch_status();
+    if (st != MDF_OK) return st;
     bwd_main_kernel<G><<<blocks, 256, 0, stream>>>(a);
     st = launch_status();
     if (st != MDF_OK) return st;
@@ -590,9 +603,8 @@ extern "C" {
 
 size_t mdf_cost_volume_train_workspace_bytes(int B, int N, int C, int G, int D, int H, int W)
 {
-    (void)D;
-    if (B <= 0 || N < 2 || C != 2 * G || G <= 0 || H <= 0 || W <= 0) return 0;
-    return make_train_workspace(B, N, G, H, W).total;
+    if (B <= 0 || N < 2 || C != 2 * G || G <= 0 || D <= 0 || H <= 0 || W <= 0) return 0;
+    return make_train_workspace(B, N, G, D, H, W).total;
 }
 
 int mdf_cost_volume_train_fwd(const float* const* features, int N, const float* ref_proj, const float* const* src_projs,
