@@ -435,3 +435,14 @@ def test_errors_and_empty_inputs():
         cv = m(f, eye, [eye], torch.full((1, 3, 1, 1), 500.0, device="cuda"))
     assert cv.shape == (1, 8, 3, 8, 8) and torch.allclose(cv, torch.full_like(cv, 0.5))    # zero features
     assert ops.launch_count() > 0
+
+
+@pytest.mark.parametrize("h0,w0,nviews,stage", [(1056, 1920, 7, 2), (1056, 1920, 7, 0), (1184, 1600, 5, 1)])
+def test_other_baseline_shapes_staged_equals_direct(h0, w0, nviews, stage):
+    """BASELINE.json configs[3] (Tanks and Temples 1920x1056, N=7) and the crop the shipped DTU loader really uses
+    (1600x1184, dtueval.py:34; rows not a multiple of the tile height): staged vs the independent direct kernel."""
+    c = stage_case(stage, h0, w0, nviews, seed=400 + stage)
+    a = run_cost_volume(c["features"], c["ref_proj"], c["src_projs"], c["hypos"], c["params"], c["G"], 1)
+    b = run_cost_volume(c["features"], c["ref_proj"], c["src_projs"], c["hypos"], c["params"], c["G"], 2)
+    assert a.shape == (1, c["G"], c["D"], c["H"], c["W"])
+    assert rel_l2(a, b) < COST_TOL and max_abs_over_max(a, b) < 2e-4
