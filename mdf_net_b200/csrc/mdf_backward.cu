@@ -213,9 +213,11 @@ __device__ __forceinline__ float dh_of(const BwdArgs& a, float aprime, float go,
     return h > 0.0f ? dact * __ldg(a.t.fc) : 0.0f;      // Conv3d(1,1,1) then ReLU
 }
 
-// phase 1 (train only): sum_v over elements of dh_v and dh_v * zhat_v
+// phase 1: z_v and A'_v of every element (handed to phase 2) and, in train mode, the sums over the elements of dh_v and
+// dh_v * zhat_v per view.  q and the upstream gradients are streamed per group quad instead of being held in registers
+// (they come from L1 after the first view), which keeps the kernel at four blocks per SM.
 template <int G>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 bwd_stats_kernel(const BwdArgs a, double* __restrict__ bsum)
 {
     constexpr int J = G / 4;
@@ -223,21 +225,33 @@ bwd_stats_kernel(const BwdArgs a, double* __restrict__ bsum)
     const Elem e = decode(t);
     const GridNormFast gn = make_grid_norm_fast(t.H, t.W);
     const size_t HW = (size_t)t.H * t.W;
-    float4 q4[J];
-    float gout[G];
+    const size_t gstride = (size_t)t.D * HW;
+    const size_t o0 = ((size_t)e.b * G * t.D + e.d) * HW + e.pix;
     float go = 0.0f;
-#pragma unroll
-    for (int j = 0; j < J; ++j) q4[j] = __ldg(t.Q4 + ((size_t)e.b * J + j) * HW + e.pix);
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-        const size_t o = (((size_t)e.b * G + g) * t.D + e.d) * HW + e.pix;
-        gout[g] = e.ok ? __ldg(a.gout + o) : 0.0f;
-        go = fmaf(gout[g], e.ok ? __ldg(a.out + o) : 0.0f, go);
-    }
+#pragma unroll 8
+    for (int g = 0; g < G; ++g)
+        go = fmaf(e.ok ? __ldg(a.gout + o0 + (size_t)g * gstride) : 0.0f, e.ok ? __ldg(a.out + o0 + (size_t)g * gstride) : 0.0f, go);
     float zv[kMaxSrcViews], wv[kMaxSrcViews], hv[kMaxSrcViews], av[kMaxSrcViews];
     float wsum = 0.0f;
     for (int v = 0; v < t.V; ++v) {
-        zv[v] = view_z<G>(t, e, v, taps_of(t, e, v, gn), q4, gout, &av[v]);
+        const Taps tp = taps_of(t, e, v, gn);
+        const float4* Sv = t.S4 + ((size_t)v * t.B + e.b) * J * HW;
+        float z = 0.0f, ap = 0.0f;
+#pragma unroll 2
+        for (int j = 0; j < J; ++j) {
+            float4 tt = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (tp.valid) tt = sample4(Sv + (size_t)j * HW, t.H, t.W, tp);
+            const float4 q = __ldg(t.Q4 + ((size_t)e.b * J + j) * HW + e.pix);
+            const float s0 = fmaf(q.x, sigm2(tt.x) - 0.5f, 0.5f), s1 = fmaf(q.y, sigm2(tt.y) - 0.5f, 0.5f);
+            const float s2 = fmaf(q.z, sigm2(tt.z) - 0.5f, 0.5f), s3 = fmaf(q.w, sigm2(tt.w) - 0.5f, 0.5f);
+            z = fmaf(__ldg(t.cw + 4 * j + 0), s0, z); z = fmaf(__ldg(t.cw + 4 * j + 1), s1, z);
+            z = fmaf(__ldg(t.cw + 4 * j + 2), s2, z); z = fmaf(__ldg(t.cw + 4 * j + 3), s3, z);
+            const float* gp = a.gout + o0 + (size_t)(4 * j) * gstride;
+            ap = fmaf(e.ok ? __ldg(gp) : 0.0f, s0, ap); ap = fmaf(e.ok ? __ldg(gp + gstride) : 0.0f, s1, ap);
+            ap = fmaf(e.ok ? __ldg(gp + 2 * gstride) : 0.0f, s2, ap); ap = fmaf(e.ok ? __ldg(gp + 3 * gstride) : 0.0f, s3, ap);
+        }
+        zv[v] = z;
+        av[v] = ap;
         wv[v] = view_weight(t, v, zv[v], &hv[v]);
         wsum += wv[v];
     }
