@@ -131,3 +131,28 @@ def test_fused_stage_tails_match_the_unit_by_unit_path():
     with torch.no_grad():
         out = fused(imgs, E, K, dr)
     assert isinstance(out["depth"], list) and len(out["depth"]) == 4
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "net")), reason="reference checkout not present (GPU box)")
+def test_regulariser_body_stops_the_reference_modules_in_front_of_prob():
+    """`regulariser_body` on the reference's own RegularNet_3Scales / RegularNet_4Scales: what it returns is exactly the
+    tensor their forward() feeds to `self.prob` (conv + squeeze + softmax of it reproduce the module's output), the
+    module is left untouched (no hook stays behind), and `_fusable_prob_layer` accepts both."""
+    sys.dont_write_bytecode = True
+    sys.path.insert(0, REF)
+    try:
+        from net.unit.regular import RegularNet_3Scales, RegularNet_4Scales
+    finally:
+        sys.path.remove(REF)
+    from mdf_net_b200.core import _fusable_prob_layer, regulariser_body
+    torch.manual_seed(0)
+    for net, shape in ((RegularNet_3Scales(32).eval(), (1, 32, 8, 8, 12)), (RegularNet_4Scales(8).eval(), (2, 8, 8, 16, 16))):
+        cv = torch.rand(shape)
+        with torch.no_grad():
+            x = regulariser_body(net, cv)
+            want = net(cv)
+            got = F.softmax(net.prob(x).squeeze(1), dim=1)
+        assert x.shape == (shape[0], net.prob.in_channels) + shape[2:]
+        assert torch.equal(got, want)
+        assert len(net.prob._forward_pre_hooks) == 0
+        assert _fusable_prob_layer(net) is net.prob
