@@ -283,6 +283,60 @@ def time_regulariser_tail(dev, h0, w0, batch, host_view):
             "cudnn_conv3d_alone_us": cudnn, "not_in_value": True}
 
 
+def time_other_rows(dev):
+    """Other rows of the scope table, reported next to the headline (not part of `value`): train-mode forward + backward
+    of the fused op at BASELINE.json configs[4] (768x576, N=5, batch 8), `homo_warping` at configs[1] stage 0 and the
+    geometric-consistency filter at 1600x1200 with 10 source views.  CUDA events around eager calls, median of 5, ms."""
+    import torch
+    import mdf_net_b200 as mdf
+    from mdf_net_b200 import ops
+
+    def med(fn, n=5, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(n):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return statistics.median(ts)
+
+    cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    out = {"not_in_value": True}
+    h0, w0, nviews, batch = 576, 768, 5, 8
+    K, E = syn.camera_rig(batch, nviews, h0, w0, seed=3)
+    train = []
+    for s in range(3):
+        H, W = syn.stage_shapes(h0, w0)[s]
+        C, D, G = syn.STAGE_CHANNELS[s], syn.STAGE_DEPTHS[s], syn.STAGE_GROUPS[s]
+        P = syn.projection_matrices(K, E, 2.0 ** (3 - s))
+        feats = [cu(f).requires_grad_(True) for f in syn.smooth_features(batch, nviews, C, H, W, seed=60 + s)]
+        hyp = cu(syn.uniform_hypos(batch, D) if s == 0 else syn.pixel_hypos(batch, D, H, W, seed=61 + s))
+        rp, sps = cu(P[:, 0]), [cu(P[:, v]) for v in range(1, nviews)]
+        m = mdf.VectorAggregate(G).to(dev).train()
+        go = torch.randn((batch, G, D, H, W), device=dev)
+        train.append(med(lambda: m(feats, rp, sps, hyp).backward(go), n=3, warm=1))
+        del feats, go, m
+    out["train_fwd_bwd_ms_768x576_n5_b8"] = train
+    K, E = syn.camera_rig(1, 5, 1152, 1600, seed=1)
+    H, W = syn.stage_shapes(1152, 1600)[0]
+    P = syn.projection_matrices(K, E, 8.0)
+    f = cu(syn.smooth_features(1, 2, 64, H, W, seed=10)[1])
+    hyp = cu(syn.uniform_hypos(1, 48))
+    t = med(lambda: ops.homo_warp(f, cu(P[:, 1]), cu(P[:, 0]), hyp))
+    out["homo_warp_stage0"] = {"ms": t, "output_GBps": 64 * 48 * H * W * 4 / 1e9 / (t / 1e3)}
+    S, Hf, Wf = 10, 1200, 1600
+    Kf, Ef = syn.camera_rig(1, S + 1, Hf, Wf, seed=321)
+    gen = torch.Generator(device=dev).manual_seed(1)
+    depths = [700.0 + 20.0 * torch.rand((Hf, Wf), device=dev, generator=gen) for _ in range(S + 1)]
+    conf = torch.rand((Hf, Wf), device=dev, generator=gen)
+    Kt, Et = cu(Kf[0]), cu(Ef[0])
+    out["geo_filter_1600x1200_10src_ms"] = med(lambda: ops.geo_filter(depths[0], Kt[0], Et[0], depths[1:], Kt[1:], Et[1:], conf,
+                                                                        0.8, 3, 4.0, 1300.0))
+    return out
+
+
 # ----------------------------------------------------------------------------------------- GPU arm
 def run_b200(args, workload, out):
     import torch
@@ -550,6 +604,13 @@ def run_b200(args, workload, out):
                 line["regulariser_tail"] = time_regulariser_tail(dev, h0, w0, batch, host_views[0])
             except Exception as e:  # pragma: no cover - the headline must not depend on the extra
                 line["regulariser_tail"] = {"error": f"{type(e).__name__}: {e}"}
+        if world == 1 and not args.no_tail:
+            try:
+                del dev_views, pin_views, packed, graphs
+                torch.cuda.empty_cache()
+                line["other_rows"] = time_other_rows(dev)
+            except Exception as e:  # pragma: no cover - the headline must not depend on the extras
+                line["other_rows"] = {"error": f"{type(e).__name__}: {e}"}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(host_views[0], args.cpu_budget, batch)
         out.emit(json.dumps(line))
