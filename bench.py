@@ -571,7 +571,10 @@ def run_b200(args, workload, out):
             h2d = packed[0][0].numel() * 4          # what actually crosses PCIe per step: the arena incl. its alignment padding
         H2, W2 = syn.stage_shapes(h0, w0)[2]
         d2h = 4 * batch * (sum(h * w for h, w in syn.stage_shapes(h0, w0)) + 4 * H2 * W2)
-        achieved = sum(cv_bytes) / 1e9 / (sum(cv_ms) / 1e3)
+        # the dominant kernel (cost_volume_staged_kernel: ~84 % of the step): algorithmic bytes of its three launches over
+        # its own CUDA-event time; the op-level figure (layout pass + setup included) is kept next to it
+        achieved = sum(cv_bytes) / 1e9 / (sum(hot_ms) / 1e3)
+        achieved_op = sum(cv_bytes) / 1e9 / (sum(cv_ms) / 1e3)
         line = {
             "metric": "DTU views/s (plane-sweep cost-volume path)", "value": views / (elapsed_ms / 1e3), "unit": "views/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps,
@@ -584,7 +587,9 @@ def run_b200(args, workload, out):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_DRAM_TRAFFIC.get(workload), "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback",
-                         "kernel": "mdf_cost_volume_fwd (setup_kernel || prep_kernel, then cost_volume_staged_kernel), 3 calls of the op per step",
+                         "kernel": "cost_volume_staged_kernel<G=32|16|8> (the three launches of one step; events recorded inside the library around the kernel alone)",
+                         "op_level": {"what": "mdf_cost_volume_fwd = setup_kernel || prep_kernel, then the kernel above", "GBps": achieved_op,
+                                      "frac": achieved_op / peak},
                          "algorithmic_bytes_per_step": sum(cv_bytes),
                          "per_stage": [{"bytes": b, "ms": ms, "GB/s": b / 1e9 / (ms / 1e3), "hot_kernel_ms": hk}
                                        for b, ms, hk in zip(cv_bytes, cv_ms, hot_ms)],
