@@ -302,6 +302,73 @@ __device__ __forceinline__ void var_sample(const VarTap& f, int c0, int C, size_
     for (int u = 0; u < U; ++u) out[u] = blend4(nw[u], ne[u], sw[u], se[u], f.t);
 }
 
+// CMAX >= C: every warped view is sampled ONCE -- its C channel values stay in registers for the softmax (max, sum of
+// exponentials, the probabilities themselves), and the per-channel sum / sum of squares over the views are register
+// arrays too.  CMAX = 64 costs ~200 registers (one block per SM) but a third of the taps and half of the exponentials of
+// the chunked version below, which remains for C > 64.
+template <int CMAX>
+__global__ void __launch_bounds__(256)
+variance_volume_reg_kernel(const VarArgs a)
+{
+    constexpr int U = 8;
+    static_assert(CMAX % U == 0, "chunks of 8 channels");
+    const size_t HW = (size_t)a.H * a.W;
+    const size_t total = (size_t)a.B * a.D * HW;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int x = (int)(idx % a.W);
+    const int y = (int)((idx / a.W) % a.H);
+    const int d = (int)((idx / HW) % a.D);
+    const int b = (int)(idx / (HW * a.D));
+    const int C = a.C;
+    const GridNorm gn = make_grid_norm(a.H, a.W);
+    const float depth = a.per_pixel ? __ldg(a.hypos + ((size_t)b * a.D + d) * HW + (size_t)y * a.W + x)
+                                    : __ldg(a.hypos + (size_t)b * a.D + d);
+    float s1[CMAX], s2[CMAX];
+    const float* ref = a.fea.p[0] + (size_t)b * C * HW + (size_t)y * a.W + x;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+        const float rv = c < C ? __ldg(ref + (size_t)c * HW) : 0.0f;        // the raw reference feature (homoaggregate.py:56-57)
+        s1[c] = rv;
+        s2[c] = rv * rv;
+    }
+    for (int v = 0; v < a.V; ++v) {
+        const VarTap f = var_tap(a, v, b, x, y, depth, gn);
+        float val[CMAX];
+#pragma unroll
+        for (int c0 = 0; c0 < CMAX; c0 += U) {
+            float chunk[U];
+            var_sample<U>(f, c0, C, HW, a.W, chunk);
+#pragma unroll
+            for (int u = 0; u < U; ++u) val[c0 + u] = chunk[u];
+        }
+        float m = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c)
+            if (c < C) m = fmaxf(m, val[c]);
+        float s = 0.0f;
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c)
+            if (c < C) { val[c] = expf(val[c] - m); s += val[c]; }          // channel order, as the chunked kernel
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c)
+            if (c < C) {
+                const float pr = val[c] / s;
+                s1[c] += pr;
+                s2[c] = fmaf(pr, pr, s2[c]);
+            }
+    }
+    const float nviews = (float)(a.V + 1);
+    float* o = a.out + (((size_t)b * C * a.D + d) * a.H + y) * a.W + x;
+    const size_t ostride = (size_t)a.D * HW;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+        if (c < C) {
+            const float mean = s1[c] / nviews;
+            __stcs(o + (size_t)c * ostride, s2[c] / nviews - mean * mean);
+        }
+}
+
 __global__ void __launch_bounds__(256)
 variance_volume_kernel(const VarArgs a)
 {
@@ -631,7 +698,11 @@ int mdf_variance_volume_fwd(const float* const* features, int N, const float* re
     a.rt = rt; a.hypos = depth_hypos; a.out = cost_volume;
     a.per_pixel = hypos_per_pixel; a.V = N - 1; a.B = B; a.C = C; a.D = D; a.H = H; a.W = W;
     const size_t total = (size_t)B * D * H * W;
-    variance_volume_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(a);
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    if (C <= 16) variance_volume_reg_kernel<16><<<blocks, 256, 0, stream>>>(a);
+    else if (C <= 32) variance_volume_reg_kernel<32><<<blocks, 256, 0, stream>>>(a);
+    else if (C <= 64) variance_volume_reg_kernel<64><<<blocks, 256, 0, stream>>>(a);
+    else variance_volume_kernel<<<blocks, 256, 0, stream>>>(a);
     return launch_status();
 }
 

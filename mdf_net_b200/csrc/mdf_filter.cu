@@ -110,14 +110,6 @@ __device__ __forceinline__ void mat34v(const float* __restrict__ m, const float 
         o[r] = __fadd_rn(__fmaf_rn(m[r * 4 + 2], v[2], __fmaf_rn(m[r * 4 + 1], v[1], __fmul_rn(m[r * 4], v[0]))), m[r * 4 + 3]);
 }
 
-// a / b, correctly rounded: the reciprocal + residual-correction sequence of mdf_common.cuh (what nvcc emits for the
-// fast path of __fdiv_rn) when the operands are in the range where it is exact, the IEEE division otherwise.  `rb` is
-// refine_rcp(b), shared between the divisions by the same b.
-__device__ __forceinline__ float div_shared(float a, float b, float rb)
-{
-    return (range_ok(b) && fabsf(a) < 1.0e30f && fabsf(a) > 1.0e-30f) ? div_by(a, b, rb) : __fdiv_rn(a, b);
-}
-
 // grid_sample(bilinear, zeros, align_corners=True) through bilinear_sampler's normalisation (data_io.py:121-125)
 __device__ __forceinline__ float sample_depth_ac(const float* __restrict__ img, int H, int W, float px, float py,
                                                  float r_wm1, float r_hm1)

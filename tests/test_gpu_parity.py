@@ -256,6 +256,23 @@ def test_variance_aggregate_golden(name):
     assert_cost_close(out.cpu().numpy(), z["cost_volume"], name)
 
 
+@pytest.mark.parametrize("C", [12, 32, 64, 72])
+def test_variance_aggregate_channel_counts_vs_oracle(C):
+    """The register-resident kernels (C <= 16 / 32 / 64, incl. a count that is not a multiple of 8) and the chunked
+    kernel (C > 64) against the oracle."""
+    import mdf_net_b200 as mdf
+    from oracle import c_oracle as co
+    B, N, D, H, W = 2, 4, 5, 20, 28
+    K, E = syn.camera_rig(B, N, 8 * H, 8 * W, seed=77)
+    P = syn.projection_matrices(K, E, level_div=8.0)
+    feats = syn.smooth_features(B, N, C, H, W, seed=78)
+    hyp = syn.pixel_hypos(B, D, H, W, seed=79)
+    out = mdf.homo_aggregate_by_variance([cu(f) for f in feats], cu(P[:, 0]), [cu(P[:, v]) for v in range(1, N)], cu(hyp))
+    ref = co.variance_aggregate(feats, hyp, ref_proj=P[:, 0], src_projs=[P[:, v] for v in range(1, N)])
+    assert out.shape == (B, C, D, H, W)
+    assert_cost_close(out.cpu().numpy(), ref, f"variance C={C}")
+
+
 # --------------------------------------------------------------------------------------------- head
 @pytest.mark.parametrize("name", ["head_d48", "head_d24", "head_d8"])
 def test_head_golden(name):
