@@ -291,7 +291,7 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
     const float fcw = __ldg(a.dwp + 2), fcb = __ldg(a.dwp + 3);
     float w_void_view = 0.0f;                    // MODE 2: weight of an out-of-image sample of the view being prepared
     float wvoid[MODE == 2 ? PT : 1];             // MODE 2: sum over the views of those weights, per plane
-    double zs1 = 0.0, zs2 = 0.0;                 // MODE 1: sum z, sum z^2 of the samples this thread gathered for one view
+    float zs1 = 0.0f, zs2 = 0.0f;                // MODE 1: sum z, sum z^2 of the (at most PT) samples this thread gathered for one view
     __shared__ double stats_s[MODE == 1 ? 2 * kMaxSrcViews : 2];
     if (MODE == 2) {
 #pragma unroll
@@ -308,10 +308,12 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
     };
     auto flush_stats = [&](int v) {
         if (MODE == 1) {
+            // a thread's handful of samples in float, everything beyond that (32 lanes, the CTA, the grid) in double
+            double d1 = (double)zs1, d2 = (double)zs2;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { zs1 += __shfl_xor_sync(0xffffffffu, zs1, o); zs2 += __shfl_xor_sync(0xffffffffu, zs2, o); }
-            if (lane == 0 && (zs1 != 0.0 || zs2 != 0.0)) { atomicAdd(&stats_s[2 * v], zs1); atomicAdd(&stats_s[2 * v + 1], zs2); }
-            zs1 = 0.0; zs2 = 0.0;
+            for (int o = 16; o > 0; o >>= 1) { d1 += __shfl_xor_sync(0xffffffffu, d1, o); d2 += __shfl_xor_sync(0xffffffffu, d2, o); }
+            if (lane == 0 && (d1 != 0.0 || d2 != 0.0)) { atomicAdd(&stats_s[2 * v], d1); atomicAdd(&stats_s[2 * v + 1], d2); }
+            zs1 = 0.0f; zs2 = 0.0f;
         }
     };
 
@@ -440,7 +442,7 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
                 z2 = __ffma2_rn(make_float2(c.z, c.w), p23, z2);
             }
             const float z = z2.x + z2.y;
-            if (MODE == 1) { zs1 += (double)z; zs2 += (double)z * (double)z; continue; }     // statistics pass: z is all it wants
+            if (MODE == 1) { zs1 += z; zs2 = fmaf(z, z, zs2); continue; }     // statistics pass: z is all it wants
             float h = fmaf(z, alpha, betap);              // BatchNorm3d (eval fold, or this view's batch statistics)
             h = fmaxf(h, 0.0f);                           // ReLU
             h = fmaf(h, fcw, fcb);                        // Conv3d(1,1,1)
