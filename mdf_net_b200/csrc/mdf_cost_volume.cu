@@ -144,7 +144,7 @@ cost_volume_direct_kernel(const DirectArgs a)
 // weights once, then walks the C channel planes.  The op is bound by writing the (B,C,D,H,W) volume (354 MB per
 // call at BASELINE configs[1]): the channel loop is unrolled by 8 so that 32 independent tap loads (L1 / L2 hits:
 // neighbouring lanes read neighbouring texels) are in flight per thread and the stores -- 128-byte rows per warp,
-// written once with a streaming hint -- keep HBM busy.  Warps whose 32 footprints are all inside the source map
+// written once (plain stores: a streaming hint measured 7 % slower, 16 channels in flight 14 % slower) -- keep HBM busy.  Warps whose 32 footprints are all inside the source map
 // (the common case) take a path without bounds predicates.
 // ------------------------------------------------------------------------------------------------
 template <bool INTERIOR, bool SHARE>
@@ -175,7 +175,7 @@ __device__ __forceinline__ void warp_channels(const float* __restrict__ p, float
             }
             if (live) {
 #pragma unroll
-                for (int u = 0; u < U; ++u) __stcs(po + (size_t)u * ostride, blend4(nw[u], ne[u], sw[u], se[u], t));
+                for (int u = 0; u < U; ++u) po[(size_t)u * ostride] = blend4(nw[u], ne[u], sw[u], se[u], t);
             }
             po += (size_t)U * ostride;
         }
