@@ -206,7 +206,7 @@ __device__ __forceinline__ void warp_channels(const float* __restrict__ p, float
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            if (live && c0 + u < C) __stcs(po, blend4(nw[u], ne[u], sw[u], se[u], t));
+            if (live && c0 + u < C) *po = blend4(nw[u], ne[u], sw[u], se[u], t);
             po += ostride;
         }
     }
@@ -365,7 +365,7 @@ variance_volume_reg_kernel(const VarArgs a)
     for (int c = 0; c < CMAX; ++c)
         if (c < C) {
             const float mean = s1[c] / nviews;
-            __stcs(o + (size_t)c * ostride, s2[c] / nviews - mean * mean);
+            o[(size_t)c * ostride] = s2[c] / nviews - mean * mean;
         }
 }
 
@@ -437,7 +437,7 @@ variance_volume_kernel(const VarArgs a)
         for (int u = 0; u < U; ++u) {
             if (c0 + u >= a.C) break;
             const float mean = s1[u] / nviews;
-            __stcs(o + (size_t)(c0 + u) * ostride, s2[u] / nviews - mean * mean);
+            o[(size_t)(c0 + u) * ostride] = s2[u] / nviews - mean * mean;
         }
     }
 }
