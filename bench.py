@@ -387,7 +387,7 @@ def run_b200(args, workload, out):
         depths, conf = [], None
         for s, st in enumerate(view):
             if kernel_events is not None:      # events around the hot kernel alone, recorded inside the library
-                _cabi.lib().mdf_debug_time_next_hot_kernel(kernel_events[s][0].cuda_event, kernel_events[s][1].cuda_event)
+                ops.time_next_hot_kernel(kernel_events[s][0], kernel_events[s][1])
             if events is not None:
                 events[s][0].record()
             cv = ops.cost_volume(st["features"], st["ref_proj"], st["src_projs"], st["hypos"], *st["w"][:5], st["eps"],

@@ -17,8 +17,10 @@
  *
  * Conventions:
  *   - all tensors float32, contiguous, NCHW / NCDHW (W fastest), DEVICE pointers unless noted;
- *   - the library allocates nothing and keeps no global state: the caller owns inputs, outputs and
- *     the scratch `workspace` (size from the *_workspace_bytes query, 256-byte aligned);
+ *   - the library allocates nothing and keeps no state between calls (the one exception is errno-like: the
+ *     cudaError_t behind the calling thread's last MDF_ERR_CUDA, mdf_last_cuda_error): the caller owns inputs,
+ *     outputs and the scratch `workspace` (size from the *_workspace_bytes query, 256-byte aligned);
+ *   - test / benchmark / tuning entry points live in mdf_b200_debug.h, not here;
  *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant, and runs
  *     on the device that owns the output pointer; nothing synchronises the device;
  *   - return value: MDF_OK or a negative status; no exceptions, no exit().  There is NO CPU
@@ -95,17 +97,6 @@ MDF_API int mdf_cost_volume_fwd(const float *const *features,   /* HOST array of
                         void *workspace, size_t workspace_bytes,
                         mdf_stream_t stream);
 
-/* Same op, algorithm selection for tests/benchmarks: 0 = auto, 1 = staged (TMA box) kernel,
- * 2 = direct kernel (any C/G, taps straight from the NCHW features), 16 + k = staged kernel, tuning
- * variant k (tile / slab / box shapes; MDF_ERR_UNSUPPORTED when k does not exist). */
-MDF_API int mdf_cost_volume_fwd_ex(const float *const *features, int N, const float *ref_proj,
-                           const float *const *src_projs, const float *depth_hypos, int hypos_per_pixel,
-                           const float *conv_weight, const float *bn_weight, const float *bn_bias,
-                           const float *bn_mean, const float *bn_var, float bn_eps,
-                           const float *fc_weight, const float *fc_bias,
-                           int B, int C, int G, int D, int H, int W, float *cost_volume,
-                           void *workspace, size_t workspace_bytes, int algo, mdf_stream_t stream);
-
 /* ---- VectorAggregate under autograd / in train mode (C == 2*G, G in {8,16,32}) ---------------
  * Reference: net/unit/homoaggregate.py:25-46 driven by torch autograd (train.py:33-50).
  * training != 0: BatchNorm3d uses the batch statistics of each source view's z over (B,D,H,W) (the module is
@@ -176,12 +167,6 @@ MDF_API int mdf_prob_head_fwd(const float *x, const float *prob_weight, const fl
                               int B, int C, int D, int H, int W, float *logits, float *prob, float *depth,
                               float *confidence, int conf_n, int conf_pad_front, int conf_pad_back, int conf_upsample,
                               int curve, float *s, mdf_stream_t stream);
-/* algo: 0 = default, 1.. = alternative tile / depth-slab shapes of the same kernel (tools/time_prob_head.py). */
-MDF_API int mdf_prob_head_fwd_ex(const float *x, const float *prob_weight, const float *depth_hypos, int hypos_per_pixel,
-                                 int B, int C, int D, int H, int W, float *logits, float *prob, float *depth,
-                                 float *confidence, int conf_n, int conf_pad_front, int conf_pad_back, int conf_upsample,
-                                 int curve, float *s, int algo, mdf_stream_t stream);
-
 MDF_API int mdf_depth_regression_fwd(const float *prob, const float *depth_hypos, int hypos_per_pixel,
                              int B, int D, int H, int W, float *depth, mdf_stream_t stream);
 
@@ -221,20 +206,6 @@ MDF_API int mdf_geo_filter_fwd(const float *ref_depth, const float *ref_intrinsi
                                float thre1, float thre2, uint16_t *src_bits, float *depth_reprojected,
                                float *depth_averaged, uint8_t *geo_mask, uint8_t *photo_mask, uint8_t *final_mask,
                                void *workspace, size_t workspace_bytes, mdf_stream_t stream);
-
-/* ---- diagnostics --------------------------------------------------------------------------- */
-/* Sample positions (pixel units of the source map, as grid_sample uses them: base.py:102-119 +
- * ATen unnormalize) of every (d, y, x) for one precomposed projection `rot_trans` (12 floats:
- * rot row-major, then trans), computed with the hot kernel's division-free coordinate chain.
- * Exists so that the parity tests can pin that chain bit for bit; no product path calls it. */
-MDF_API int mdf_debug_sample_positions(const float *rot_trans, const float *depth_hypos, int hypos_per_pixel,
-                                       int D, int H, int W, float *ix /* (D,H,W) */, float *iy /* (D,H,W) */,
-                                       mdf_stream_t stream);
-
-/* The next mdf_cost_volume_fwd[_ex] call of the calling thread that takes the staged path records the two
- * cudaEvent_t around its hot kernel (cost_volume_staged_kernel) only -- not around the layout pass -- and
- * then forgets them.  bench.py uses it for the live per-kernel roofline numbers.  Pass NULL, NULL to cancel. */
-MDF_API int mdf_debug_time_next_hot_kernel(void *start_event, void *stop_event);
 
 #ifdef __cplusplus
 }

@@ -11,7 +11,7 @@ import os
 import threading
 from ctypes import c_char_p, c_float, c_int, c_size_t, c_void_p
 
-from .build import LIB_PATH
+from .build import LIB_PATH, TUNING_LIB_PATH
 
 _lock = threading.Lock()
 _lib = None
@@ -32,7 +32,7 @@ SIGNATURES = {
     "mdf_cost_volume_fwd": (_I, [_P, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P, c_float, _P, _P,
                                  _I, _I, _I, _I, _I, _I, _P, _P, c_size_t, _P]),
     "mdf_cost_volume_fwd_ex": (_I, [_P, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P, c_float, _P, _P,
-                                    _I, _I, _I, _I, _I, _I, _P, _P, c_size_t, _I, _P]),
+                                    _I, _I, _I, _I, _I, _I, _P, _P, c_size_t, _I, _P, _P, _P]),
     "mdf_variance_volume_workspace_bytes": (c_size_t, [_I] * 6),
     "mdf_variance_volume_fwd": (_I, [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, c_size_t, _P]),
     "mdf_softmax_regress_fwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P]),
@@ -51,9 +51,10 @@ SIGNATURES = {
     "mdf_geo_filter_workspace_bytes": (c_size_t, [_I]),
     "mdf_geo_filter_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, c_float, _I, c_float, c_float, _P, _P, _P, _P, _P, _P,
                                 _P, c_size_t, _P]),
-    "mdf_debug_time_next_hot_kernel": (_I, [_P, _P]),
     "mdf_debug_sample_positions": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
 }
+# only exported by the tuning build (MDF_B200_TUNING=1 in the environment makes tools/ load it instead of the product)
+TUNING_SIGNATURES = {"mdf_debug_read_trace": (_I, [_P, _I])}
 
 
 class MdfError(RuntimeError):
@@ -68,12 +69,13 @@ def lib() -> ctypes.CDLL:
     if _lib is None:
         with _lock:
             if _lib is None:
-                if not os.path.exists(LIB_PATH):
+                path = TUNING_LIB_PATH if os.environ.get("MDF_B200_TUNING") == "1" else LIB_PATH
+                if not os.path.exists(path):
                     raise ImportError(
-                        f"{LIB_PATH} not found: the sm_100a library is the only implementation of this "
+                        f"{path} not found: the sm_100a library is the only implementation of this "
                         "package (no CPU / PyTorch fallback). Build it with `python -m mdf_net_b200.build`.")
-                handle = ctypes.CDLL(LIB_PATH)
-                for name, (res, args) in SIGNATURES.items():
+                handle = ctypes.CDLL(path)
+                for name, (res, args) in {**SIGNATURES, **TUNING_SIGNATURES}.items():
                     try:
                         fn = getattr(handle, name)
                     except AttributeError:

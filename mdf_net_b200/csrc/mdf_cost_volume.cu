@@ -17,15 +17,18 @@
 #include <limits.h>
 #include <stdint.h>
 
+#include "../../include/mdf_b200_debug.h"
 #include "mdf_common.cuh"
 #include "mdf_host.cuh"
 #include "mdf_setup.cuh"
 #include "mdf_staged.cuh"
+#ifdef MDF_TUNING
+#include "experimental/mdf_pipe.cuh"
+#endif
 
 namespace mdf {
 
-thread_local int g_last_cuda_error = 0;
-thread_local cudaEvent_t g_time_events[2] = {nullptr, nullptr};
+thread_local int g_last_cuda_error = 0;     // errno-like: the code behind the last MDF_ERR_CUDA of this thread
 
 // ------------------------------------------------------------------------------------------------
 // workspace layout (all offsets 256-byte aligned)
@@ -147,15 +150,11 @@ cost_volume_direct_kernel(const DirectArgs a)
 // written once (plain stores: a streaming hint measured 7 % slower, 16 channels in flight 14 % slower) -- keep HBM busy.  Warps whose 32 footprints are all inside the source map
 // (the common case) take a path without bounds predicates.
 // ------------------------------------------------------------------------------------------------
-template <bool INTERIOR, bool SHARE>
+template <bool INTERIOR>
 __device__ __forceinline__ void warp_channels(const float* __restrict__ p, float* __restrict__ o, int C, size_t HW, size_t ostride,
                                               int W, const Taps& t, bool x0in, bool x1in, bool y0in, bool y1in, bool live)
 {
-    // SHARE (all 32 footprints inside the map, lane i+1's cell is the right-hand neighbour of lane i's): the east
-    // taps of a lane are the west taps of the next lane -- two loads + two shuffles per channel instead of four
-    // loads (the L1 data pipe is the co-limit of this kernel); lane 31 loads its own east taps.
     constexpr int U = 8;
-    const bool last = (threadIdx.x & 31) == 31;
     // running pointers (north row, south row, output), advanced by one plane per channel: the loads use immediate
     // offsets and the loop carries no 64-bit multiplications (the first version spent more issue slots on address
     // arithmetic than on the taps)
@@ -163,7 +162,7 @@ __device__ __forceinline__ void warp_channels(const float* __restrict__ p, float
     const float* __restrict__ ps = p + W;
     float* __restrict__ po = o;
     int c0 = 0;
-    if (INTERIOR && !SHARE) {
+    if (INTERIOR) {
         // full chunks of U channels, no predicate anywhere: 4*U loads, then U blends and stores
         for (; c0 + U <= C; c0 += U) {
             float nw[U], ne[U], sw[U], se[U];
@@ -187,22 +186,10 @@ __device__ __forceinline__ void warp_channels(const float* __restrict__ p, float
             const bool on = c0 + u < C;
             nw[u] = (on && (INTERIOR || (x0in && y0in))) ? __ldg(pn) : 0.0f;
             sw[u] = (on && (INTERIOR || (x0in && y1in))) ? __ldg(ps) : 0.0f;
-            if (SHARE) {
-                ne[u] = (on && last) ? __ldg(pn + 1) : 0.0f;
-                se[u] = (on && last) ? __ldg(ps + 1) : 0.0f;
-            } else {
-                ne[u] = (on && (INTERIOR || (x1in && y0in))) ? __ldg(pn + 1) : 0.0f;
-                se[u] = (on && (INTERIOR || (x1in && y1in))) ? __ldg(ps + 1) : 0.0f;
-            }
+            ne[u] = (on && (INTERIOR || (x1in && y0in))) ? __ldg(pn + 1) : 0.0f;
+            se[u] = (on && (INTERIOR || (x1in && y1in))) ? __ldg(ps + 1) : 0.0f;
             pn += HW;
             ps += HW;
-        }
-        if (SHARE) {
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const float a = __shfl_down_sync(0xffffffffu, nw[u], 1), b = __shfl_down_sync(0xffffffffu, sw[u], 1);
-                if (!last) { ne[u] = a; se[u] = b; }
-            }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -237,16 +224,8 @@ homo_warp_kernel(const float* __restrict__ src, const float* __restrict__ rt_all
     const float* p = src + (size_t)b * C * HW + (ptrdiff_t)t.y0 * W + t.x0;
     float* o = out + (((size_t)b * C * D + d) * H + y) * W + x;
     const size_t ostride = (size_t)D * HW;
-    // is lane i+1's cell the right-hand neighbour of mine?  (lane 31 has no successor in the warp)
-    const int nx0 = __shfl_down_sync(0xffffffffu, t.x0, 1), ny0 = __shfl_down_sync(0xffffffffu, t.y0, 1);
-    const bool chained = (threadIdx.x & 31) == 31 || (nx0 == t.x0 + 1 && ny0 == t.y0);
-    if (__all_sync(0xffffffffu, interior)) {
-        // (sharing the east taps between neighbouring lanes by shuffle -- the SHARE variant -- measured slower: 192 vs 160 us)
-        (void)chained;
-        warp_channels<true, false>(p, o, C, HW, ostride, W, t, true, true, true, true, live);
-    } else {
-        warp_channels<false, false>(p, o, C, HW, ostride, W, t, x0in, x1in, y0in, y1in, live);
-    }
+    if (__all_sync(0xffffffffu, interior)) warp_channels<true>(p, o, C, HW, ostride, W, t, true, true, true, true, live);
+    else warp_channels<false>(p, o, C, HW, ostride, W, t, x0in, x1in, y0in, y1in, live);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -518,7 +497,7 @@ int mdf_cost_volume_fwd_ex(const float* const* features, int N, const float* ref
                            const float* bn_weight, const float* bn_bias, const float* bn_mean, const float* bn_var,
                            float bn_eps, const float* fc_weight, const float* fc_bias, int B, int C, int G, int D,
                            int H, int W, float* cost_volume, void* workspace, size_t workspace_bytes, int algo,
-                           mdf_stream_t stream_)
+                           void* hot_start_event, void* hot_stop_event, mdf_stream_t stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (B < 0 || C <= 0 || G <= 0 || D < 0 || H < 0 || W < 0 || N < 2 || C % G != 0) return MDF_ERR_INVALID_SHAPE;
@@ -528,9 +507,17 @@ int mdf_cost_volume_fwd_ex(const float* const* features, int N, const float* ref
         !bn_var || !fc_weight || !fc_bias || !cost_volume)
         return MDF_ERR_NULL_POINTER;
     const int V = N - 1;
-    const bool staged = staged_supported(C, G) && algo != 2;
+    // the staged path needs the grid of its layout pass and its tensor maps to stay in range; beyond that the direct kernel
+    // serves the call when the caller did not insist on the staged one
+    const bool staged_fits = (long long)H * W <= INT_MAX - 256 && (long long)N * B <= 65535 && (long long)V * B <= 256;
+    if (algo == 1 && !staged_fits) return MDF_ERR_UNSUPPORTED;
+    const bool staged = staged_supported(C, G) && algo != 2 && staged_fits;
     if ((algo == 1 || algo >= 16) && !staged) return MDF_ERR_UNSUPPORTED;
     if (algo < 0 || (algo > 2 && algo < 16)) return MDF_ERR_UNSUPPORTED;
+#ifndef MDF_TUNING
+    if (algo >= 16) return MDF_ERR_UNSUPPORTED;      // tuning variants exist in tuning builds only
+#endif
+    if ((hot_start_event == nullptr) != (hot_stop_event == nullptr)) return MDF_ERR_NULL_POINTER;
     const Workspace ws = make_workspace(B, N, G, H, W, staged);
     if (!workspace || ((uintptr_t)workspace & 255) != 0 || workspace_bytes < ws.total) return MDF_ERR_WORKSPACE;
 
@@ -564,6 +551,7 @@ int mdf_cost_volume_fwd_ex(const float* const* features, int N, const float* ref
         a.rt = rt; a.dwp = dwp; a.conv_w = conv_weight; a.hypos = depth_hypos; a.out = cost_volume;
         a.per_pixel = hypos_per_pixel; a.V = V; a.B = B; a.C = C; a.G = G; a.D = D; a.H = H; a.W = W;
         const size_t total = (size_t)B * D * H * W;
+        if ((total + 255) / 256 > 0x7fffffffull) return MDF_ERR_UNSUPPORTED;
         cost_volume_direct_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(a);
         return launch_status();
     }
@@ -575,7 +563,6 @@ int mdf_cost_volume_fwd_ex(const float* const* features, int N, const float* ref
         FeaPtrs fp;
         for (int i = 0; i < MDF_MAX_VIEWS; ++i) fp.p[i] = i < N ? features[i] : nullptr;
         const long long HW = (long long)H * W;
-        if (HW > INT_MAX - 256 || (long long)N * B > 65535 || (long long)V * B > 256) return MDF_ERR_UNSUPPORTED;
         PrepSetup su;
         for (int v = 0; v < kMaxSrcViews; ++v) su.src_projs.p[v] = v < V ? src_projs[v] : nullptr;
         su.ref_proj = ref_proj; su.V = V; su.rt = rt; su.dwp = dwp;
@@ -590,7 +577,14 @@ int mdf_cost_volume_fwd_ex(const float* const* features, int N, const float* ref
     a.tiles_x = a.tiles_y = a.slabs = 0;
     StagedBuffers buf;
     buf.S4 = reinterpret_cast<const float*>(S4); buf.Q4 = reinterpret_cast<const float*>(Q4); buf.CQ4 = reinterpret_cast<const float*>(CQ4);
-    return launch_staged_variant(G, algo >= 16 ? algo - 16 : 0, a, buf, stream);
+    HotEvents ev;
+    ev.start = (cudaEvent_t)hot_start_event; ev.stop = (cudaEvent_t)hot_stop_event;
+#ifdef MDF_TUNING
+    // 32 + k (+ 256 * rounds per item): variant k of the experimental pipelined kernel; 16 + k: staged variant k
+    if ((algo & 255) >= 32) return launch_pipe_variant(G, (algo & 255) - 32, algo >> 8, a, buf, stream, ev);
+    if (algo >= 16) return launch_staged_variant(G, algo - 16, a, buf, stream, ev);
+#endif
+    return launch_staged_default<0>(G, a, buf, stream, ev);
 }
 
 int mdf_cost_volume_fwd(const float* const* features, int N, const float* ref_proj, const float* const* src_projs,
@@ -601,16 +595,23 @@ int mdf_cost_volume_fwd(const float* const* features, int N, const float* ref_pr
 {
     return mdf_cost_volume_fwd_ex(features, N, ref_proj, src_projs, depth_hypos, hypos_per_pixel, conv_weight, bn_weight,
                                   bn_bias, bn_mean, bn_var, bn_eps, fc_weight, fc_bias, B, C, G, D, H, W, cost_volume,
-                                  workspace, workspace_bytes, 0, stream);
+                                  workspace, workspace_bytes, 0, nullptr, nullptr, stream);
 }
 
-int mdf_debug_time_next_hot_kernel(void* start_event, void* stop_event)
+#ifdef MDF_TUNING
+// diagnostic: copy the phase timestamps of the last traced launch (StagedCfg::TRACE variants) to the host and reset them
+int mdf_debug_read_trace(long long* host_dst, int max_slots)
 {
-    if ((start_event == nullptr) != (stop_event == nullptr)) return MDF_ERR_NULL_POINTER;
-    g_time_events[0] = (cudaEvent_t)start_event;
-    g_time_events[1] = (cudaEvent_t)stop_event;
-    return MDF_OK;
+    unsigned n = 0;
+    if (cudaMemcpyFromSymbol(&n, g_trace_count, sizeof(n)) != cudaSuccess) return -1;
+    if ((int)n > max_slots) n = max_slots;
+    if (n > (unsigned)kTraceSlots) n = kTraceSlots;
+    if (n && cudaMemcpyFromSymbol(host_dst, g_trace, (size_t)n * kTraceWords * sizeof(long long)) != cudaSuccess) return -1;
+    unsigned zero = 0;
+    cudaMemcpyToSymbol(g_trace_count, &zero, sizeof(zero));
+    return (int)n;
 }
+#endif
 
 int mdf_debug_sample_positions(const float* rot_trans, const float* depth_hypos, int hypos_per_pixel, int D, int H, int W,
                                float* ix, float* iy, mdf_stream_t stream)
@@ -656,6 +657,7 @@ int mdf_homo_warp_fwd(const float* src_fea, const float* src_proj, const float* 
     st = run_setup(sp, ref_proj, 1, B, rt, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f, nullptr, nullptr, 0, nullptr, stream);
     if (st != MDF_OK) return st;
     const size_t total = (size_t)B * D * H * W;
+    if ((total + 255) / 256 > 0x7fffffffull) return MDF_ERR_UNSUPPORTED;
     homo_warp_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(src_fea, rt, depth_hypos, hypos_per_pixel, B, C, D, H, W, warped);
     return launch_status();
 }
@@ -698,6 +700,7 @@ int mdf_variance_volume_fwd(const float* const* features, int N, const float* re
     a.rt = rt; a.hypos = depth_hypos; a.out = cost_volume;
     a.per_pixel = hypos_per_pixel; a.V = N - 1; a.B = B; a.C = C; a.D = D; a.H = H; a.W = W;
     const size_t total = (size_t)B * D * H * W;
+    if ((total + 255) / 256 > 0x7fffffffull) return MDF_ERR_UNSUPPORTED;
     const unsigned blocks = (unsigned)((total + 255) / 256);
     if (C <= 16) variance_volume_reg_kernel<16><<<blocks, 256, 0, stream>>>(a);
     else if (C <= 32) variance_volume_reg_kernel<32><<<blocks, 256, 0, stream>>>(a);

@@ -23,6 +23,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/mdf_b200_debug.h"
 #include "mdf_common.cuh"
 #include "mdf_host.cuh"
 #include "mdf_tail.cuh"

@@ -166,10 +166,12 @@ static inline unsigned prep_zsplit(int threads_x, int images, int G)
 //   MINB   CTAs per SM the register allocation aims at
 //   CQS    keep the per-pixel similarity weights cq_g = conv_w[g]*q_g in shared memory instead of registers
 // ------------------------------------------------------------------------------------------------
-template <int G_, int PT_, int TH_, int PG_, int BW_, int BH_, int MINB_, bool CQS_, bool EARLY_ = true>
+template <int G_, int PT_, int TH_, int PG_, int BW_, int BH_, int MINB_, bool CQS_, bool EARLY_ = true, bool BF_ = false, bool RCP2_ = false, bool TRACE_ = false, int ABL_ = 0>
 struct StagedCfg {
     static constexpr int G = G_, PT = PT_, TH = TH_, PG = PG_, BW = BW_, BH = BH_, MINB = MINB_;
-    static constexpr bool CQS = CQS_, EARLY = EARLY_;
+    static constexpr bool RCP2 = RCP2_, TRACE = TRACE_;
+    static constexpr int ABL = ABL_;   // ablation study (wrong results): 1 no MUFU, 2 no tap loads, 4 no stores, 8 cheap positions, 16 no cq loads
+    static constexpr bool CQS = CQS_, EARLY = EARLY_, BF = BF_;   // BF: branch-free sample bodies (samples of a thread interleave)
     static constexpr int J = G / 4;
     static constexpr int NCQ = CQS ? 1 : G;
     static constexpr int THREADS = 32 * TH * PG;
@@ -208,6 +210,13 @@ struct StagedMaps {
 
 constexpr int kNone = INT_MAX;
 
+// phase timestamps of a sample of CTAs (tuning builds only: StagedCfg::TRACE)
+constexpr int kTraceSlots = 4096, kTraceWords = 32;
+#ifdef MDF_TUNING
+__device__ long long g_trace[kTraceSlots * kTraceWords];
+__device__ unsigned g_trace_count;
+#endif
+
 // order-preserving integer key of a sample coordinate in (-1, size): negative -> -1, else its bit pattern
 __device__ __forceinline__ int coord_key(float v) { return v < 0.0f ? -1 : __float_as_int(v); }
 __device__ __forceinline__ int key_floor(int k) { return k < 0 ? -1 : (int)__int_as_float(k); }
@@ -235,6 +244,11 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
 
     const int lane = threadIdx.x, ty = threadIdx.y, pg = threadIdx.z;
     const int tid = lane + 32 * (ty + TH * pg);
+    long long tr[kTraceWords];
+    int trn = 0;
+    const bool tracing = Cfg::TRACE && lane == 0 && (blockIdx.x % 8) == 3;
+    auto stamp = [&]() { if (Cfg::TRACE) { if (trn < kTraceWords) tr[trn] = clock64(); ++trn; } };
+    stamp();                                     // 0: start
     const uint32_t q_s = box0 + Cfg::OFF_Q + (uint32_t)(ty * 32 + lane) * 16u;      // [j][ty][lane] float4
     const uint32_t cq_s = box0 + Cfg::OFF_CQ + (uint32_t)(ty * 32 + lane) * 16u;
     constexpr uint32_t TJ = TH * 32 * 16;                                           // plane stride of the tiles
@@ -327,7 +341,9 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
     }
     uint64_t n_void = 0;                         // 8 bits per plane: views whose sample fell outside the source image
     uint32_t left = 0;                           // bit v: some sample of mine did not fit view v's box
+    stamp();                                     // 1: hypotheses requested, before the first barrier
     __syncthreads();                             // rt_s, mbarriers and control words are set up
+    stamp();                                     // 2: after the first barrier
 
     // rot | trans of view v from shared memory (issued early, consumed by `positions`)
     auto load_rt = [&](int v, float (&rt)[12]) {
@@ -341,8 +357,13 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
         // all planes through the branch-free fast chain first (PT independent dependency chains in one basic
         // block); the IEEE chain only if some lane of the warp met an operand the fast divisions do not cover
         bool exact = !tiny_map;
+        if (Cfg::ABL & 8) {
+#pragma unroll
+            for (int i = 0; i < PT; ++i) { ix[i] = fmaf(depth[i], 0.002f, (float)px); iy[i] = fmaf(r.x, 1e-9f, (float)py + 0.25f); }
+        } else {
 #pragma unroll
         for (int i = 0; i < PT; ++i) exact = sample_position_try(r, rt, depth[i], gf, ix[i], iy[i]) && exact;
+        }
         if (__any_sync(0xffffffffu, !exact)) {
 #pragma unroll
             for (int i = 0; i < PT; ++i) sample_position(r, rt, depth[i], gf.g, ix[i], iy[i]);
@@ -393,20 +414,26 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
 
     float cq[NCQ];
     float ksum = 0.0f;
+    auto ex2_approx = [](float x) -> float { return (Cfg::ABL & 1) ? fmaf(x, 0.5f, 1.0f) : mdf::ex2_approx(x); };
+    auto rcp_approx = [](float x) -> float { return (Cfg::ABL & 1) ? x * 0.25f : mdf::rcp_approx(x); };
     // gather the samples of `todo` that lie inside the box with origin (ox, oy); returns the rest
     auto gather = [&](uint32_t box, int ox, int oy, const float (&ix)[PT], const float (&iy)[PT], uint32_t todo) -> uint32_t {
 #pragma unroll
         for (int i = 0; i < PT; ++i) {
-            if (!((todo >> i) & 1u)) continue;
+            const bool act = (todo >> i) & 1u;
+            if (!Cfg::BF && !act) continue;
+            const float sx = (Cfg::BF && !act) ? 0.0f : ix[i], sy = (Cfg::BF && !act) ? 0.0f : iy[i];
             float fx0, fy0;
             int x0, y0;
-            floor_small(ix[i], fx0, x0);
-            floor_small(iy[i], fy0, y0);
-            const int rx = x0 - ox, ry = y0 - oy;
-            if ((unsigned)rx >= (unsigned)(BW - 1) || (unsigned)ry >= (unsigned)(BH - 1)) continue;   // not in this box
-            todo &= ~(1u << i);
-            const float ax = __fsub_rn(__fadd_rn(fx0, 1.0f), ix[i]), bx = __fsub_rn(ix[i], fx0);
-            const float ay = __fsub_rn(__fadd_rn(fy0, 1.0f), iy[i]), by = __fsub_rn(iy[i], fy0);
+            floor_small(sx, fx0, x0);
+            floor_small(sy, fy0, y0);
+            int rx = x0 - ox, ry = y0 - oy;
+            const bool inb = act && (unsigned)rx < (unsigned)(BW - 1) && (unsigned)ry < (unsigned)(BH - 1);
+            if (!Cfg::BF && !inb) continue;                       // not in this box
+            if (Cfg::BF && !inb) { rx = 0; ry = 0; }              // a harmless cell of the box; the sample's weight is zeroed below
+            if (inb) todo &= ~(1u << i);
+            const float ax = __fsub_rn(__fadd_rn(fx0, 1.0f), sx), bx = __fsub_rn(sx, fx0);
+            const float ay = __fsub_rn(__fadd_rn(fy0, 1.0f), sy), by = __fsub_rn(sy, fy0);
             const float wnw = __fmul_rn(ax, ay), wne = __fmul_rn(bx, ay), wsw = __fmul_rn(ax, by), wse = __fmul_rn(bx, by);
             const float2 Wnw = make_float2(wnw, wnw), Wne = make_float2(wne, wne);
             const float2 Wsw = make_float2(wsw, wsw), Wse = make_float2(wse, wse);
@@ -415,12 +442,19 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
             float2 z2 = make_float2(-ksum, 0.0f);
 #pragma unroll
             for (int j = 0; j < J; ++j) {
-                const float4 nw = lds128(addr + j * PLANE);                 // constant offsets -> LDS.128 [R + imm]
-                const float4 ne = lds128(addr + j * PLANE + 16);
-                const float4 sw = lds128(addr + j * PLANE + BW * 16);
-                const float4 se = lds128(addr + j * PLANE + BW * 16 + 16);
+                float4 nw, ne, sw, se;
+                if (Cfg::ABL & 2) {
+                    const float fa = __uint_as_float(addr + j);
+                    nw = make_float4(ax, bx, ay, fa); ne = make_float4(bx, ay, fa, ax); sw = make_float4(ay, fa, ax, bx); se = make_float4(fa, by, bx, ay);
+                } else {
+                    nw = lds128(addr + j * PLANE);                 // constant offsets -> LDS.128 [R + imm]
+                    ne = lds128(addr + j * PLANE + 16);
+                    sw = lds128(addr + j * PLANE + BW * 16);
+                    se = lds128(addr + j * PLANE + BW * 16 + 16);
+                }
                 float4 c;
-                if (Cfg::CQS) c = lds128(cq_s + (uint32_t)j * TJ);
+                if (Cfg::CQS && (Cfg::ABL & 16)) c = make_float4(ax, bx, ay, by);
+                else if (Cfg::CQS) c = lds128(cq_s + (uint32_t)j * TJ);
                 else c = make_float4(cq[(4 * j + 0) % NCQ], cq[(4 * j + 1) % NCQ], cq[(4 * j + 2) % NCQ], cq[(4 * j + 3) % NCQ]);
                 // bilinear blend, two groups per instruction; per component the reference's order
                 // fma(se,wse, fma(sw,wsw, fma(ne,wne, nw*wnw)))
@@ -432,21 +466,32 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
                 // beyond the cap the similarity is below 1e-18 either way.  One MUFU.RCP serves two groups:
                 // r = 1/(u0*u1), 1/u0 = r*u1, 1/u1 = r*u0.
                 const float2 one2 = make_float2(1.0f, 1.0f);
-                const float2 u01 = __fadd2_rn(make_float2(ex2_approx(fminf(t01.x, 62.0f)), ex2_approx(fminf(t01.y, 62.0f))), one2);
-                const float2 u23 = __fadd2_rn(make_float2(ex2_approx(fminf(t23.x, 62.0f)), ex2_approx(fminf(t23.y, 62.0f))), one2);
-                const float r01 = rcp_approx(u01.x * u01.y), r23 = rcp_approx(u23.x * u23.y);
-                const float2 p01 = __fmul2_rn(make_float2(r01, r01), make_float2(u01.y, u01.x));
-                const float2 p23 = __fmul2_rn(make_float2(r23, r23), make_float2(u23.y, u23.x));
+                float2 p01, p23;
+                if (Cfg::RCP2) {
+                    // one MUFU.RCP per group: 2^t = inf gives 1/inf = 0, no cap and no cross multiplications (the XU pipe has
+                    // room: it is a third busy, the issue slots are what the kernel runs out of)
+                    const float2 u01 = __fadd2_rn(make_float2(ex2_approx(t01.x), ex2_approx(t01.y)), one2);
+                    const float2 u23 = __fadd2_rn(make_float2(ex2_approx(t23.x), ex2_approx(t23.y)), one2);
+                    p01 = make_float2(rcp_approx(u01.x), rcp_approx(u01.y));
+                    p23 = make_float2(rcp_approx(u23.x), rcp_approx(u23.y));
+                } else {
+                    const float2 u01 = __fadd2_rn(make_float2(ex2_approx(fminf(t01.x, 62.0f)), ex2_approx(fminf(t01.y, 62.0f))), one2);
+                    const float2 u23 = __fadd2_rn(make_float2(ex2_approx(fminf(t23.x, 62.0f)), ex2_approx(fminf(t23.y, 62.0f))), one2);
+                    const float r01 = rcp_approx(u01.x * u01.y), r23 = rcp_approx(u23.x * u23.y);
+                    p01 = __fmul2_rn(make_float2(r01, r01), make_float2(u01.y, u01.x));
+                    p23 = __fmul2_rn(make_float2(r23, r23), make_float2(u23.y, u23.x));
+                }
                 p[2 * j] = p01; p[2 * j + 1] = p23;
                 z2 = __ffma2_rn(make_float2(c.x, c.y), p01, z2);
                 z2 = __ffma2_rn(make_float2(c.z, c.w), p23, z2);
             }
-            const float z = z2.x + z2.y;
+            const float z = (Cfg::BF && !inb) ? 0.0f : z2.x + z2.y;
             if (MODE == 1) { zs1 += z; zs2 = fmaf(z, z, zs2); continue; }     // statistics pass: z is all it wants
             float h = fmaf(z, alpha, betap);              // BatchNorm3d (eval fold, or this view's batch statistics)
             h = fmaxf(h, 0.0f);                           // ReLU
             h = fmaf(h, fcw, fcb);                        // Conv3d(1,1,1)
-            const float w = rcp_approx(1.0f + ex2_approx(-kLog2e * h));   // Sigmoid
+            float w = rcp_approx(1.0f + ex2_approx(-kLog2e * h));   // Sigmoid
+            if (Cfg::BF && !inb) w = 0.0f;
             wsum[i] += w;
             const float2 w2 = make_float2(w, w);
 #pragma unroll
@@ -463,8 +508,11 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
         set_void_view(0);
         todo = positions(rt, ix, iy, true);
     }
+    stamp();                                     // 3: positions of view 0 done (the hypotheses have arrived)
     announce(0, ix, iy, todo);
+    stamp();                                     // 4: announced
     mbar_wait(bar0 + 24, 0);                     // q / cq tiles have landed
+    stamp();                                     // 5: tiles landed
     {   // ksum = 0.5 * sum_g cq_g (z accumulates sum_g cq_g (p_g - 0.5)); cq stays in registers unless CQS
         float s4 = 0.0f;
 #pragma unroll
@@ -488,11 +536,14 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
             ntodo = positions(rt, nx, ny, true);
             announce(v + 1, nx, ny, ntodo);
         }
+        stamp();                                 // 6 + 3v: next view prepared, waiting for this view's box
         mbar_wait(bar0 + 8u * (v & 1), (uint32_t)(v >> 1) & 1u);
+        stamp();                                 // 7 + 3v: box landed
         const int ox = ctl[kOrg + 2 * v], oy = ctl[kOrg + 2 * v + 1];
         set_view(v);
         todo = gather(box0 + (uint32_t)(v & 1) * Cfg::BOX_BYTES, ox, oy, ix, iy, todo);
         flush_stats(v);
+        stamp();                                 // 8 + 3v: gathered
         if (todo != 0u) left |= 1u << v;
 #pragma unroll
         for (int i = 0; i < PT; ++i) { ix[i] = nx[i]; iy[i] = ny[i]; }
@@ -520,7 +571,7 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
                 const float4 q = lds128(q_s + (uint32_t)j * TJ);
                 const float2 o01 = __ffma2_rn(make_float2(q.x, q.y), __ffma2_rn(acc[i][2 * j], rw2, c02), half2);
                 const float2 o23 = __ffma2_rn(make_float2(q.z, q.w), __ffma2_rn(acc[i][2 * j + 1], rw2, c02), half2);
-                op[0] = o01.x; op[gstride] = o01.y; op[2 * gstride] = o23.x; op[3 * gstride] = o23.y;
+                if (!(Cfg::ABL & 4) || a.D < 0) { op[0] = o01.x; op[gstride] = o01.y; op[2 * gstride] = o23.x; op[3 * gstride] = o23.y; }
                 op += 4 * gstride;
             }
         }
@@ -530,6 +581,7 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
     // of the slower warps); the others write after the retry rounds.
     const bool early = MODE != 1 && Cfg::EARLY && __all_sync(0xffffffffu, left == 0u);
     if (early) epilogue();
+    stamp();                                     // early epilogue done
 
     // ---- samples that did not fit their view's box (rough depth maps, silhouettes): synchronous staging
     //      rounds.  x origin = min over the samples left; y origin = min over those whose column fits, so the
@@ -597,6 +649,19 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
         return;
     }
     if (!early) epilogue();
+    stamp();                                     // end
+#ifdef MDF_TUNING
+    if (tracing) {
+        const unsigned slot = atomicAdd(&g_trace_count, 1u);
+        if (slot < kTraceSlots) {
+            for (int k = 0; k < kTraceWords; ++k) g_trace[slot * kTraceWords + k] = k < trn ? tr[k] : 0;
+            g_trace[slot * kTraceWords + kTraceWords - 1] = ((long long)blockIdx.x << 8) | (ty + TH * pg);
+            g_trace[slot * kTraceWords + kTraceWords - 2] = trn;
+        }
+    }
+#else
+    (void)tracing;
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -621,11 +686,11 @@ static int encode_planes(CUtensorMap* tmap, const float* base, int W, int H, lon
 
 struct StagedBuffers { const float* S4; const float* Q4; const float* CQ4; };
 
-// diagnostic (mdf_debug_time_next_hot_kernel): events recorded around the next hot-kernel launch of this thread
-extern thread_local cudaEvent_t g_time_events[2];
+// optional timing hook of mdf_cost_volume_fwd_ex: two events recorded around the hot kernel alone
+struct HotEvents { cudaEvent_t start = nullptr, stop = nullptr; };
 
 template <class Cfg, int MODE = 0>
-static int launch_staged(const StagedArgs& args, const StagedBuffers& buf, cudaStream_t stream)
+static int launch_staged(const StagedArgs& args, const StagedBuffers& buf, cudaStream_t stream, const HotEvents& ev = HotEvents())
 {
     StagedMaps maps;
     int st = encode_planes(&maps.s4, buf.S4, args.W, args.H, (long long)args.V * args.B * Cfg::J, Cfg::BW, Cfg::BH, Cfg::J);
@@ -642,63 +707,88 @@ static int launch_staged(const StagedArgs& args, const StagedBuffers& buf, cudaS
     const long long items = (long long)a.tiles_x * a.tiles_y * a.slabs * a.B;
     if (items <= 0) return MDF_OK;
     if (items > INT_MAX) return MDF_ERR_UNSUPPORTED;
-    const bool timed = g_time_events[0] != nullptr;
-    if (timed) cudaEventRecord(g_time_events[0], stream);
+    if (ev.start) cudaEventRecord(ev.start, stream);
     kern<<<(unsigned)items, dim3(32, Cfg::TH, Cfg::PG), Cfg::SMEM, stream>>>(maps, a);
-    if (timed) { cudaEventRecord(g_time_events[1], stream); g_time_events[0] = g_time_events[1] = nullptr; }
+    if (ev.stop) cudaEventRecord(ev.stop, stream);
     return launch_status();
 }
 
-// Tuning variants per G (algo = 16 + k selects variant k; variant 0 is the default).
-//                         G  PT TH PG  BW  BH MINB CQS   EARLY
+// The product build ships ONE configuration per G (variant 0).  Tuning builds (-DMDF_TUNING) add the shape variants,
+// the diagnostic variants (branch-free samples, one reciprocal per group, phase timestamps, ablations) behind
+// algo = 16 + k: every one of them was measured within +-3 % of variant 0 or slower (profiles/r02_*).
+//                         G  PT TH PG  BW  BH MINB CQS
 using CfgG32_0 = StagedCfg<32, 1, 2, 4, 40, 6, 2, true>;     // 256 thr x 2 CTAs; tile 32x2, slab 4 planes; 2 x 30 KiB boxes + 2 x 8 KiB tiles
-using CfgG32_1 = StagedCfg<32, 1, 4, 2, 40, 7, 2, true>;     // tile 32x4, slab 2 planes
-using CfgG32_2 = StagedCfg<32, 1, 4, 2, 40, 7, 2, true, false>;
-using CfgG32_3 = StagedCfg<32, 1, 1, 8, 48, 4, 2, true>;     // tile 32x1, slab 8 planes
 using CfgG16_0 = StagedCfg<16, 2, 2, 4, 64, 6, 2, false>;    // 256 thr x 2 CTAs; tile 32x2, slab 8 planes; 2 x 24 KiB boxes
-using CfgG16_1 = StagedCfg<16, 2, 4, 2, 64, 8, 2, false>;    // tile 32x4, slab 4 planes
-using CfgG16_2 = StagedCfg<16, 2, 4, 2, 48, 8, 2, false>;    // narrower box
-using CfgG16_3 = StagedCfg<16, 2, 1, 8, 80, 4, 2, false>;    // tile 32x1, slab 16 planes
 using CfgG8_0  = StagedCfg<8, 4, 4, 2, 64, 10, 2, false>;    // 256 thr x 2 CTAs; tile 32x4, slab 8 planes; 2 x 20 KiB boxes
-using CfgG8_1  = StagedCfg<8, 4, 8, 1, 64, 14, 2, false>;    // tile 32x8, slab 4 planes
-using CfgG8_2  = StagedCfg<8, 2, 4, 2, 64, 10, 3, false>;    // 3 CTAs, slab 4 planes
-using CfgG8_3  = StagedCfg<8, 2, 2, 4, 64, 6, 3, false>;     // tile 32x2, slab 8 planes, 3 CTAs
 
-// the default configuration of a stage in training mode (MODE 1: batch statistics, MODE 2: per-view BatchNorm folds)
+// the configuration of a stage; MODE 1 / 2 = training (batch statistics / per-view BatchNorm folds)
+template <int MODE>
+static int launch_staged_default(int G, const StagedArgs& a, const StagedBuffers& S, cudaStream_t stream, const HotEvents& ev = HotEvents())
+{
+    if (G == 32) return launch_staged<CfgG32_0, MODE>(a, S, stream, ev);
+    if (G == 16) return launch_staged<CfgG16_0, MODE>(a, S, stream, ev);
+    if (G == 8) return launch_staged<CfgG8_0, MODE>(a, S, stream, ev);
+    return MDF_ERR_UNSUPPORTED;
+}
 template <int MODE>
 static int launch_staged_train(int G, const StagedArgs& a, const StagedBuffers& S, cudaStream_t stream)
 {
-    if (G == 32) return launch_staged<CfgG32_0, MODE>(a, S, stream);
-    if (G == 16) return launch_staged<CfgG16_0, MODE>(a, S, stream);
-    if (G == 8) return launch_staged<CfgG8_0, MODE>(a, S, stream);
-    return MDF_ERR_UNSUPPORTED;
+    return launch_staged_default<MODE>(G, a, S, stream);
 }
 
-static int launch_staged_variant(int G, int variant, const StagedArgs& a, const StagedBuffers& S, cudaStream_t stream)
+#ifdef MDF_TUNING
+//                         G  PT TH PG  BW  BH MINB CQS   EARLY  BF    RCP2   TRACE  ABL
+using CfgG32_1 = StagedCfg<32, 1, 4, 2, 40, 7, 2, true>;     // tile 32x4, slab 2 planes
+using CfgG32_2 = StagedCfg<32, 1, 4, 2, 40, 7, 2, true, false>;
+using CfgG32_3 = StagedCfg<32, 1, 1, 8, 48, 4, 2, true>;     // tile 32x1, slab 8 planes
+using CfgG16_1 = StagedCfg<16, 2, 4, 2, 64, 8, 2, false>;    // tile 32x4, slab 4 planes
+using CfgG16_2 = StagedCfg<16, 2, 4, 2, 48, 8, 2, false>;    // narrower box
+using CfgG16_3 = StagedCfg<16, 2, 1, 8, 80, 4, 2, false>;    // tile 32x1, slab 16 planes
+using CfgG8_1  = StagedCfg<8, 4, 8, 1, 64, 14, 2, false>;    // tile 32x8, slab 4 planes
+using CfgG8_2  = StagedCfg<8, 2, 4, 2, 64, 10, 3, false>;    // 3 CTAs / SM, slab 4 planes
+using CfgG8_3  = StagedCfg<8, 2, 2, 4, 64, 6, 3, false>;     // tile 32x2, slab 8 planes, 3 CTAs / SM
+using CfgG16_4 = StagedCfg<16, 2, 2, 4, 64, 6, 2, false, true, true>;          // branch-free samples
+using CfgG8_4  = StagedCfg<8, 4, 4, 2, 64, 10, 2, false, true, true>;
+using CfgG8_5  = StagedCfg<8, 2, 4, 2, 64, 10, 3, false, true, true>;
+using CfgG32_6 = StagedCfg<32, 1, 2, 4, 40, 6, 2, true, true, false, true>;    // one reciprocal per group
+using CfgG16_6 = StagedCfg<16, 2, 2, 4, 64, 6, 2, false, true, false, true>;
+using CfgG8_6  = StagedCfg<8, 4, 4, 2, 64, 10, 2, false, true, false, true>;
+using CfgG8_7  = StagedCfg<8, 2, 4, 2, 64, 10, 3, false, true, false, true>;
+template <int ABL> using CfgG32_A = StagedCfg<32, 1, 2, 4, 40, 6, 2, true, true, false, false, false, ABL>;   // ablations
+template <int ABL> using CfgG16_A = StagedCfg<16, 2, 2, 4, 64, 6, 2, false, true, false, false, false, ABL>;
+template <int ABL> using CfgG8_A  = StagedCfg<8, 4, 4, 2, 64, 10, 2, false, true, false, false, false, ABL>;
+using CfgG32_T = StagedCfg<32, 1, 2, 4, 40, 6, 2, true, true, false, false, true>;    // phase timestamps
+using CfgG16_T = StagedCfg<16, 2, 2, 4, 64, 6, 2, false, true, false, false, true>;
+using CfgG8_T  = StagedCfg<8, 4, 4, 2, 64, 10, 2, false, true, false, false, true>;
+
+// algo = 16 + variant: 0 default, 1-3 shapes, 4-5 branch-free, 6-7 one reciprocal per group, 8-13 ablations
+// (no MUFU / no tap loads / no stores / cheap positions / no cq loads / all of them), 15 phase timestamps
+static int launch_staged_variant(int G, int variant, const StagedArgs& a, const StagedBuffers& S, cudaStream_t stream, const HotEvents& ev)
 {
+#define MDF_V(k, Cfg) case k: return launch_staged<Cfg>(a, S, stream, ev)
     if (G == 32) {
         switch (variant) {
-            case 0: return launch_staged<CfgG32_0>(a, S, stream);
-            case 1: return launch_staged<CfgG32_1>(a, S, stream);
-            case 2: return launch_staged<CfgG32_2>(a, S, stream);
-            case 3: return launch_staged<CfgG32_3>(a, S, stream);
+            MDF_V(0, CfgG32_0); MDF_V(1, CfgG32_1); MDF_V(2, CfgG32_2); MDF_V(3, CfgG32_3); MDF_V(6, CfgG32_6);
+            MDF_V(8, CfgG32_A<1>); MDF_V(9, CfgG32_A<2>); MDF_V(10, CfgG32_A<4>); MDF_V(11, CfgG32_A<8>); MDF_V(12, CfgG32_A<16>);
+            MDF_V(13, CfgG32_A<31>); MDF_V(15, CfgG32_T);
         }
     } else if (G == 16) {
         switch (variant) {
-            case 0: return launch_staged<CfgG16_0>(a, S, stream);
-            case 1: return launch_staged<CfgG16_1>(a, S, stream);
-            case 2: return launch_staged<CfgG16_2>(a, S, stream);
-            case 3: return launch_staged<CfgG16_3>(a, S, stream);
+            MDF_V(0, CfgG16_0); MDF_V(1, CfgG16_1); MDF_V(2, CfgG16_2); MDF_V(3, CfgG16_3); MDF_V(4, CfgG16_4); MDF_V(6, CfgG16_6);
+            MDF_V(8, CfgG16_A<1>); MDF_V(9, CfgG16_A<2>); MDF_V(10, CfgG16_A<4>); MDF_V(11, CfgG16_A<8>); MDF_V(13, CfgG16_A<15>);
+            MDF_V(15, CfgG16_T);
         }
     } else if (G == 8) {
         switch (variant) {
-            case 0: return launch_staged<CfgG8_0>(a, S, stream);
-            case 1: return launch_staged<CfgG8_1>(a, S, stream);
-            case 2: return launch_staged<CfgG8_2>(a, S, stream);
-            case 3: return launch_staged<CfgG8_3>(a, S, stream);
+            MDF_V(0, CfgG8_0); MDF_V(1, CfgG8_1); MDF_V(2, CfgG8_2); MDF_V(3, CfgG8_3); MDF_V(4, CfgG8_4); MDF_V(5, CfgG8_5);
+            MDF_V(6, CfgG8_6); MDF_V(7, CfgG8_7);
+            MDF_V(8, CfgG8_A<1>); MDF_V(9, CfgG8_A<2>); MDF_V(10, CfgG8_A<4>); MDF_V(11, CfgG8_A<8>); MDF_V(13, CfgG8_A<15>);
+            MDF_V(15, CfgG8_T);
         }
     }
+#undef MDF_V
     return MDF_ERR_UNSUPPORTED;
 }
+#endif  // MDF_TUNING
 
 }  // namespace mdf

@@ -27,7 +27,7 @@ from . import _cabi
 
 __all__ = ["cost_volume", "homo_warp", "variance_volume", "softmax_regress", "softmax_regress_fit", "prob_head", "depth_regression",
            "confidence", "hypos_fit", "hypos_generate", "geo_filter",
-           "launch_count", "reset_launch_count"]
+           "launch_count", "reset_launch_count", "time_next_hot_kernel"]
 
 # kernels launched through this module since the last reset (bench.py's `gpu_launches`)
 _launches = 0
@@ -48,6 +48,17 @@ def reset_launch_count() -> None:
 def _count(n: int) -> None:
     global _launches
     _launches += n
+
+
+# (start, stop) torch.cuda.Event pair the NEXT cost_volume call of this process records around its hot kernel alone
+# (mdf_cost_volume_fwd_ex's timing hook; bench.py's live roofline numbers).  Python-side state: the library keeps none.
+_hot_events = None
+
+
+def time_next_hot_kernel(start: "torch.cuda.Event", stop: "torch.cuda.Event") -> None:
+    global _hot_events
+    start.record(); stop.record()        # materialise the handles
+    _hot_events = (start, stop)
 
 
 def _stream(t: Tensor):
@@ -110,12 +121,15 @@ def cost_volume(features: List[Tensor], ref_proj: Tensor, src_projs: List[Tensor
     out = torch.empty((B, groups, D, H, W), dtype=torch.float32, device=feats[0].device)
     ws_bytes = lib.mdf_cost_volume_workspace_bytes(B, N, C, groups, D, H, W)
     ws = _workspace(ws_bytes, out.device)
+    global _hot_events
+    ev, _hot_events = _hot_events, None
     st = lib.mdf_cost_volume_fwd_ex(
         _cabi.ptr_array([f.data_ptr() for f in feats]), N, refp.data_ptr(),
         _cabi.ptr_array([p.data_ptr() for p in projs]), hyp.data_ptr(), per_pixel,
         params[0].data_ptr(), params[1].data_ptr(), params[2].data_ptr(), params[3].data_ptr(), params[4].data_ptr(),
         float(bn_eps), params[5].data_ptr(), params[6].data_ptr(),
-        B, C, groups, D, H, W, out.data_ptr(), ws.data_ptr(), ws.numel(), int(algo), _stream(out))
+        B, C, groups, D, H, W, out.data_ptr(), ws.data_ptr(), ws.numel(), int(algo),
+        ev[0].cuda_event if ev else None, ev[1].cuda_event if ev else None, _stream(out))
     _cabi.check("mdf_cost_volume_fwd", st)
     staged = algo != 2 and C == 2 * groups and groups in (8, 16, 32)
     _count(_LAUNCHES_STAGED if staged else _LAUNCHES_DIRECT)

@@ -12,13 +12,18 @@ import torch
 
 from conftest import ROOT, load_golden
 
-HEADER = os.path.join(ROOT, "include", "mdf_b200.h")
+HEADER = os.path.join(ROOT, "include", "mdf_b200.h")              # the drop-in boundary
+DEBUG_HEADER = os.path.join(ROOT, "include", "mdf_b200_debug.h")  # test / bench / tuning entry points
 
 
-def declared_symbols():
-    text = open(HEADER).read()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"MDF_API\s+[\w\s\*]*?\b(mdf_\w+)\s*\(", text)))
+def declared_symbols(headers=(HEADER, DEBUG_HEADER)):
+    names = set()
+    for h in headers:
+        text = open(h).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        text = re.sub(r"#ifdef MDF_TUNING.*?#endif", "", text, flags=re.S)      # tuning builds only
+        names |= set(re.findall(r"MDF_API\s+[\w\s\*]*?\b(mdf_\w+)\s*\(", text))
+    return sorted(names)
 
 
 @pytest.fixture(scope="module")
@@ -28,7 +33,8 @@ def libpath():
 
 
 def test_header_declares_the_path():
-    names = declared_symbols()
+    names = declared_symbols((HEADER,))
+    assert not [n for n in names if n.endswith("_ex") or n.startswith("mdf_debug_")], "diagnostics belong in mdf_b200_debug.h"
     for required in ("mdf_cost_volume_fwd", "mdf_homo_warp_fwd", "mdf_variance_volume_fwd", "mdf_softmax_regress_fwd",
                      "mdf_depth_regression_fwd", "mdf_confidence_fwd", "mdf_cost_volume_workspace_bytes"):
         assert required in names

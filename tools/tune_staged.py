@@ -9,6 +9,7 @@ sys.path.insert(0, ROOT)
 import numpy as np
 import torch
 
+os.environ.setdefault("MDF_B200_TUNING", "1")      # the variants live in the tuning build
 import bench
 from mdf_net_b200 import _cabi, ops, synthetic as syn
 
