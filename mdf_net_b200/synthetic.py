@@ -200,6 +200,30 @@ def regulariser_logits(batch: int, ndepths: int, h: int, w: int, seed: int = 5, 
     return (x + np.float32(peak) * np.exp(-0.5 * ((k - centre) / width) ** 2)).astype(np.float32)
 
 
+def scene_logits(batch: int, stage: int, h: int, w: int, seed: int = 6, dmin: float = DTU_DEPTH_RANGE[0],
+                 dmax: float = DTU_DEPTH_RANGE[1], peak: float = 9.0) -> np.ndarray:
+    """Stand-in for the 3-D CNN output (B,D,H,W) of `stage` that makes the coarse-to-fine CHAIN behave like a real scene:
+    one bump per pixel plus noise, placed so that stage 0 regresses to `scene_depth` over the uniform hypotheses and the
+    later stages regress to a smooth offset around the middle of whatever hypotheses HyposByFit hands them.  The bump
+    width varies smoothly over the image, so the fitted search ranges of the next stage do too (8-30 mm, like
+    `scene_hypos`).  Used where the hypotheses of stages 1-2 are produced on the device (bench.py's end-to-end leg)."""
+    rng = np.random.default_rng(seed + 100 + stage)
+    D = STAGE_DEPTHS[stage]
+    v, u = np.meshgrid(np.linspace(0, 1, h, dtype=np.float32), np.linspace(0, 1, w, dtype=np.float32), indexing="ij")
+    ph = rng.uniform(0, 6.28, 4)
+    t = 0.5 + 0.25 * np.sin(5.0 * u + ph[0]) * np.cos(4.0 * v + ph[1]) + 0.25 * np.sin(9.0 * v + ph[2]) * np.cos(7.0 * u + ph[3])
+    if stage == 0:
+        interval = (dmax - dmin) / (D - 1)
+        centre = (scene_depth(batch, h, w, seed) - np.float32(dmin)) / np.float32(interval)        # (B,1,h,w) in planes
+        width = (0.6 + 1.0 * t)[None, None]
+    else:
+        centre = np.broadcast_to(((D - 1) / 2.0 + (D / 8.0) * (2.0 * t - 1.0))[None, None], (batch, 1, h, w))
+        width = (np.float32(D) / 16.0 + 0.6 * t)[None, None]
+    k = np.arange(D, dtype=np.float32).reshape(1, D, 1, 1)
+    x = np.float32(0.3) * rng.standard_normal((batch, D, h, w), dtype=np.float32)
+    return (x + np.float32(peak) * np.exp(-0.5 * ((k - centre) / width) ** 2)).astype(np.float32)
+
+
 def projection_matrices(K: np.ndarray, E: np.ndarray, level_div: float = 1.0) -> np.ndarray:
     """(B,N,4,4) float32 P = [K/level_div (rows 0-1) @ E[:3,:4]; E[3]]  -- what scale_cam returns
     (scale.py:4-20), computed in float32 with numpy for fixtures that bypass torch."""

@@ -33,6 +33,11 @@ def pytest_sessionstart(session):
         c_oracle.build()
     except Exception as e:  # pragma: no cover
         print(f"[conftest] could not build the oracle: {e}")
+    try:
+        from oracle import ref_install
+        ref_install.install()           # no-op where /root/reference does not exist (the GPU box uses the shipped copy)
+    except Exception as e:  # pragma: no cover
+        print(f"[conftest] could not install oracle/_ref: {e}")
 
 
 def pytest_collection_modifyitems(config, items):

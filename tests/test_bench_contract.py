@@ -51,5 +51,45 @@ def test_reference_arm_prints_the_contract_line():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "views/s" and line["higher_is_better"] is True
     assert line["config"] == bench.make_config("dtu_640x512_n3")
-    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["kind"] == "port"
+    from oracle import ref_install
+    # the unmodified reference on torch CPU wherever its copy is present (build container, GPU box); the C port otherwise
+    assert line["e2e"]["h2d_bytes_per_step"] == 0
+    assert line["cpu_baseline"]["kind"] == ("reference" if ref_install.available() else "port")
     assert line["cpu_baseline"]["cores"] >= 1 and line["value"] > 0
+    assert line["cpu_baseline"]["value"] == line["value"]
+
+
+def test_reference_copy_is_the_unmodified_reference():
+    """oracle/_ref (git-ignored, travels with the gpurun snapshot) hashes to the committed manifest of /root/reference."""
+    from oracle import ref_install
+    if not ref_install.available():
+        import pytest
+        pytest.skip("oracle/_ref not installed here")
+    ref_install.verify()
+    import json as js
+    manifest = js.load(open(os.path.join(ROOT, "oracle", "ref_manifest.json")))
+    assert sorted(manifest) == sorted(ref_install.FILES)
+    if os.path.isdir(ref_install.REF_SRC):        # build container: the manifest itself matches the checkout
+        for rel in ref_install.FILES:
+            assert ref_install._sha(os.path.join(ref_install.REF_SRC, rel)) == manifest[rel]
+
+
+def test_chain_logits_make_scene_like_hypotheses():
+    """bench.py's end-to-end leg forms the stage-1/2 hypotheses on the device from synthetic logits: the oracle chain on the
+    same logits gives smooth, scene-like hypotheses (not the adversarial i.i.d. case)."""
+    from oracle import c_oracle as co
+    h0, w0 = 256, 320
+    drange = np.array([[425.0, 935.0]], np.float32)
+    hyp, depth, prob = syn.uniform_hypos(1, 48), None, None
+    curves, th = (None, "gauss1", "laplace"), (0.0, 0.95, 1e-5)
+    for s in range(3):
+        H, W = syn.stage_shapes(h0, w0)[s]
+        D = syn.STAGE_DEPTHS[s]
+        if s > 0:
+            hyp = co.hypos_generate(depth, co.hypos_fit(prob, hyp, depth, curves[s]), drange, curves[s], th[s], D, True)
+            assert hyp.shape == (1, D, H, W) and (np.diff(hyp, axis=1) >= 0).all()
+            rng = hyp[:, -1] - hyp[:, 0]
+            assert 4.0 < np.median(rng) < 60.0
+            assert np.median(np.abs(np.diff(hyp[0, D // 2], axis=1))) < 2.0       # neighbouring pixels see the same surface
+        prob = co.softmax_depth(syn.scene_logits(1, s, H, W, seed=6))
+        depth = co.depth_regression(prob, hyp)

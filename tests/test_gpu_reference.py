@@ -1,0 +1,216 @@
+"""GPU parity against the UNMODIFIED reference modules running on the same B200 (ATen / cuDNN), full size.
+
+The reference's model package travels to the GPU box in the git-ignored oracle/_ref/ (oracle/ref_install.py; the copy is
+verified against the committed sha256 manifest before use).  Same seeded inputs into
+    net.unit.homoaggregate.VectorAggregate   (homoaggregate.py:8-46 + base.py:85-126)
+    F.softmax + net.unit.regress.*           (regular.py:67-69, regress.py:5-25, core.py:75-77)
+    net.unit.depthhypos.HyposByFit           (depthhypos.py:27-215)
+and into this repo's drop-ins, at BASELINE.json configs[1] (1600x1152 N=5), the crop the shipped loader really uses
+(1184 rows, dtueval.py:34) and configs[3] (1920x1056, N=7 and the reference's default N=11, config.py:119).
+
+Tolerances (north_star): cost volume 1e-5 relative (rel-L2), depth 1e-3 of the stage-0 interval, confidence-mask
+decisions identical on >= 99.99 % of pixels.
+"""
+import contextlib
+import io
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_l2
+from mdf_net_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+INTERVAL = (935.0 - 425.0) / 47.0
+SHAPES = {            # name: (h0, w0, nviews)
+    "dtu_1600x1152_n5": (1152, 1600, 5),
+    "dtu_1600x1184_n5": (1184, 1600, 5),
+    "tanks_1920x1056_n7": (1056, 1920, 7),
+    "tanks_1920x1056_n11": (1056, 1920, 11),
+}
+
+
+@pytest.fixture(scope="module")
+def ref():
+    from oracle import ref_install
+    if not ref_install.available():
+        pytest.fail("oracle/_ref is missing on this box: run `python -m oracle.ref_install` in the build container "
+                    "before gpurun (the snapshot ships ignored files)")
+    with contextlib.redirect_stdout(io.StringIO()):
+        return ref_install.modules()
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def set_params(mod, p, G):
+    dw = mod.depth_weight
+    with torch.no_grad():
+        dw[0].conv.weight.copy_(cu(p["cw"]).view(1, G, 1, 1, 1))
+        dw[0].bn.weight.fill_(float(p["bn_weight"])); dw[0].bn.bias.fill_(float(p["bn_bias"]))
+        dw[0].bn.running_mean.fill_(float(p["bn_mean"])); dw[0].bn.running_var.fill_(float(p["bn_var"]))
+        dw[1].weight.fill_(float(p["fc_weight"])); dw[1].bias.fill_(float(p["fc_bias"]))
+
+
+def stage_inputs(name, stage, seed=3):
+    h0, w0, N = SHAPES[name]
+    H, W = syn.stage_shapes(h0, w0)[stage]
+    C, D, G = syn.STAGE_CHANNELS[stage], syn.STAGE_DEPTHS[stage], syn.STAGE_GROUPS[stage]
+    K, E = syn.camera_rig(1, N, h0, w0, seed=seed)
+    P = syn.projection_matrices(K, E, 2.0 ** (3 - stage))
+    feats = syn.smooth_features(1, N, C, H, W, seed=seed + 10 + stage)
+    hyp = syn.uniform_hypos(1, D) if stage == 0 else syn.scene_hypos(1, D, H, W, seed=seed)
+    return dict(H=H, W=W, C=C, D=D, G=G, N=N, P=P, feats=feats, hyp=hyp, params=syn.depth_weight_params(G, seed=seed + 30 + stage))
+
+
+@pytest.mark.parametrize("stage", [0, 1, 2])
+@pytest.mark.parametrize("name", list(SHAPES))
+def test_cost_volume_vs_reference_module(ref, name, stage):
+    import mdf_net_b200 as mdf
+    s = stage_inputs(name, stage)
+    G, N = s["G"], s["N"]
+    feats = [cu(f) for f in s["feats"]]
+    ref_proj, src_projs, hyp = cu(s["P"][:, 0]), [cu(s["P"][:, v]) for v in range(1, N)], cu(s["hyp"])
+    with contextlib.redirect_stdout(io.StringIO()):
+        theirs = ref.homoaggregate.VectorAggregate(G).cuda().eval()
+    ours = mdf.VectorAggregate(G).cuda().eval()
+    set_params(theirs, s["params"], G)
+    ours.load_state_dict(theirs.state_dict(), strict=True)        # the reference's own checkpoint keys
+    with torch.no_grad():
+        want = theirs(feats, ref_proj, src_projs, hyp)
+        got = ours(feats, ref_proj, src_projs, hyp)
+    assert got.shape == want.shape == (1, G, s["D"], s["H"], s["W"])
+    # float64 accumulation of the norms on the device (the volumes are 118-177 MB)
+    num = torch.linalg.vector_norm((got.double() - want.double()))
+    den = torch.linalg.vector_norm(want.double())
+    r = float(num / den)
+    assert r < 1e-5, f"{name} stage {stage}: rel-L2 {r:.3g} vs the reference's VectorAggregate on the same GPU"
+    worst = float((got - want).abs().max())
+    # element-wise: the reference's own float32 coordinate chain is worth a few 1e-5 on isolated elements
+    # (ulp(1900 px) = 1.2e-4 px per rounding) -- the bound is loose on purpose, the norm is the criterion
+    assert worst < 2e-3, f"{name} stage {stage}: max abs {worst:.3g}"
+
+
+@pytest.mark.parametrize("name", ["dtu_1600x1152_n5", "tanks_1920x1056_n7"])
+def test_head_vs_reference_functions(ref, name):
+    """softmax tail + depth_regression at D = 48 / 24 / 8 and confidence_regress + nearest x2 on the last stage, full size."""
+    import mdf_net_b200 as mdf
+    h0, w0, _ = SHAPES[name]
+    for stage in range(3):
+        H, W = syn.stage_shapes(h0, w0)[stage]
+        D = syn.STAGE_DEPTHS[stage]
+        logits = cu(syn.regulariser_logits(1, D, H, W, seed=40 + stage))
+        hyp = cu(syn.uniform_hypos(1, D) if stage == 0 else syn.scene_hypos(1, D, H, W, seed=3))
+        with torch.no_grad():
+            prob_ref = torch.nn.functional.softmax(logits, dim=1)                       # regular.py:69 / :133
+            depth_ref = ref.regress.depth_regression(prob_ref, hyp)                      # regress.py:5-7
+            prob, depth, conf = mdf.softmax_regress(logits, hyp, want_confidence=stage == 2)
+        assert float((prob - prob_ref).abs().max()) < 3e-7
+        assert float((depth - depth_ref).abs().max()) < 1e-3 * INTERVAL, f"{name} stage {stage}"
+        if stage == 2:
+            with torch.no_grad():
+                conf_ref = ref.regress.confidence_regress(prob_ref)                       # regress.py:9-25
+                conf_ref = torch.nn.functional.interpolate(conf_ref.unsqueeze(1), scale_factor=2, mode="nearest").squeeze(1)  # core.py:76-77
+                # on the reference's own probability volume the window / index work is exact
+                conf_same_prob = mdf.confidence_regress(prob_ref)
+                conf_same_prob = torch.nn.functional.interpolate(conf_same_prob.unsqueeze(1), scale_factor=2, mode="nearest").squeeze(1)
+            assert torch.equal(conf_same_prob, conf_ref)
+            assert conf.shape == conf_ref.shape == (1, h0, w0)
+            same = ((conf - conf_ref).abs() < 1e-6).float().mean().item()
+            assert same >= 0.9999, f"{name}: confidence identical on {same:.6f} of the pixels"
+            for thr in (0.6, 0.8):                                                      # gipuma / dynamic filter thresholds
+                agree = ((conf > thr) == (conf_ref > thr)).float().mean().item()
+                assert agree >= 0.9999, f"{name}: mask decisions at {thr} agree on {agree:.6f}"
+
+
+@pytest.mark.parametrize("name", ["dtu_1600x1152_n5"])
+def test_hypos_by_fit_vs_reference_module(ref, name):
+    """HyposByFit (depthhypos.py:27-215), stage 1 (gauss1) and stage 2 (laplace), at full size against the reference module
+    on the same GPU.  gauss1 inverts ill-conditioned float32 normal equations in the reference: its own
+    float32 / float64 runs differ by ~0.1 mm, the bound for that stage is 0.5 mm; laplace matches to 1e-3 of an interval."""
+    import mdf_net_b200 as mdf
+    h0, w0, _ = SHAPES[name]
+    depth_range = cu(np.array([[425.0, 935.0]], np.float32))
+    curves = [None, "gauss1", "laplace"]
+    threshes = (0.0, 0.95, 1e-5)
+    for stage in (1, 2):
+        Hp, Wp = syn.stage_shapes(h0, w0)[stage - 1]
+        Dp, D = syn.STAGE_DEPTHS[stage - 1], syn.STAGE_DEPTHS[stage]
+        prev_hyp = cu(syn.uniform_hypos(1, Dp) if stage == 1 else syn.scene_hypos(1, Dp, Hp, Wp, seed=3))
+        logits = cu(syn.regulariser_logits(1, Dp, Hp, Wp, seed=50 + stage, peak=6.0))
+        with torch.no_grad():
+            prob = torch.nn.functional.softmax(logits, dim=1)
+            depth = ref.regress.depth_regression(prob, prev_hyp)
+            with contextlib.redirect_stdout(io.StringIO()):
+                theirs = ref.depthhypos.HyposByFit(D, curves[stage], threshes[stage]).cuda()
+            ours = mdf.HyposByFit(D, curves[stage], threshes[stage]).cuda()
+            want = theirs(depth, depth_range, prob, prev_hyp, upsample=True)
+            got = ours(depth, depth_range, prob, prev_hyp, upsample=True)
+        assert got.shape == want.shape
+        err = (got - want).abs()
+        tol = 0.5 if curves[stage] == "gauss1" else 1e-3 * INTERVAL
+        frac_ok = float((err < tol).float().mean())
+        assert frac_ok >= 0.9999, f"stage {stage} ({curves[stage]}): {frac_ok:.6f} of the hypotheses within {tol} mm, max {float(err.max()):.3g}"
+
+
+def test_whole_model_vs_reference_corenet(ref):
+    """The reference's CoreNet with its own units against the same CoreNet wired with this repo's drop-ins (the three
+    config.py lines of INTEGRATION.md), same seeded weights, 640x512 N=3 (BASELINE configs[0] shape) on the GPU.  The chain
+    amplifies float32 noise (3-D CNN under cuDNN, gauss1 normal equations: SURVEY 7.2), so the end-to-end bound is the
+    reference's own run-to-run band: depth within 0.5 mm on >= 99.9 % of the pixels, confidence masks agree on >= 99.9 %."""
+    import mdf_net_b200 as mdf
+    torch.backends.cudnn.benchmark = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    h0, w0, N = 512, 640, 3
+    r = ref
+    ndepths, ngroups, curves, thresh = (48, 24, 8), (32, 16, 8), [None, "gauss1", "laplace"], (0.0, 0.95, 1e-5)
+
+    def build(units_from):
+        torch.manual_seed(7)
+        with contextlib.redirect_stdout(io.StringIO()):
+            backbone = r.backbone.FPN_4Scales((8, 16, 32, 64))
+            hypos = torch.nn.ModuleList([r.depthhypos.HyposByFit(ndepths[i], curves[i], thresh[i]) for i in range(3)])
+            agg = torch.nn.ModuleList([units_from.VectorAggregate(g) for g in ngroups])
+            reg = torch.nn.ModuleList([r.regular.RegularNet_3Scales(ngroups[0])] + [r.regular.RegularNet_4Scales(g) for g in ngroups[1:]])
+            regress = [units_from.depth_regression, units_from.confidence_regress]
+            model = r.core.CoreNet(backbone, hypos, r.scale.scale_cam, agg, reg, regress, r.refine.RefineNet2())
+        return model
+
+    class RefUnits:
+        VectorAggregate = r.homoaggregate.VectorAggregate
+        depth_regression = staticmethod(r.regress.depth_regression)
+        confidence_regress = staticmethod(r.regress.confidence_regress)
+
+    theirs = build(RefUnits)
+    # default-init features are ~1e-4 (cost volume == 0.5): randomise the BatchNorm statistics
+    g = torch.Generator().manual_seed(11)
+    for m in theirs.modules():
+        if isinstance(m, (torch.nn.BatchNorm2d, torch.nn.BatchNorm3d)):
+            with torch.no_grad():
+                m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) * 0.04 + 0.002)
+                m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.05)
+                m.weight.copy_(1.0 + 0.3 * torch.randn(m.weight.shape, generator=g))
+                m.bias.copy_(0.1 * torch.randn(m.bias.shape, generator=g))
+    ours = build(mdf)
+    ours.load_state_dict(theirs.state_dict(), strict=True)
+    theirs, ours = theirs.cuda().eval(), ours.cuda().eval()
+    K, E = syn.camera_rig(1, N, h0, w0, seed=5)
+    rng = np.random.default_rng(5)
+    imgs = cu(rng.random((1, N, 3, h0, w0), dtype=np.float32))
+    args = (imgs, cu(E), cu(K), cu(np.array([[425.0, 935.0]], np.float32)))
+    with torch.no_grad():
+        a = theirs(*args)
+        b = ours(*args)
+        a2 = theirs(*args)                                   # the reference against itself: its run-to-run band
+    assert a["depth"].shape == b["depth"].shape and a["confidence"].shape == b["confidence"].shape
+    self_band = float((a["depth"] - a2["depth"]).abs().max())
+    err = (a["depth"] - b["depth"]).abs()
+    ok = float((err < 0.5).float().mean())
+    assert ok >= 0.999, f"depth within 0.5 mm on {ok:.5f} of the pixels (max {float(err.max()):.3g} mm, reference vs itself {self_band:.3g})"
+    for thr in (0.6, 0.8):
+        agree = float(((a["confidence"] > thr) == (b["confidence"] > thr)).float().mean())
+        assert agree >= 0.999, f"confidence mask at {thr} agrees on {agree:.5f}"
