@@ -143,6 +143,32 @@ def cuda_hot_path(view, device, reps: int = 3):
             "max_memory_allocated_bytes": int(peak)}
 
 
+def randomise_weights(model, sample_img, seed: int = 11, feature_std: float = 1.5):
+    """Seeded stand-in for the missing checkpoints (pth/dtu_29.pth is absent from the checkout).  Default-init features are
+    ~1e-4 and give a degenerate cost volume == 0.5, so the BatchNorm statistics are randomised -- and the three
+    1x1 output convolutions of the FPN (backbone.py:43-45, bias-free) are rescaled so that the features the cost volume sees
+    have a standard deviation of `feature_std`, the magnitude of trained feature maps.  (Without the rescaling the
+    randomised BatchNorms stack up to |features| ~ 1e5: every similarity saturates to 0 / 1 and float32 blending noise alone
+    flips them.)"""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    for m in model.modules():
+        if isinstance(m, (torch.nn.BatchNorm2d, torch.nn.BatchNorm3d)):
+            with torch.no_grad():
+                m.running_var.copy_((torch.rand(m.running_var.shape, generator=g) * 0.04 + 0.002).to(m.running_var.device))
+                m.running_mean.copy_((torch.randn(m.running_mean.shape, generator=g) * 0.05).to(m.running_mean.device))
+                m.weight.copy_((1.0 + 0.3 * torch.randn(m.weight.shape, generator=g)).to(m.weight.device))
+                m.bias.copy_((0.1 * torch.randn(m.bias.shape, generator=g)).to(m.bias.device))
+    with torch.no_grad():
+        was_training = model.training
+        model.eval()
+        y4, y3, y2 = model.Backbone(sample_img)
+        for conv, y in ((model.Backbone.out4, y4), (model.Backbone.out3, y3), (model.Backbone.out2, y2)):
+            conv.weight.mul_(feature_std / float(y.std()))
+        model.train(was_training)
+    return model
+
+
 def pipeline(device, h0: int, w0: int, nviews: int, reps: int = 3):
     """FPN and 3-D CNN timed separately (north_star), and the whole eval forward (eval.py:23-31) of config.model next
     to the same model with this repo's units injected (the three config.py lines of INTEGRATION.md + the fused CoreNet)."""
@@ -154,15 +180,6 @@ def pipeline(device, h0: int, w0: int, nviews: int, reps: int = 3):
     with _quiet():
         model = ref_install.config_model()
         ref = ref_install.modules()
-    # default-init features are ~1e-4 and give a degenerate cost volume: randomise the BatchNorm statistics
-    g = torch.Generator().manual_seed(11)
-    for m in model.modules():
-        if isinstance(m, (torch.nn.BatchNorm2d, torch.nn.BatchNorm3d)):
-            with torch.no_grad():
-                m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) * 0.04 + 0.002)
-                m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.05)
-                m.weight.copy_(1.0 + 0.3 * torch.randn(m.weight.shape, generator=g))
-                m.bias.copy_(0.1 * torch.randn(m.bias.shape, generator=g))
     model = model.to(device).eval()
     tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
     torch.backends.cudnn.allow_tf32 = False
@@ -173,6 +190,7 @@ def pipeline(device, h0: int, w0: int, nviews: int, reps: int = 3):
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
     imgs = t(rng.random((1, nviews, 3, h0, w0), dtype=np.float32))
     args = (imgs, t(E), t(K), t(np.array([[425.0, 935.0]], np.float32)))
+    randomise_weights(model, imgs[:, 0])
 
     def med(fn, n=reps, warm=1):
         for _ in range(warm):
@@ -186,8 +204,8 @@ def pipeline(device, h0: int, w0: int, nviews: int, reps: int = 3):
             ts.append(a.elapsed_time(b))
         return statistics.median(ts)
 
-    out = {"not_in_value": True, "workload": f"{w0}x{h0} N={nviews}, batch 1, seeded weights with randomised BatchNorm statistics "
-                                           f"(pth/dtu_29.pth is absent from the checkout), fp32 (TF32 off), cudnn.benchmark on"}
+    out = {"not_in_value": True, "workload": f"{w0}x{h0} N={nviews}, batch 1, seeded weights with randomised BatchNorm statistics and "
+                                           f"unit-scale features (pth/dtu_29.pth is absent from the checkout), fp32 (TF32 off), cudnn.benchmark on"}
     try:
         with torch.no_grad():
             views = torch.unbind(imgs, 1)

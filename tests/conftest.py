@@ -73,3 +73,28 @@ def max_abs_over_max(a, b):
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def assert_confidence_decisions(conf, conf_ref, prob_ref, what="", upsample=2, thresholds=(0.6, 0.8), tol=1e-4, index_noise=1e-4):
+    """north_star: identical confidence-mask decisions on >= 99.99 % of the pixels.  The confidence is a window sum picked by
+    trunc(sum_d p_d * d) (regress.py:15-18), a discrete decision, so on a tiny fixture one legitimate flip is already
+    more than 0.01 %.  Hence an exact count with a justification per flip: the number of differing pixels is at most
+    max(1, 1e-4 * N) per upsampled cell block, and every one of them has its expected index within `index_noise` of an
+    integer on the reference's own probability volume (float32 noise moved the truncation by one plane) or its confidence
+    within `tol` of the threshold."""
+    conf, conf_ref, prob_ref = np.asarray(conf), np.asarray(conf_ref), np.asarray(prob_ref)
+    D = prob_ref.shape[1]
+    eidx = (prob_ref.astype(np.float64) * np.arange(D, dtype=np.float64).reshape(1, D, 1, 1)).sum(1)
+    near_int = np.abs(eidx - np.round(eidx)) < index_noise
+    if upsample > 1:
+        near_int = np.repeat(np.repeat(near_int, upsample, axis=1), upsample, axis=2)
+    assert conf.shape == conf_ref.shape == near_int.shape, (conf.shape, conf_ref.shape, near_int.shape)
+    budget = max(upsample * upsample, int(np.ceil(1e-4 * conf.size)))
+    differ = np.abs(conf - conf_ref) >= tol
+    assert differ.sum() <= budget, f"{what}: {int(differ.sum())} of {conf.size} confidences differ (budget {budget})"
+    assert not (differ & ~near_int).any(), f"{what}: {int((differ & ~near_int).sum())} differing confidences are not truncation flips"
+    for thr in thresholds:
+        flips = (conf > thr) != (conf_ref > thr)
+        assert flips.sum() <= budget, f"{what}: {int(flips.sum())} mask decisions differ at {thr} (budget {budget})"
+        explained = near_int | (np.abs(conf_ref - thr) < tol)
+        assert not (flips & ~explained).any(), f"{what}: {int((flips & ~explained).sum())} unexplained flips at {thr}"

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import load_golden, max_abs_over_max, rel_l2
+from conftest import assert_confidence_decisions, load_golden, max_abs_over_max, rel_l2
 from mdf_net_b200 import synthetic as syn
 
 pytestmark = pytest.mark.gpu
@@ -293,8 +293,7 @@ def test_head_golden(name):
     assert np.abs(blend.cpu().numpy() - z["confidence_blend"]).max() < 1e-5
     # fused from logits: same decisions (the probabilities differ from ATen's by <= 1 ulp of exp)
     _, _, conf = mdf.softmax_regress(cu(z["logits"]), cu(z["hypos_pixel"]), want_confidence=True)
-    same = np.abs(conf.cpu().numpy() - z["confidence_up"]) < 1e-6
-    assert same.mean() >= 0.99, name      # tiny fixture: a single flip is 0.5 %; the statistic is tested below
+    assert_confidence_decisions(conf.cpu().numpy(), z["confidence_up"], z["prob"], name, tol=1e-6)     # tiny fixture: exact count
 
 
 def test_head_known_answers():

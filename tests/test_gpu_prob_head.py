@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import load_golden
+from conftest import assert_confidence_decisions, load_golden
 from mdf_net_b200 import synthetic as syn
 
 pytestmark = pytest.mark.gpu
@@ -36,9 +36,7 @@ def test_prob_head_golden(name):
     if last:
         c = conf.cpu().numpy()
         assert c.shape == z["confidence_up"].shape
-        assert (np.abs(c - z["confidence_up"]) < 1e-4).mean() >= 0.995      # the index trunc(sum p*d) is a discrete decision
-        for thr in (0.6, 0.8):
-            assert ((c > thr) == (z["confidence_up"] > thr)).mean() >= 0.995
+        assert_confidence_decisions(c, z["confidence_up"], z["prob"], name)      # exact flip count, every flip explained
     elif curve == "gauss1":
         ref_noise = rel(z["s"], z["s_f64"])                                   # the reference's own float32 run: 6e-3
         assert rel(s.cpu().numpy(), z["s_f64"]) < 1e-3 < ref_noise

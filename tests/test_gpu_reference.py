@@ -107,8 +107,9 @@ def test_head_vs_reference_functions(ref, name):
         with torch.no_grad():
             prob_ref = torch.nn.functional.softmax(logits, dim=1)                       # regular.py:69 / :133
             depth_ref = ref.regress.depth_regression(prob_ref, hyp)                      # regress.py:5-7
-            prob, depth, conf = mdf.softmax_regress(logits, hyp, want_confidence=stage == 2)
-        assert float((prob - prob_ref).abs().max()) < 3e-7
+            res = mdf.softmax_regress(logits, hyp, want_confidence=stage == 2)
+            prob, depth, conf = res if stage == 2 else (*res, None)
+        assert float((prob - prob_ref).abs().max()) < 1e-6          # ATen's CUDA softmax and this kernel round exp differently: a few ulp of 1
         assert float((depth - depth_ref).abs().max()) < 1e-3 * INTERVAL, f"{name} stage {stage}"
         if stage == 2:
             with torch.no_grad():
@@ -158,9 +159,17 @@ def test_hypos_by_fit_vs_reference_module(ref, name):
 
 def test_whole_model_vs_reference_corenet(ref):
     """The reference's CoreNet with its own units against the same CoreNet wired with this repo's drop-ins (the three
-    config.py lines of INTEGRATION.md), same seeded weights, 640x512 N=3 (BASELINE configs[0] shape) on the GPU.  The chain
-    amplifies float32 noise (3-D CNN under cuDNN, gauss1 normal equations: SURVEY 7.2), so the end-to-end bound is the
-    reference's own run-to-run band: depth within 0.5 mm on >= 99.9 % of the pixels, confidence masks agree on >= 99.9 %."""
+    config.py lines of INTEGRATION.md), same seeded weights, 640x512 N=3 (BASELINE configs[0] shape) on the GPU.
+
+    With seeded (untrained) weights the chain is chaotic: the 3-D CNN and the gauss1 normal equations amplify float32
+    noise (1e-7 relative noise on the cost volumes already moves the final depth by 1e-3 mm on average and
+    1e-2 mm at worst).  So the yardstick is the reference ITSELF under the perturbation the tolerance allows: its cost volumes
+    multiplied by (1 + 1e-5 N(0,1)), north_star's 1e-5 relative.  The drop-in model (per-stage rel-L2 1e-6 .. 8e-6, see
+    test_cost_volume_vs_reference_module) must agree with the reference at least as well as that perturbed reference does,
+    and: depth within 0.5 mm on >= 99.99 % of the pixels, within 1e-3 of a stage-0 interval (0.011 mm) on >= 99 %.
+    (Measured: drop-in 1.00000 within 0.5 mm, p99 0.0025 mm, max 0.15 mm; reference under 1e-5 noise 0.9996; tools/diag_whole_model.py.
+    The seeded weights are scaled to unit-variance features: with the raw randomised BatchNorms |features| reaches 1e5, every
+    similarity saturates and float32 blending noise alone flips them -- in the reference as much as here.)"""
     import mdf_net_b200 as mdf
     torch.backends.cudnn.benchmark = False
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -186,31 +195,32 @@ def test_whole_model_vs_reference_corenet(ref):
         confidence_regress = staticmethod(r.regress.confidence_regress)
 
     theirs = build(RefUnits)
-    # default-init features are ~1e-4 (cost volume == 0.5): randomise the BatchNorm statistics
-    g = torch.Generator().manual_seed(11)
-    for m in theirs.modules():
-        if isinstance(m, (torch.nn.BatchNorm2d, torch.nn.BatchNorm3d)):
-            with torch.no_grad():
-                m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) * 0.04 + 0.002)
-                m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.05)
-                m.weight.copy_(1.0 + 0.3 * torch.randn(m.weight.shape, generator=g))
-                m.bias.copy_(0.1 * torch.randn(m.bias.shape, generator=g))
-    ours = build(mdf)
-    ours.load_state_dict(theirs.state_dict(), strict=True)
-    theirs, ours = theirs.cuda().eval(), ours.cuda().eval()
     K, E = syn.camera_rig(1, N, h0, w0, seed=5)
     rng = np.random.default_rng(5)
     imgs = cu(rng.random((1, N, 3, h0, w0), dtype=np.float32))
+    from oracle import ref_bench
+    theirs = ref_bench.randomise_weights(theirs.cuda(), imgs[:, 0]).cpu()     # BatchNorm statistics + unit-scale features
+    ours = build(mdf)
+    ours.load_state_dict(theirs.state_dict(), strict=True)
+    theirs, ours = theirs.cuda().eval(), ours.cuda().eval()
     args = (imgs, cu(E), cu(K), cu(np.array([[425.0, 935.0]], np.float32)))
     with torch.no_grad():
         a = theirs(*args)
         b = ours(*args)
-        a2 = theirs(*args)                                   # the reference against itself: its run-to-run band
+        gen = torch.Generator(device="cuda").manual_seed(3)
+        hooks = [m.register_forward_hook(lambda mod, inp, out: out * (1.0 + 1e-5 * torch.randn(out.shape, device=out.device, generator=gen)))
+                 for m in theirs.Homoaggre]
+        c = theirs(*args)                                    # the reference with its cost volumes perturbed by 1e-5
+        for h in hooks:
+            h.remove()
     assert a["depth"].shape == b["depth"].shape and a["confidence"].shape == b["confidence"].shape
-    self_band = float((a["depth"] - a2["depth"]).abs().max())
-    err = (a["depth"] - b["depth"]).abs()
-    ok = float((err < 0.5).float().mean())
-    assert ok >= 0.999, f"depth within 0.5 mm on {ok:.5f} of the pixels (max {float(err.max()):.3g} mm, reference vs itself {self_band:.3g})"
+    within = lambda x, y: float(((x - y).abs() < 0.5).float().mean())
+    ok, band = within(a["depth"], b["depth"]), within(a["depth"], c["depth"])
+    assert ok >= band and ok >= 0.9999, \
+        f"depth within 0.5 mm on {ok:.5f} of the pixels; the reference under 1e-5 noise on its cost volumes: {band:.5f}"
+    fine = float(((a["depth"] - b["depth"]).abs() < 1e-3 * INTERVAL).float().mean())
+    assert fine >= 0.99, f"depth within 1e-3 of an interval on {fine:.5f} of the pixels"
     for thr in (0.6, 0.8):
         agree = float(((a["confidence"] > thr) == (b["confidence"] > thr)).float().mean())
-        assert agree >= 0.999, f"confidence mask at {thr} agrees on {agree:.5f}"
+        noise = float(((a["confidence"] > thr) == (c["confidence"] > thr)).float().mean())
+        assert agree >= min(0.9999, noise) and agree >= 0.9995, f"confidence mask at {thr}: {agree:.5f} (reference under noise {noise:.5f})"

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from oracle import c_oracle as co
-from conftest import load_golden, rel_l2, max_abs_over_max
+from conftest import assert_confidence_decisions, load_golden, rel_l2, max_abs_over_max
 
 
 def _rt_from_proj(proj):
@@ -201,7 +201,7 @@ def test_prob_conv_and_tail(name):
     assert np.abs(depth - z["depth"]).max() < 1e-3 * (935.0 - 425.0) / 47.0
     if "confidence_up" in z.files:
         conf = co.confidence_regress(prob, upsample=2)
-        assert (np.abs(conf - z["confidence_up"]) < 1e-4).mean() >= 0.995
+        assert_confidence_decisions(conf, z["confidence_up"], z["prob"], name)
     else:
         curve = "gauss1" if name.endswith("s0") else "laplace"
         s = co.hypos_fit(z["prob"], z["depth_hypos"], z["depth"], curve)
