@@ -12,7 +12,10 @@ Here the regulariser's body still runs as the injected module (PyTorch / cuDNN, 
 of its last layer: `ops.prob_head` takes that layer's input and weight and produces depth, the fitted scale the next
 stage's hypotheses need, and the confidence, without the logits or the probability volume ever being written
 (SURVEY 8f rows 1-2).  Anything that does not fit (other module types, gradients required, D not in {8,24,48}) goes
-through the injected units exactly like the reference (`fuse=False` forces that path).
+through the injected units exactly like the reference (`fuse=False` forces that path).  The tail is fused only for the
+regularisers and regress functions it reimplements (the reference's RegularNet_3Scales / _4Scales, depth_regression,
+confidence_regress, or this package's); a custom module opts in with a class attribute `mdf_fusable_tail = True`
+(its forward must end with `self.prob(x).squeeze(1)` -> softmax over D) or the caller passes `fuse="force"`.
 """
 from __future__ import annotations
 
@@ -70,8 +73,19 @@ class CoreNet(nn.Module):
         self.fuse = fuse
 
     # ------------------------------------------------------------------------------------------------
+    def _known_units(self, stage: int) -> bool:
+        """The fused tail replaces Regular's last two lines, Depth_regress and Confidence_regress: it may only do so when those
+        are the functions it reimplements -- the reference's (net/unit/regress.py, net/unit/regular.py) or this package's --
+        never a user's own callable that merely has a `.prob` attribute.  `fuse="force"` skips the check."""
+        if self.fuse == "force":
+            return True
+        def known(fn, name):
+            return getattr(fn, "__name__", "") == name and getattr(fn, "__module__", "").rsplit(".", 1)[-1] in ("regress", "units")
+        reg_ok = type(self.Regular[stage]).__name__ in ("RegularNet_3Scales", "RegularNet_4Scales") or getattr(self.Regular[stage], "mdf_fusable_tail", False)
+        return reg_ok and known(self.Depth_regress, "depth_regression") and known(self.Confidence_regress, "confidence_regress")
+
     def _can_fuse(self, stage: int, cost_volume: torch.Tensor) -> bool:
-        if not self.fuse or self.training or not cost_volume.is_cuda:
+        if not self.fuse or self.training or not cost_volume.is_cuda or not self._known_units(stage):
             return False
         if torch.is_grad_enabled() and (cost_volume.requires_grad or any(p.requires_grad for p in self.Regular[stage].parameters())):
             return False              # the fused tail has no backward: training / fine-tuning goes through the injected units

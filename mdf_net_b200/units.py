@@ -13,6 +13,7 @@ Homoaggre, Regular, Regress, Refine)` (net/core.py:5-26, wired in config.py:186-
 """
 from __future__ import annotations
 
+import warnings
 from typing import Sequence
 
 import torch
@@ -52,9 +53,20 @@ class VectorAggregate(nn.Module):
         cbr, fc = self.depth_weight[0], self.depth_weight[1]
         needs_grad = torch.is_grad_enabled() and any(t.requires_grad for t in (*features, *self.parameters()))
         if self.training or needs_grad:
-            # train-mode BatchNorm (batch statistics per source view) and / or autograd: csrc/mdf_backward.cu
-            from . import autograd
-            return autograd.vector_aggregate_train(self, list(features), ref_proj, list(src_projs), depth_hypos)
+            # train-mode BatchNorm (batch statistics per source view) and / or autograd: csrc/mdf_backward.cu.
+            # (Inference should run under torch.no_grad(), as eval.py:24 does: an eval-mode call with grad enabled and
+            # parameters that require grad takes this differentiable path, which saves the inputs for backward.)
+            C = features[0].shape[1]
+            if C != 2 * self.ngroups or self.ngroups not in (8, 16, 32):
+                if self.training:
+                    raise NotImplementedError(
+                        f"mdfnet_b200: train-mode VectorAggregate needs C == 2*G with G in (8, 16, 32) (the reference's configured "
+                        f"stages, config.py:196-205); got C={C}, G={self.ngroups}")
+                warnings.warn(f"mdfnet_b200: no backward kernel for C={C}, G={self.ngroups}: this eval-mode call runs the "
+                              "non-differentiable kernel (wrap inference in torch.no_grad())", RuntimeWarning, stacklevel=2)
+            else:
+                from . import autograd
+                return autograd.vector_aggregate_train(self, list(features), ref_proj, list(src_projs), depth_hypos)
         return ops.cost_volume(list(features), ref_proj, list(src_projs), depth_hypos,
                                cbr.conv.weight, cbr.bn.weight, cbr.bn.bias, cbr.bn.running_mean, cbr.bn.running_var,
                                cbr.bn.eps, fc.weight, fc.bias, self.ngroups, self.algo)

@@ -63,6 +63,7 @@ class _Backbone(nn.Module):
 
 class _Regular(nn.Module):
     """Stand-in regulariser with the reference's tail: ... -> self.prob -> squeeze -> softmax (regular.py:43,67-69)."""
+    mdf_fusable_tail = True       # opts in to the fused tail (custom modules are not fused unless they say so)
 
     def __init__(self, in_chs, c0):
         super().__init__()
@@ -162,3 +163,24 @@ def test_regulariser_body_stops_the_reference_modules_in_front_of_prob():
         assert torch.equal(got, want)
         assert len(net.prob._forward_pre_hooks) == 0
         assert _fusable_prob_layer(net) is net.prob
+
+
+def test_fused_tail_only_replaces_the_units_it_reimplements():
+    """A user's own regress callable, or a regulariser that merely has a `.prob` layer, is never bypassed silently."""
+    import mdf_net_b200 as mdf
+
+    class Plain(nn.Module):                     # has .prob but did not opt in
+        def __init__(self):
+            super().__init__()
+            self.prob = nn.Conv3d(8, 1, 3, padding=1, bias=False)
+
+    def my_depth(prob_volume, depth_hypos):      # a custom regression with another name
+        return (prob_volume * depth_hypos).sum(1)
+
+    hyp = nn.ModuleList([mdf.HyposByFit(8, None, 0.0)])
+    args = lambda reg, regress: (nn.Identity(), hyp, None, nn.ModuleList([mdf.VectorAggregate(8)]), nn.ModuleList([reg]), regress, nn.Identity())
+    ok = mdf.CoreNet(*args(_Regular(8, 8), [mdf.depth_regression, mdf.confidence_regress]))
+    assert ok._known_units(0)
+    assert not mdf.CoreNet(*args(Plain(), [mdf.depth_regression, mdf.confidence_regress]))._known_units(0)
+    assert not mdf.CoreNet(*args(_Regular(8, 8), [my_depth, mdf.confidence_regress]))._known_units(0)
+    assert mdf.CoreNet(*args(Plain(), [my_depth, mdf.confidence_regress]), fuse="force")._known_units(0)

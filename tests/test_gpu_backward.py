@@ -2,8 +2,8 @@
 
 References: (1) gradients of the unmodified reference under torch autograd (tests/golden/vecagg_grad_*.npz),
 (2) tests/torch_ref.py -- a plain-PyTorch restatement pinned on (1) by the CPU suite -- evaluated on the GPU
-in float64 (mid sizes) or float32 (BlendedMVS train shape, batch 8).  Tolerance: gradients rel-L2 < 1e-4
-(float32 atomics reorder the scatter), cost volume rel-L2 < 1e-5.
+in float64 (mid sizes and the BlendedMVS train shape, batch 8).  Tolerance: cost volume rel-L2 < 1e-5; gradients as close
+to float64 autograd as float32 autograd of the same formulae is, and rel-L2 < 1e-4 where float32 autograd is that good.
 """
 import numpy as np
 import pytest
@@ -116,17 +116,20 @@ def test_gradients_vs_float64_autograd(stage, training):
     compare(r, ref, ref32, f"stage {stage} training={training}")
 
 
-@pytest.mark.parametrize("stage", [0, 2])
+@pytest.mark.parametrize("stage", [0, 1, 2])
 def test_blendedmvs_train_shape_batch8(stage):
-    """BASELINE.json configs[4]: 768x576, N=5, batch 8, forward + backward vs autograd of the restatement."""
+    """BASELINE.json configs[4]: 768x576, N=5, batch 8, train-mode forward + backward, all three stages, against FLOAT64
+    autograd of the restatement with the mid-size criterion: the CUDA gradients are as close to float64 as float32
+    autograd of the same formulae is (the float64 graph of the whole batch fits the 180 GB of a B200)."""
     feats, ref_proj, src_projs, hyp, p, G, gout = case(stage, 576, 768, 5, 8, seed=600)
     m = make_module(G, p)
     m.train(True)
     r = run_module(m, feats, ref_proj, src_projs, hyp, gout)
-    ref = reference_grads(feats, ref_proj, src_projs, hyp, p, G, gout, True, torch.float32)
-    assert rel_l2(r["cv"], ref["cv"]) < 1e-5
-    assert rel_l2(r["gf"], ref["gf"]) < 3e-3       # the reference side is float32 autograd here (see compare())
-    assert rel_l2(r["gcw"], ref["gcw"]) < 2e-2
+    ref = reference_grads(feats, ref_proj, src_projs, hyp, p, G, gout, True, torch.float64)
+    torch.cuda.empty_cache()
+    ref32 = reference_grads(feats, ref_proj, src_projs, hyp, p, G, gout, True, torch.float32)
+    torch.cuda.empty_cache()
+    compare(r, ref, ref32, f"BlendedMVS train shape, stage {stage}")
 
 
 def test_backward_is_linear_and_eval_train_paths_agree():
