@@ -367,6 +367,35 @@ def time_other_rows(dev):
     hyp = cu(syn.uniform_hypos(1, 48))
     t = med(lambda: ops.homo_warp(f, cu(P[:, 1]), cu(P[:, 0]), hyp))
     out["homo_warp_stage0"] = {"ms": t, "output_GBps": 64 * 48 * H * W * 4 / 1e9 / (t / 1e3)}
+    # the FPN hand-off: one view's three cost volumes from prepared maps (setup + hot kernel, no layout pass),
+    # next to the NCHW drop-in entry on features of the same content; and the library's 1x1 output convolutions (N views)
+    try:
+        K, E = syn.camera_rig(1, 5, 1152, 1600, seed=1)
+        nchw, prepped, conv1x1 = [], [], []
+        for s in range(3):
+            H, W = syn.stage_shapes(1152, 1600)[s]
+            C, D, G = syn.STAGE_CHANNELS[s], syn.STAGE_DEPTHS[s], syn.STAGE_GROUPS[s]
+            P = syn.projection_matrices(K, E, 2.0 ** (3 - s))
+            gen = torch.Generator(device=dev).manual_seed(70 + s)
+            xs = [torch.nn.functional.avg_pool2d(torch.randn((1, 64, H, W), device=dev, generator=gen), 3, 1, 1) * 3.0 for _ in range(5)]
+            wt = torch.randn((C, 64), device=dev, generator=gen) * 0.08
+            hyp = cu(syn.uniform_hypos(1, D) if s == 0 else syn.scene_hypos(1, D, H, W, seed=1))
+            m = mdf.VectorAggregate(G).to(dev).eval()
+            cwt = m.depth_weight[0].conv.weight
+            rp, sps = cu(P[:, 0]), [cu(P[:, v]) for v in range(1, 5)]
+            feats = [torch.nn.functional.conv2d(x, wt.view(C, 64, 1, 1)) for x in xs]
+            with torch.no_grad():
+                conv1x1.append(med(lambda: [ops.fpn_out_prepped(x, wt, G, cwt, i == 0) for i, x in enumerate(xs)]))
+                q4, cq4 = ops.fpn_out_prepped(xs[0], wt, G, cwt, True)
+                s4 = torch.stack([ops.fpn_out_prepped(x, wt, G, cwt, False)[0] for x in xs[1:]], 0)
+                nchw.append(med(lambda: m(feats, rp, sps, hyp)))
+                prepped.append(med(lambda: m(mdf.PreppedFeatures(q4, cq4, s4), rp, sps, hyp)))
+            del xs, feats, s4, q4, cq4
+        out["fpn_handoff_1600x1152_n5"] = {"cost_volume_nchw_entry_ms": nchw, "cost_volume_prepped_entry_ms": prepped,
+                                           "library_1x1_output_convs_5_views_ms": conv1x1,
+                                           "note": "eager calls, CUDA events, median of 5; the prepared entry runs setup + hot kernel (no prep_kernel)"}
+    except Exception as e:  # pragma: no cover
+        out["fpn_handoff_1600x1152_n5"] = {"error": f"{type(e).__name__}: {e}"}
     S, Hf, Wf = 10, 1200, 1600
     Kf, Ef = syn.camera_rig(1, S + 1, Hf, Wf, seed=321)
     gen = torch.Generator(device=dev).manual_seed(1)

@@ -97,6 +97,28 @@ MDF_API int mdf_cost_volume_fwd(const float *const *features,   /* HOST array of
                         void *workspace, size_t workspace_bytes,
                         mdf_stream_t stream);
 
+/* ---- optional fast entry: the FPN hand-off ---------------------------------------
+ * The reference's backbone ends every scale with a bias-free 1x1 convolution (net/unit/backbone.py:43-45, 59-63):
+ * features[k] = out_k(x_k).  mdf_fpn_out_prepped_fwd IS that convolution for one view, writing the hot kernel's own input
+ * layout instead of NCHW features: per float4 plane j (groups 4j..4j+3) and pixel
+ *     source view (s4 != NULL, q4 = cq4 = NULL):   s4 = (y[2g+1] - y[2g]) * log2(e)              (B, G/4, H, W, 4)
+ *     reference view (s4 == NULL):                 q4 = 2*sigmoid(y[2g] - y[2g+1]) - 1,  cq4 = depth_weight_conv[g] * q4
+ * with y = out_weight (2G, Cin) applied to x (B, Cin, H, W).  mdf_cost_volume_fwd_prepped then computes the same cost
+ * volume as mdf_cost_volume_fwd from those maps (s4: the N-1 source views back to back, (N-1, B, G/4, H, W, 4)) without
+ * the layout pass.  C == 2G with G in {8, 16, 32}; Cin a multiple of 4.  The NCHW entry point above stays the drop-in. */
+MDF_API int mdf_fpn_out_prepped_fwd(const float *x, const float *out_weight, int B, int Cin, int G, int H, int W,
+                                    const float *depth_weight_conv, float *s4, float *q4, float *cq4, mdf_stream_t stream);
+
+MDF_API size_t mdf_cost_volume_prepped_workspace_bytes(int B, int N);
+
+MDF_API int mdf_cost_volume_fwd_prepped(const float *s4, const float *q4, const float *cq4, int N, const float *ref_proj,
+                                        const float *const *src_projs, const float *depth_hypos, int hypos_per_pixel,
+                                        const float *conv_weight, const float *bn_weight, const float *bn_bias,
+                                        const float *bn_mean, const float *bn_var, float bn_eps,
+                                        const float *fc_weight, const float *fc_bias,
+                                        int B, int G, int D, int H, int W, float *cost_volume,
+                                        void *workspace, size_t workspace_bytes, mdf_stream_t stream);
+
 /* ---- VectorAggregate under autograd / in train mode (C == 2*G, G in {8,16,32}) ---------------
  * Reference: net/unit/homoaggregate.py:25-46 driven by torch autograd (train.py:33-50).
  * training != 0: BatchNorm3d uses the batch statistics of each source view's z over (B,D,H,W) (the module is

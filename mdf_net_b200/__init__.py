@@ -7,8 +7,8 @@ CUDA kernels behind a C ABI
 calling an op without the built library or with CPU tensors raises.
 """
 from .core import CoreNet
-from .units import (HyposByFit, VectorAggregate, check_geometric_consistency, confidence_regress, depth_regression,
+from .units import (FPNHandOff, HyposByFit, PreppedFeatures, VectorAggregate, check_geometric_consistency, confidence_regress, depth_regression,
                     geometric_filter, homo_aggregate_by_variance, homo_warping, softmax_regress)
 
 __all__ = ["VectorAggregate", "homo_warping", "homo_aggregate_by_variance", "depth_regression", "confidence_regress",
-           "softmax_regress", "HyposByFit", "CoreNet", "check_geometric_consistency", "geometric_filter"]
+           "softmax_regress", "HyposByFit", "CoreNet", "FPNHandOff", "PreppedFeatures", "check_geometric_consistency", "geometric_filter"]

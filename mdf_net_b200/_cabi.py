@@ -33,6 +33,10 @@ SIGNATURES = {
                                  _I, _I, _I, _I, _I, _I, _P, _P, c_size_t, _P]),
     "mdf_cost_volume_fwd_ex": (_I, [_P, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P, c_float, _P, _P,
                                     _I, _I, _I, _I, _I, _I, _P, _P, c_size_t, _I, _P, _P, _P]),
+    "mdf_fpn_out_prepped_fwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "mdf_cost_volume_prepped_workspace_bytes": (c_size_t, [_I] * 2),
+    "mdf_cost_volume_fwd_prepped": (_I, [_P, _P, _P, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P, c_float, _P, _P,
+                                         _I, _I, _I, _I, _I, _P, _P, c_size_t, _P]),
     "mdf_variance_volume_workspace_bytes": (c_size_t, [_I] * 6),
     "mdf_variance_volume_fwd": (_I, [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, c_size_t, _P]),
     "mdf_softmax_regress_fwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P]),

@@ -15,7 +15,7 @@ CSRC = os.path.join(PKG, "csrc")
 INCLUDE = os.path.join(os.path.dirname(PKG), "include")
 LIB_PATH = os.path.join(PKG, "libmdf_b200.so")
 TUNING_LIB_PATH = os.path.join(PKG, "libmdf_b200_tuning.so")   # -DMDF_TUNING: shape / diagnostic variants for tools/ (never the product)
-SOURCES = ("mdf_cost_volume.cu", "mdf_head.cu", "mdf_backward.cu", "mdf_hypos.cu", "mdf_prob_head.cu", "mdf_filter.cu")
+SOURCES = ("mdf_cost_volume.cu", "mdf_head.cu", "mdf_backward.cu", "mdf_hypos.cu", "mdf_prob_head.cu", "mdf_filter.cu", "mdf_fpn.cu")
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

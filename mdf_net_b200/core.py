@@ -61,8 +61,12 @@ class CoreNet(nn.Module):
     """net/core.py:4-78 with fused stage tails.  forward(origin_imgs, extrinsics, intrinsics, depth_range) ->
     {"depth", "confidence"} in eval mode, {"depth": [per-stage depths..., refined]} in training mode."""
 
-    def __init__(self, Backbone, Depth_hypos, scale, Homoaggre, Regular, Regress, Refine, fuse: bool = True):
+    def __init__(self, Backbone, Depth_hypos, scale, Homoaggre, Regular, Regress, Refine, fuse: bool = True,
+                 fpn_handoff: bool = False):
         super().__init__()
+        # fpn_handoff: (inference, opt-in) run the backbone without its 1x1 output convolutions and let the library apply them
+        # straight into the cost-volume kernel's input layout (units.FPNHandOff, SURVEY 8f row 3)
+        self.fpn_handoff = fpn_handoff
         self.Backbone = Backbone
         self.Depth_hypos = Depth_hypos
         self.scale = scale
@@ -99,12 +103,19 @@ class CoreNet(nn.Module):
 
     def forward(self, origin_imgs, extrinsics, intrinsics, depth_range):
         views = torch.unbind(origin_imgs.float(), 1)
-        features = [self.Backbone(img) for img in views]                                   # core.py:42
+        from .units import FPNHandOff, VectorAggregate
+        handoff = (self.fpn_handoff and not self.training and not torch.is_grad_enabled() and origin_imgs.is_cuda
+                   and FPNHandOff.supports(self.Backbone) and all(isinstance(h, VectorAggregate) for h in self.Homoaggre))
+        if handoff:
+            prepped = FPNHandOff(self.Backbone)(views, list(self.Homoaggre))
+            features = None
+        else:
+            features = [self.Backbone(img) for img in views]                               # core.py:42
         nstages = len(self.Depth_hypos)
         depth = depth_hypos = prob_volume = fitted = None
         depths, confidence = [], None
         for stage in range(nstages):
-            feature = [f[stage] for f in features]
+            feature = prepped[stage] if handoff else [f[stage] for f in features]
             ref_proj, src_projs = self.scale(intrinsics, extrinsics, stage)                # core.py:52
             unit = self.Depth_hypos[stage]
             if fitted is not None:

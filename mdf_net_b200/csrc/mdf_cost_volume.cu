@@ -459,6 +459,11 @@ static int run_setup(const float* const* src_projs, const float* ref_proj, int V
     return launch_status();
 }
 
+int launch_staged_eval(int G, const StagedArgs& a, const StagedBuffers& S, cudaStream_t stream)
+{
+    return launch_staged_default<0>(G, a, S, stream);
+}
+
 }  // namespace mdf
 
 using namespace mdf;

@@ -735,6 +735,8 @@ static int launch_staged_train(int G, const StagedArgs& a, const StagedBuffers& 
 {
     return launch_staged_default<MODE>(G, a, S, stream);
 }
+// the eval-mode launch for other translation units (defined in mdf_cost_volume.cu: one instantiation of the kernels)
+int launch_staged_eval(int G, const StagedArgs& a, const StagedBuffers& S, cudaStream_t stream);
 
 #ifdef MDF_TUNING
 //                         G  PT TH PG  BW  BH MINB CQS   EARLY  BF    RCP2   TRACE  ABL

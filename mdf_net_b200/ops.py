@@ -7,6 +7,8 @@ hard error, there is no fallback (BASELINE.json north_star).
 
 Reference call sites replaced (file:line into the reference checkout):
   cost_volume       net/unit/homoaggregate.py:25-46   VectorAggregate.forward (eval-mode BN)
+  fpn_out_prepped   net/unit/backbone.py:43-45,59-63  the FPN's 1x1 output convolutions, emitting the hot kernel's layout
+  cost_volume_prepped  the same cost volume from those maps (optional fast entry, no layout pass)
   homo_warp         net/unit/base.py:85-126           homo_warping
   variance_volume   net/unit/homoaggregate.py:49-69   homo_aggregate_by_variance
   softmax_regress   net/unit/regular.py:67-69,130-133 + net/unit/regress.py:5-25
@@ -25,7 +27,7 @@ from torch import Tensor
 
 from . import _cabi
 
-__all__ = ["cost_volume", "homo_warp", "variance_volume", "softmax_regress", "softmax_regress_fit", "prob_head", "depth_regression",
+__all__ = ["cost_volume", "cost_volume_prepped", "fpn_out_prepped", "homo_warp", "variance_volume", "softmax_regress", "softmax_regress_fit", "prob_head", "depth_regression",
            "confidence", "hypos_fit", "hypos_generate", "geo_filter",
            "launch_count", "reset_launch_count", "time_next_hot_kernel"]
 
@@ -141,6 +143,73 @@ def _(features, ref_proj, src_projs, depth_hypos, conv_weight, bn_weight, bn_bia
       fc_weight, fc_bias, groups, algo=0):
     B, _, H, W = features[0].shape
     return features[0].new_empty((B, groups, depth_hypos.shape[1], H, W))
+
+
+# ------------------------------------------------------------- FPN hand-off (optional fast entry)
+@torch.library.custom_op("mdfnet_b200::fpn_out_prepped", mutates_args=(), device_types="cuda")
+def fpn_out_prepped(x: Tensor, out_weight: Tensor, groups: int, depth_weight_conv: Tensor, is_reference: bool) -> Tuple[Tensor, Tensor]:
+    """The FPN's bias-free 1x1 output convolution (backbone.py:43-45, 59-63) of ONE view, emitting the hot kernel's input
+    layout instead of NCHW features.  x (B,Cin,H,W), out_weight (2G,Cin[,1,1]).  Source view: returns (S4, empty) with
+    S4 (B,G/4,H,W,4) = (y[2g+1]-y[2g])*log2(e); reference view: returns (Q4, CQ4), Q4 = 2*sigmoid(y[2g]-y[2g+1])-1 and
+    CQ4 = depth_weight.0.conv.weight[g] * Q4."""
+    xx = _f32c(x, "x")
+    B, Cin, H, W = xx.shape
+    w = _f32c(out_weight, "out_weight").reshape(out_weight.shape[0], -1)
+    if w.shape != (2 * groups, Cin):
+        raise RuntimeError(f"mdfnet_b200: out_weight must be (2*groups, Cin) = {(2 * groups, Cin)}, got {tuple(w.shape)}")
+    J = groups // 4
+    a = torch.empty((B, J, H, W, 4), dtype=torch.float32, device=xx.device)
+    b = torch.empty((B, J, H, W, 4), dtype=torch.float32, device=xx.device) if is_reference else torch.empty(0, device=xx.device)
+    cw = _f32c(depth_weight_conv, "depth_weight_conv").reshape(-1) if is_reference else None
+    st = _cabi.lib().mdf_fpn_out_prepped_fwd(xx.data_ptr(), w.data_ptr(), B, Cin, groups, H, W,
+                                             cw.data_ptr() if is_reference else None,
+                                             None if is_reference else a.data_ptr(),
+                                             a.data_ptr() if is_reference else None, b.data_ptr() if is_reference else None, _stream(xx))
+    _cabi.check("mdf_fpn_out_prepped_fwd", st)
+    _count(_LAUNCHES_SIMPLE)
+    return a, b
+
+
+@fpn_out_prepped.register_fake
+def _(x, out_weight, groups, depth_weight_conv, is_reference):
+    B, _, H, W = x.shape
+    a = x.new_empty((B, groups // 4, H, W, 4))
+    return a, (x.new_empty((B, groups // 4, H, W, 4)) if is_reference else x.new_empty(0))
+
+
+@torch.library.custom_op("mdfnet_b200::cost_volume_prepped", mutates_args=(), device_types="cuda")
+def cost_volume_prepped(s4: Tensor, q4: Tensor, cq4: Tensor, ref_proj: Tensor, src_projs: List[Tensor], depth_hypos: Tensor,
+                        conv_weight: Tensor, bn_weight: Tensor, bn_bias: Tensor, bn_mean: Tensor, bn_var: Tensor,
+                        bn_eps: float, fc_weight: Tensor, fc_bias: Tensor, groups: int) -> Tensor:
+    """The fused cost volume from prepared maps: s4 (V,B,G/4,H,W,4) of the V source views, q4 / cq4 (B,G/4,H,W,4) of the
+    reference view (ops.fpn_out_prepped).  Same result as ops.cost_volume on the NCHW features, no layout pass."""
+    S, Q, CQ = _f32c(s4, "s4"), _f32c(q4, "q4"), _f32c(cq4, "cq4")
+    if S.dim() != 6 or Q.dim() != 5 or S.shape[1:] != Q.shape or Q.shape != CQ.shape or S.shape[2] * 4 != groups or S.shape[-1] != 4:
+        raise RuntimeError(f"mdfnet_b200: s4 {tuple(S.shape)} / q4 {tuple(Q.shape)} / cq4 {tuple(CQ.shape)} do not fit groups={groups}")
+    V, B, _, H, W, _ = S.shape
+    if len(src_projs) != V:
+        raise RuntimeError(f"mdfnet_b200: {V} source views in s4, {len(src_projs)} source projections")
+    hyp, D, per_pixel = _hypos(depth_hypos, B, H, W)
+    projs = [_f32c(p, "src_projs") for p in src_projs]
+    refp = _f32c(ref_proj, "ref_proj")
+    params = [_f32c(t, n) for t, n in ((conv_weight, "conv_weight"), (bn_weight, "bn_weight"), (bn_bias, "bn_bias"),
+                                        (bn_mean, "bn_mean"), (bn_var, "bn_var"), (fc_weight, "fc_weight"), (fc_bias, "fc_bias"))]
+    lib = _cabi.lib()
+    out = torch.empty((B, groups, D, H, W), dtype=torch.float32, device=S.device)
+    ws = _workspace(lib.mdf_cost_volume_prepped_workspace_bytes(B, V + 1), out.device)
+    st = lib.mdf_cost_volume_fwd_prepped(
+        S.data_ptr(), Q.data_ptr(), CQ.data_ptr(), V + 1, refp.data_ptr(), _cabi.ptr_array([p.data_ptr() for p in projs]),
+        hyp.data_ptr(), per_pixel, params[0].data_ptr(), params[1].data_ptr(), params[2].data_ptr(), params[3].data_ptr(),
+        params[4].data_ptr(), float(bn_eps), params[5].data_ptr(), params[6].data_ptr(), B, groups, D, H, W,
+        out.data_ptr(), ws.data_ptr(), ws.numel(), _stream(out))
+    _cabi.check("mdf_cost_volume_fwd_prepped", st)
+    _count(_LAUNCHES_STAGED - 1)              # setup + hot kernel: no layout pass
+    return out
+
+
+@cost_volume_prepped.register_fake
+def _(s4, q4, cq4, ref_proj, src_projs, depth_hypos, conv_weight, bn_weight, bn_bias, bn_mean, bn_var, bn_eps, fc_weight, fc_bias, groups):
+    return s4.new_empty((s4.shape[1], groups, depth_hypos.shape[1], s4.shape[3], s4.shape[4]))
 
 
 # -------------------------------------------------------------------------------------- homo_warp

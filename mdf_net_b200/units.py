@@ -51,6 +51,12 @@ class VectorAggregate(nn.Module):
     def forward(self, features: Sequence[Tensor], ref_proj: Tensor, src_projs: Sequence[Tensor],
                 depth_hypos: Tensor) -> Tensor:
         cbr, fc = self.depth_weight[0], self.depth_weight[1]
+        if isinstance(features, PreppedFeatures):          # the FPN hand-off (inference only): no layout pass
+            if self.training:
+                raise RuntimeError("mdfnet_b200: prepared features are an inference path (no backward through the hand-off)")
+            return ops.cost_volume_prepped(features.s4, features.q4, features.cq4, ref_proj, list(src_projs), depth_hypos,
+                                           cbr.conv.weight, cbr.bn.weight, cbr.bn.bias, cbr.bn.running_mean, cbr.bn.running_var,
+                                           cbr.bn.eps, fc.weight, fc.bias, self.ngroups)
         needs_grad = torch.is_grad_enabled() and any(t.requires_grad for t in (*features, *self.parameters()))
         if self.training or needs_grad:
             # train-mode BatchNorm (batch statistics per source view) and / or autograd: csrc/mdf_backward.cu.
@@ -70,6 +76,60 @@ class VectorAggregate(nn.Module):
         return ops.cost_volume(list(features), ref_proj, list(src_projs), depth_hypos,
                                cbr.conv.weight, cbr.bn.weight, cbr.bn.bias, cbr.bn.running_mean, cbr.bn.running_var,
                                cbr.bn.eps, fc.weight, fc.bias, self.ngroups, self.algo)
+
+
+class PreppedFeatures:
+    """What `FPNHandOff` hands to `VectorAggregate` instead of the list of NCHW feature maps: the hot kernel's own input
+    layout for one stage (q4 / cq4 of the reference view, s4 of the source views back to back)."""
+
+    def __init__(self, q4: Tensor, cq4: Tensor, s4: Tensor):
+        self.q4, self.cq4, self.s4 = q4, cq4, s4
+
+
+class FPNHandOff(nn.Module):
+    """Optional fast entry.  Wraps a backbone shaped like the reference's FPN_4Scales
+    (net/unit/backbone.py:9-66: trunk conv01..conv34, laterals lat2 / lat3, bias-free 1x1 output convolutions out4 / out3 /
+    out2) and runs it up to -- not including -- those output convolutions; `ops.fpn_out_prepped` then applies them and
+    writes the pair-difference maps the cost-volume kernel gathers from, so neither the NCHW features nor the layout pass
+    exist on this path.  The wrapped module is used as it is (same parameters, same state-dict keys).
+
+    forward(views, aggregates) -> [PreppedFeatures per stage]; views: the N images, view 0 = reference (core.py:39-42);
+    aggregates: the VectorAggregate of every stage (their depth_weight.0.conv.weight goes into cq4)."""
+
+    def __init__(self, backbone: nn.Module):
+        super().__init__()
+        self.backbone = backbone
+
+    @staticmethod
+    def supports(backbone: nn.Module) -> bool:
+        names = ("conv01", "conv12", "conv23", "conv34", "lat2", "lat3", "out2", "out3", "out4")
+        if not all(hasattr(backbone, n) for n in names):
+            return False
+        return all(isinstance(c, nn.Conv2d) and c.bias is None and tuple(c.kernel_size) == (1, 1) and tuple(c.stride) == (1, 1)
+                   and c.groups == 1 and c.in_channels % 4 == 0 for c in (backbone.out2, backbone.out3, backbone.out4))
+
+    def trunk(self, x: Tensor):
+        """backbone.py:51-63 without the three output convolutions: the merged maps at 1/8, 1/4, 1/2."""
+        bb = self.backbone
+        x2 = bb.conv12(bb.conv01(x))
+        x3 = bb.conv23(x2)
+        x4 = bb.conv34(x3)
+        m3 = nn.functional.interpolate(x4, scale_factor=2.0, mode="bilinear", align_corners=False) + bb.lat3(x3)
+        m2 = nn.functional.interpolate(m3, scale_factor=2.0, mode="bilinear", align_corners=False) + bb.lat2(x2)
+        return x4, m3, m2
+
+    def forward(self, views: Sequence[Tensor], aggregates: Sequence["VectorAggregate"]):
+        bb = self.backbone
+        outs = (bb.out4, bb.out3, bb.out2)
+        stages = [dict(q4=None, cq4=None, s4=[]) for _ in outs]
+        for v, img in enumerate(views):
+            for st, conv, agg, m in zip(stages, outs, aggregates, self.trunk(img)):
+                a, b = ops.fpn_out_prepped(m, conv.weight, agg.ngroups, agg.depth_weight[0].conv.weight, v == 0)
+                if v == 0:
+                    st["q4"], st["cq4"] = a, b
+                else:
+                    st["s4"].append(a)
+        return [PreppedFeatures(st["q4"], st["cq4"], torch.stack(st["s4"], 0)) for st in stages]
 
 
 def homo_warping(src_fea: Tensor, src_proj: Tensor, ref_proj: Tensor, depth_hypos: Tensor) -> Tensor:
