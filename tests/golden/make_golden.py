@@ -421,8 +421,24 @@ def gen_corenet():
     save("corenet_64x64_n3", **cap)
 
 
+def gen_output_files():
+    """The files eval.py:36-50 writes per view, byte for byte: depth PFM, depth PNG ((d-500)/2 as 8-bit), confidence PFM
+    (tools/data_io.py:44-75), on a small seeded depth / confidence pair."""
+    import tempfile
+    from tools.data_io import save_pfm, write_depth_img
+    rng = np.random.default_rng(12)
+    depth = (700.0 + 150.0 * rng.standard_normal((48, 64))).astype(np.float32)      # some values leave [500, 1010]: the PNG clips
+    conf = rng.random((48, 64), dtype=np.float32)
+    with tempfile.TemporaryDirectory() as d:
+        save_pfm(os.path.join(d, "d.pfm"), torch.from_numpy(depth))
+        write_depth_img(os.path.join(d, "d.png"), depth)
+        save_pfm(os.path.join(d, "c.pfm"), torch.from_numpy(conf))
+        rd = lambda n: np.frombuffer(open(os.path.join(d, n), "rb").read(), np.uint8)
+        save("output_files", depth=depth, confidence=conf, depth_pfm=rd("d.pfm"), depth_png=rd("d.png"), confidence_pfm=rd("c.pfm"))
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
-    for fn in (gen_warp, gen_vecagg, gen_vecagg_grad, gen_varagg, gen_head, gen_hypos, gen_prob_head, gen_geo_filter, gen_scale, gen_corenet):
+    for fn in (gen_output_files, gen_warp, gen_vecagg, gen_vecagg_grad, gen_varagg, gen_head, gen_hypos, gen_prob_head, gen_geo_filter, gen_scale, gen_corenet):
         if not only or fn.__name__ in only:
             fn()
