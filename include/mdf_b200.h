@@ -145,6 +145,7 @@ MDF_API int mdf_cost_volume_bwd(const float *const *features, int N, const float
                                 const float *fc_weight, const float *fc_bias, int training,
                                 int B, int C, int G, int D, int H, int W,
                                 const float *cost_volume /* saved forward output */, const float *grad_out,
+                                const float *batch_stats /* what the training forward returned, or NULL: recomputed */,
                                 float *const *grad_features, float *grad_params,
                                 void *workspace, size_t workspace_bytes, mdf_stream_t stream);
 

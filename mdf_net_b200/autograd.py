@@ -23,7 +23,8 @@ class _VectorAggregateFn(torch.autograd.Function):
         out, stats = ops.cost_volume_train(features, ref_proj, src_projs, depth_hypos, conv_w, bn_w, bn_b, bn_mean, bn_var,
                                            bn_eps, fc_w, fc_b, groups, training)
         # the running statistics may be updated in place after this call: keep the values the forward saw
-        ctx.save_for_backward(ref_proj, depth_hypos, conv_w, bn_w, bn_b, bn_mean.clone(), bn_var.clone(), fc_w, fc_b, out, *tensors)
+        # (`stats`: the batch statistics per source view go back into the backward, which then skips its own statistics sweep)
+        ctx.save_for_backward(ref_proj, depth_hypos, conv_w, bn_w, bn_b, bn_mean.clone(), bn_var.clone(), fc_w, fc_b, out, stats, *tensors)
         ctx.meta = (n_feats, groups, training, bn_eps)
         ctx.mark_non_differentiable(stats)
         return out, stats
@@ -31,11 +32,11 @@ class _VectorAggregateFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out, _grad_stats):
         n_feats, groups, training, bn_eps = ctx.meta
-        ref_proj, depth_hypos, conv_w, bn_w, bn_b, bn_mean, bn_var, fc_w, fc_b, out = ctx.saved_tensors[:10]
-        tensors = ctx.saved_tensors[10:]
+        ref_proj, depth_hypos, conv_w, bn_w, bn_b, bn_mean, bn_var, fc_w, fc_b, out, stats = ctx.saved_tensors[:11]
+        tensors = ctx.saved_tensors[11:]
         features, src_projs = list(tensors[:n_feats]), list(tensors[n_feats:])
         gfeats, gp = ops.cost_volume_bwd(features, ref_proj, src_projs, depth_hypos, conv_w, bn_w, bn_b, bn_mean, bn_var,
-                                         bn_eps, fc_w, fc_b, groups, training, out, grad_out.contiguous())
+                                         bn_eps, fc_w, fc_b, groups, training, out, grad_out.contiguous(), stats)
         g_conv = gp[4:].reshape(conv_w.shape)
         return (None, None, None, None, None, None, g_conv, gp[0:1].reshape(bn_w.shape), gp[1:2].reshape(bn_b.shape),
                 None, None, gp[2:3].reshape(fc_w.shape), gp[3:4].reshape(fc_b.shape), *gfeats, *([None] * len(src_projs)))

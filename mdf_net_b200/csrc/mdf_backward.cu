@@ -13,11 +13,14 @@
 //   w_v = sigmoid(fcw*relu(h_v) + fcb)   out_g = sum_v w_v sim_vg / sum_v w_v
 //
 // The train-mode FORWARD runs the tuned TMA-staged kernel of mdf_staged.cuh twice: in its statistics mode (sum z, sum z^2
-// per source view) and, after the per-view BatchNorm folds (bn_fold_kernel), in its per-view-fold mode.  The BACKWARD
-// kernels below are the simple, correct version: one thread per (b,d,y,x), taps through L1/L2 straight from the
-// planar-float4 maps the prep kernel writes.  Feature gradients are scattered with 128-bit vector reductions
-// (red.global.add.v4.f32) into a difference-gradient map dS4 -- half the atomics of scattering into both
-// channels of a pair -- and a finishing kernel turns dS4 / dQ4 into NCHW feature gradients.
+// per source view) and, after the per-view BatchNorm folds (bn_fold_kernel), in its per-view-fold mode.  The BACKWARD is
+// two sweeps with taps through L1/L2 straight from the planar-float4 maps the prep kernel writes: phase 1, one thread per
+// (b,d,y,x), computes what needs all views of an element (dh_v, z_v, w_v / sum w, the batch sums, d fc); phase 2, one thread
+// per (pixel, view, group slice), walks the depth planes and scatters the feature gradient with 128-bit vector reductions
+// (red.global.add.v4.f32) into a difference-gradient map dS4 -- half the atomics of scattering into both channels of a
+// pair, and only when the sample leaves its source cell (the scatter is what bounds the backward) -- and a finishing
+// kernel turns dS4 / dQ4 into NCHW feature gradients.  The forward's batch statistics come back in through the ABI, so
+// the backward does not repeat the statistics sweep.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -156,7 +159,7 @@ __global__ void bn_fold_kernel(const double* __restrict__ stats, double count, i
                                const float* __restrict__ fc_w, const float* __restrict__ fc_b,
                                const float* __restrict__ cw, int G,
                                float* __restrict__ bnv, float* __restrict__ fc, float* __restrict__ vparams,
-                               float* __restrict__ batch_stats)
+                               float* __restrict__ batch_stats, const float* __restrict__ saved_stats)
 {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     fc[0] = fc_w[0]; fc[1] = fc_b[0];
@@ -165,12 +168,16 @@ __global__ void bn_fold_kernel(const double* __restrict__ stats, double count, i
     hcw *= 0.5;
     for (int v = 0; v < V; ++v) {
         double mean = bn_mean[0], var = bn_var[0];
-        if (training) {
+        if (training && saved_stats) {
+            // the forward's batch statistics (mean, unbiased variance), handed back by the caller: no second statistics sweep
+            mean = (double)saved_stats[2 * v];
+            var = (double)saved_stats[2 * v + 1] * (count > 1.0 ? (count - 1.0) / count : 1.0);
+        } else if (training) {
             const double mk = stats[2 * v] / count;
             mean = mk + hcw;
             var = stats[2 * v + 1] / count - mk * mk;
             if (var < 0.0) var = 0.0;
-            if (batch_stats) {
+            if (batch_stats && training && !saved_stats) {
                 batch_stats[2 * v] = (float)mean;
                 batch_stats[2 * v + 1] = (float)(count > 1.0 ? var * count / (count - 1.0) : var);
             }
@@ -196,7 +203,7 @@ struct BwdArgs {
     const float* out;       // saved forward output (B,G,D,H,W)
     const float* gout;      // upstream gradient      (B,G,D,H,W)
     const double* bsum;     // [V][2] train: sum dh_v, sum dh_v*zhat_v  (phase 1 result)
-    float* za;              // [V][2][B*D*H*W]: z_v and A'_v of every element, written by phase 1, read by phase 2
+    float* za;              // [V][3][B*D*H*W]: dh_v, z_v, w_v / sum w of every element, written by phase 1, read by phase 2
     double count;
     int training;
     float4* dS4;            // [V][B][J][H][W]  zero-initialised
@@ -255,23 +262,28 @@ bwd_stats_kernel(const BwdArgs a, double* __restrict__ bsum)
         wv[v] = view_weight(t, v, zv[v], &hv[v]);
         wsum += wv[v];
     }
-    // hand z_v and A'_v over to the main sweep (it would otherwise gather every view a second time just for them)
+    // hand dh_v, z_v and the normalised view weight over to the main sweep (one thread of which walks the planes of a
+    // (pixel, view) pair: it cannot see the other views of an element), and reduce what only needs per-element values:
+    // the batch sums sum dh_v, sum dh_v*zhat_v per view (train-mode BatchNorm backward; d gamma / d beta in both modes)
+    // and d fc.weight, d fc.bias
     const size_t total = (size_t)t.B * t.D * HW, idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e.ok)
-        for (int v = 0; v < t.V; ++v) {
-            a.za[(size_t)(2 * v) * total + idx] = zv[v];
-            a.za[(size_t)(2 * v + 1) * total + idx] = av[v];
-        }
-    if (!a.training) return;                     // uniform: the batch sums only exist in train mode
+    double gfc[2] = {0.0, 0.0};
     for (int v = 0; v < t.V; ++v) {
         double s[2] = {0.0, 0.0};
         if (e.ok) {
-            const float dh = dh_of(a, av[v], go, wsum, wv[v], hv[v], nullptr);
+            float dact;
+            const float dh = dh_of(a, av[v], go, wsum, wv[v], hv[v], &dact);
             const float zhat = (zv[v] - __ldg(t.bnv + 4 * v + 3)) * __ldg(t.bnv + 4 * v + 2);
             s[0] = dh; s[1] = (double)dh * zhat;
+            gfc[0] += (double)dact * fmaxf(hv[v], 0.0f);
+            gfc[1] += dact;
+            a.za[(size_t)(3 * v) * total + idx] = dh;
+            a.za[(size_t)(3 * v + 1) * total + idx] = zv[v];
+            a.za[(size_t)(3 * v + 2) * total + idx] = wv[v] / wsum;
         }
         block_accumulate<2>(s, bsum + 2 * v);
     }
+    block_accumulate<2>(gfc, a.gparam + 2);
 }
 
 __device__ __forceinline__ void red_add_v4(float4* addr, float4 v)
@@ -280,123 +292,130 @@ __device__ __forceinline__ void red_add_v4(float4* addr, float4 v)
                  ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-// phase 2: everything else.  Registers decide this kernel's speed (one thread carries the gradient state of a whole
-// (b,d,y,x) element), so it is organised in two parts:
-//   A  per-view scalars z_v, A'_v (handed over by phase 1, which needs them anyway), w_v, h_v;
-//   B  the groups in slices of GS = 8: upstream gradients, q, d q and d conv.weight of ONE slice live in registers while
-//      the source views are walked again (the footprint is recomputed per slice: ~100 instructions against ~2000 of
-//      slice work), the tap gradients go out as vector reductions, then the slice's d q / d conv.weight are flushed.
-// G = 32 used 212 registers (1 block per SM) as one piece; sliced it fits 2-3 blocks per SM.
+// phase 2: one thread = one (pixel, source view, slice of GS groups) walking ALL depth planes.
+// Why: the scatter of the tap gradients bounds the backward (340 M 16-byte reductions at the BlendedMVS train shape, stage 0:
+// the LSU needs ~1.3 cycles per lane for them) -- and consecutive planes of a pixel hit the same or the neighbouring source
+// cell (0.1-0.2 px per plane at stages 1-2, ~1 px at stage 0).  So the four tap gradients of the current cell stay in
+// registers while the planes are walked and go out as vector reductions only when the cell changes; when it moves by one
+// column the two shared taps stay.  d q accumulates over the planes too (one reduction per thread instead of one per element),
+// d conv.weight is reduced once per thread.  What a thread cannot see -- the other views of an element -- comes from phase 1
+// (dh_v, z_v, w_v / sum w).
 template <int G>
 __global__ void __launch_bounds__(256, 2)
-bwd_main_kernel(const BwdArgs a)
+bwd_sweep_kernel(const BwdArgs a)
 {
     constexpr int J = G / 4, GS = 8, JS = GS / 4, NS = G / GS;
     const TrainArgs& t = a.t;
-    const Elem e = decode(t);
-    const GridNormFast gn = make_grid_norm_fast(t.H, t.W);
     const size_t HW = (size_t)t.H * t.W;
+    const int s = blockIdx.y % NS, v = (blockIdx.y / NS) % t.V, b = blockIdx.y / (NS * t.V);
+    const size_t pix0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = pix0 < HW;                      // idle lanes of the last block shadow the last pixel and contribute nothing
+    const size_t pix = live ? pix0 : HW - 1;
+    const int x = (int)(pix % t.W), y = (int)(pix / t.W);
+    const GridNormFast gn = make_grid_norm_fast(t.H, t.W);
+    const size_t total = (size_t)t.B * t.D * HW;
     const size_t gstride = (size_t)t.D * HW;
-    const size_t o0 = ((size_t)e.b * G * t.D + e.d) * HW + e.pix;            // element of group 0 in (B,G,D,H,W)
-    float zv[kMaxSrcViews], wv[kMaxSrcViews], hv[kMaxSrcViews], av[kMaxSrcViews];
-    float wsum = 0.0f, go = 0.0f;
-    {   // ---- part A: z_v and A'_v come from phase 1; go = sum_g gout_g out_g is a plain sweep ----
-        const size_t total = (size_t)t.B * t.D * HW, idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-#pragma unroll 8
-        for (int g = 0; g < G; ++g)
-            go = fmaf(e.ok ? __ldg(a.gout + o0 + (size_t)g * gstride) : 0.0f, e.ok ? __ldg(a.out + o0 + (size_t)g * gstride) : 0.0f, go);
-        for (int v = 0; v < t.V; ++v) {
-            zv[v] = e.ok ? __ldg(a.za + (size_t)(2 * v) * total + idx) : 0.0f;
-            av[v] = e.ok ? __ldg(a.za + (size_t)(2 * v + 1) * total + idx) : 0.0f;
-            wv[v] = view_weight(t, v, zv[v], &hv[v]);
-            wsum += wv[v];
-        }
-    }
-    double gp[4] = {0.0, 0.0, 0.0, 0.0};         // d bn_w, d bn_b, d fc_w, d fc_b
-    __shared__ double dcw_s[G];                  // d conv.weight of the block: warp sums land here, one flush at the end
-    if (threadIdx.x < G) dcw_s[threadIdx.x] = 0.0;
+    __shared__ double dcw_s[GS];
+    if (threadIdx.x < GS) dcw_s[threadIdx.x] = 0.0;
     __syncthreads();
-    // ---- part B ----
-    for (int s = 0; s < NS; ++s) {
-        float4 q4[JS];
-        float gout[GS], dq[GS], dcw[GS];
+    const float* rt = t.rt + ((size_t)v * t.B + b) * 12;
+    const RotXYZ r = rot_xyz(rt, (float)x, (float)y);
+    float q[GS], cw[GS];
 #pragma unroll
-        for (int jj = 0; jj < JS; ++jj) q4[jj] = __ldg(t.Q4 + ((size_t)e.b * J + s * JS + jj) * HW + e.pix);
+    for (int jj = 0; jj < JS; ++jj) {
+        const float4 qq = __ldg(t.Q4 + ((size_t)b * J + s * JS + jj) * HW + pix);
+        q[4 * jj] = qq.x; q[4 * jj + 1] = qq.y; q[4 * jj + 2] = qq.z; q[4 * jj + 3] = qq.w;
+    }
 #pragma unroll
-        for (int k = 0; k < GS; ++k) {
-            gout[k] = e.ok ? __ldg(a.gout + o0 + (size_t)(s * GS + k) * gstride) : 0.0f;
-            dq[k] = 0.0f;
-            dcw[k] = 0.0f;
+    for (int k = 0; k < GS; ++k) cw[k] = __ldg(t.cw + s * GS + k);
+    const float invstd = __ldg(t.bnv + 4 * v + 2), mean = __ldg(t.bnv + 4 * v + 3), alpha = __ldg(t.bnv + 4 * v);
+    const float m1 = a.training ? (float)(a.bsum[2 * v] / a.count) : 0.0f, m2 = a.training ? (float)(a.bsum[2 * v + 1] / a.count) : 0.0f;
+    const float4* Sv = t.S4 + (((size_t)v * t.B + b) * J + s * JS) * HW;
+    float4* dSv = a.dS4 + (((size_t)v * t.B + b) * J + s * JS) * HW;
+    float dq[GS], dcw[GS];
+    float gnw[GS], gne[GS], gsw[GS], gse[GS];         // tap gradients of the current cell (cx, cy)
+#pragma unroll
+    for (int k = 0; k < GS; ++k) { dq[k] = 0.0f; dcw[k] = 0.0f; gnw[k] = gne[k] = gsw[k] = gse[k] = 0.0f; }
+    int cx = INT_MIN, cy = INT_MIN;
+    // flush `west` / `east` columns of the cell (cx, cy) with bounds (zero padding: out-of-image taps have no gradient)
+    auto flush = [&](bool west, bool east) {
+        const bool y0in = live && (unsigned)cy < (unsigned)t.H, y1in = live && (unsigned)(cy + 1) < (unsigned)t.H;
+        const bool x0in = (unsigned)cx < (unsigned)t.W, x1in = (unsigned)(cx + 1) < (unsigned)t.W;
+#pragma unroll
+        for (int jj = 0; jj < JS; ++jj) {
+            float4* d = dSv + (size_t)jj * HW + (ptrdiff_t)cy * t.W + cx;
+            if (west && x0in && y0in) red_add_v4(d, make_float4(gnw[4 * jj], gnw[4 * jj + 1], gnw[4 * jj + 2], gnw[4 * jj + 3]));
+            if (west && x0in && y1in) red_add_v4(d + t.W, make_float4(gsw[4 * jj], gsw[4 * jj + 1], gsw[4 * jj + 2], gsw[4 * jj + 3]));
+            if (east && x1in && y0in) red_add_v4(d + 1, make_float4(gne[4 * jj], gne[4 * jj + 1], gne[4 * jj + 2], gne[4 * jj + 3]));
+            if (east && x1in && y1in) red_add_v4(d + t.W + 1, make_float4(gse[4 * jj], gse[4 * jj + 1], gse[4 * jj + 2], gse[4 * jj + 3]));
         }
-        for (int v = 0; v < t.V; ++v) {
-            if (!e.ok) break;
-            float dact;
-            const float dh = dh_of(a, av[v], go, wsum, wv[v], hv[v], &dact);
-            const float invstd = __ldg(t.bnv + 4 * v + 2), mean = __ldg(t.bnv + 4 * v + 3), alpha = __ldg(t.bnv + 4 * v);
-            const float zhat = (zv[v] - mean) * invstd;
-            float dz;
-            if (a.training) {
-                // BatchNorm with batch statistics: dz = (gamma/std) * (dh - mean(dh) - zhat * mean(dh*zhat))
-                const float m1 = (float)(a.bsum[2 * v] / a.count), m2 = (float)(a.bsum[2 * v + 1] / a.count);
-                dz = alpha * (dh - m1 - zhat * m2);
+    };
+    for (int d = 0; d < t.D; ++d) {
+        const size_t idx = ((size_t)b * t.D + d) * HW + pix;
+        const float dh = __ldg(a.za + (size_t)(3 * v) * total + idx), z = __ldg(a.za + (size_t)(3 * v + 1) * total + idx);
+        const float wn = __ldg(a.za + (size_t)(3 * v + 2) * total + idx);
+        const float zhat = (z - mean) * invstd;
+        const float dz = a.training ? alpha * (dh - m1 - zhat * m2) : alpha * dh;
+        const float depth = t.per_pixel ? __ldg(t.hypos + idx) : __ldg(t.hypos + (size_t)b * t.D + d);
+        float ix, iy;
+        sample_position_fast(r, rt, depth, gn, ix, iy);
+        const Taps tp = make_taps(ix, iy, gn.g);
+        if (tp.valid && (tp.x0 != cx || tp.y0 != cy)) {
+            // the cell moved: write out what leaves the 2x2 footprint, keep the column that stays
+            if (tp.y0 == cy && tp.x0 == cx + 1) {
+                flush(true, false);
+#pragma unroll
+                for (int k = 0; k < GS; ++k) { gnw[k] = gne[k]; gsw[k] = gse[k]; gne[k] = 0.0f; gse[k] = 0.0f; }
+            } else if (tp.y0 == cy && tp.x0 == cx - 1) {
+                flush(false, true);
+#pragma unroll
+                for (int k = 0; k < GS; ++k) { gne[k] = gnw[k]; gse[k] = gsw[k]; gnw[k] = 0.0f; gsw[k] = 0.0f; }
             } else {
-                dz = alpha * dh;
-            }
-            if (s == 0) {
-                gp[2] += (double)dact * fmaxf(hv[v], 0.0f);
-                gp[3] += dact;
-                gp[0] += (double)dh * zhat;           // d gamma = sum dh * zhat   (both modes: h = gamma*zhat + beta)
-                gp[1] += dh;                          // d beta
-            }
-            const float wn = wv[v] / wsum;
-            const Taps tp = taps_of(t, e, v, gn);
-            const float4* Sv = t.S4 + ((size_t)v * t.B + e.b) * J * HW;
-            float4* dSv = a.dS4 + ((size_t)v * t.B + e.b) * J * HW;
-            const bool x0in = (unsigned)tp.x0 < (unsigned)t.W, x1in = (unsigned)(tp.x0 + 1) < (unsigned)t.W;
-            const bool y0in = (unsigned)tp.y0 < (unsigned)t.H, y1in = (unsigned)(tp.y0 + 1) < (unsigned)t.H;
+                if (cx != INT_MIN) flush(true, true);
 #pragma unroll
-            for (int jj = 0; jj < JS; ++jj) {
-                const int j = s * JS + jj;
-                float4 tt = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (tp.valid) tt = sample4(Sv + (size_t)j * HW, t.H, t.W, tp);
-                const float tv[4] = {tt.x, tt.y, tt.z, tt.w};
-                const float qv[4] = {q4[jj].x, q4[jj].y, q4[jj].z, q4[jj].w};
-                float dt[4];
+                for (int k = 0; k < GS; ++k) gnw[k] = gne[k] = gsw[k] = gse[k] = 0.0f;
+            }
+            cx = tp.x0; cy = tp.y0;
+        }
+        const float* gp = a.gout + ((size_t)b * G * t.D + d) * HW + pix + (size_t)(s * GS) * gstride;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int gl = 4 * jj + k;
-                    const float p = sigm2(tv[k]);
-                    const float sim = fmaf(qv[k], p - 0.5f, 0.5f);
-                    const float dsim = fmaf(gout[gl], wn, dz * __ldg(t.cw + 4 * j + k));
-                    dcw[gl] = fmaf(dz, sim, dcw[gl]);
-                    dq[gl] = fmaf(dsim, p - 0.5f, dq[gl]);
-                    dt[k] = -kLn2 * p * (1.0f - p) * (dsim * qv[k]);      // dp/dt = -ln2 p (1-p)
-                }
+        for (int jj = 0; jj < JS; ++jj) {
+            float4 tt = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (tp.valid) tt = sample4(Sv + (size_t)jj * HW, t.H, t.W, tp);
+            const float tv[4] = {tt.x, tt.y, tt.z, tt.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int gl = 4 * jj + k;
+                const float p = sigm2(tv[k]);
+                const float sim = fmaf(q[gl], p - 0.5f, 0.5f);
+                const float dsim = fmaf(__ldg(gp + (size_t)gl * gstride), wn, dz * cw[gl]);
+                dcw[gl] = fmaf(dz, sim, dcw[gl]);
+                dq[gl] = fmaf(dsim, p - 0.5f, dq[gl]);
+                const float dt = -kLn2 * p * (1.0f - p) * (dsim * q[gl]);      // dp/dt = -ln2 p (1-p)
                 if (tp.valid) {
-                    float4* d = dSv + (size_t)j * HW + (ptrdiff_t)tp.y0 * t.W + tp.x0;
-                    if (x0in && y0in) red_add_v4(d, make_float4(dt[0] * tp.wnw, dt[1] * tp.wnw, dt[2] * tp.wnw, dt[3] * tp.wnw));
-                    if (x1in && y0in) red_add_v4(d + 1, make_float4(dt[0] * tp.wne, dt[1] * tp.wne, dt[2] * tp.wne, dt[3] * tp.wne));
-                    if (x0in && y1in) red_add_v4(d + t.W, make_float4(dt[0] * tp.wsw, dt[1] * tp.wsw, dt[2] * tp.wsw, dt[3] * tp.wsw));
-                    if (x1in && y1in) red_add_v4(d + t.W + 1, make_float4(dt[0] * tp.wse, dt[1] * tp.wse, dt[2] * tp.wse, dt[3] * tp.wse));
+                    gnw[gl] = fmaf(dt, tp.wnw, gnw[gl]); gne[gl] = fmaf(dt, tp.wne, gne[gl]);
+                    gsw[gl] = fmaf(dt, tp.wsw, gsw[gl]); gse[gl] = fmaf(dt, tp.wse, gse[gl]);
                 }
             }
-        }
-        if (e.ok) {
-            float4* dqp = a.dQ4 + ((size_t)e.b * J + s * JS) * HW + e.pix;
-#pragma unroll
-            for (int jj = 0; jj < JS; ++jj)
-                red_add_v4(dqp + (size_t)jj * HW, make_float4(dq[4 * jj], dq[4 * jj + 1], dq[4 * jj + 2], dq[4 * jj + 3]));
-        }
-#pragma unroll
-        for (int k = 0; k < GS; ++k) {
-            float c = e.ok ? dcw[k] : 0.0f;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-            if ((threadIdx.x & 31) == 0 && c != 0.0f) atomicAdd(&dcw_s[s * GS + k], (double)c);
         }
     }
-    block_accumulate<4>(gp, a.gparam);           // ends with a barrier: dcw_s is complete
-    if (threadIdx.x < G && dcw_s[threadIdx.x] != 0.0) atomicAdd(a.gparam + 4 + threadIdx.x, dcw_s[threadIdx.x]);
+    if (cx != INT_MIN) flush(true, true);
+    if (live) {
+        float4* dqp = a.dQ4 + ((size_t)b * J + s * JS) * HW + pix;
+#pragma unroll
+        for (int jj = 0; jj < JS; ++jj)
+            red_add_v4(dqp + (size_t)jj * HW, make_float4(dq[4 * jj], dq[4 * jj + 1], dq[4 * jj + 2], dq[4 * jj + 3]));
+    }
+    // d conv.weight: warp shuffle -> shared-memory doubles -> one global atomic per block and group
+#pragma unroll
+    for (int k = 0; k < GS; ++k) {
+        float c = live ? dcw[k] : 0.0f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if ((threadIdx.x & 31) == 0 && c != 0.0f) atomicAdd(&dcw_s[k], (double)c);
+    }
+    __syncthreads();
+    if (threadIdx.x < GS && dcw_s[threadIdx.x] != 0.0) atomicAdd(a.gparam + 4 + s * GS + threadIdx.x, dcw_s[threadIdx.x]);
 }
 
 // dS4 / dQ4 -> NCHW feature gradients.  One thread per pixel per view; blockIdx.y = view * B + b.
@@ -432,10 +451,17 @@ bwd_finish_kernel(GradPtrs grads, int B, int G, int HW, const float4* __restrict
     }
 }
 
-__global__ void gparam_to_float_kernel(const double* __restrict__ src, float* __restrict__ dst, int n)
+// d bn.weight = sum_v sum dh_v * zhat_v, d bn.bias = sum_v sum dh_v (the per-view batch sums of phase 1); the rest is in place
+__global__ void gparam_to_float_kernel(const double* __restrict__ src, const double* __restrict__ bsum, int V, float* __restrict__ dst, int n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dst[i] = (float)src[i];
+    if (i >= n) return;
+    double val = src[i];
+    if (i < 2) {
+        val = 0.0;
+        for (int v = 0; v < V; ++v) val += bsum[2 * v + (1 - i)];
+    }
+    dst[i] = (float)val;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -459,7 +485,7 @@ static TrainWorkspace make_train_workspace(int B, int N, int G, int D, int H, in
     w.bnv = take(kMaxSrcViews * 4 * sizeof(float));
     w.vparams = take(kMaxSrcViews * 4 * sizeof(float));
     w.fc = take(2 * sizeof(float));
-    w.za = take(V * 2 * (size_t)B * D * H * W * sizeof(float));      // z_v, A'_v of every element (backward phase 1 -> 2)
+    w.za = take(V * 3 * (size_t)B * D * H * W * sizeof(float));      // dh_v, z_v, w_v / sum w of every element (backward phase 1 -> 2)
     w.stats = take(kMaxSrcViews * 2 * sizeof(double));      // stats | bsum | gparam are contiguous: one memset
     w.bsum = take(kMaxSrcViews * 2 * sizeof(double));
     w.gparam = take((4 + 32) * sizeof(double));
@@ -523,7 +549,7 @@ static StagedBuffers staged_buffers(uint8_t* wsb, const TrainWorkspace& ws)
 
 // prep (S4, Q4, rt) + BatchNorm constants; returns the TrainArgs for the sweeps
 template <int G>
-static int prepare(const TrainCall& c, uint8_t* wsb, const TrainWorkspace& ws, float* batch_stats, cudaStream_t stream, TrainArgs* out)
+static int prepare(const TrainCall& c, uint8_t* wsb, const TrainWorkspace& ws, float* batch_stats, const float* saved_stats, cudaStream_t stream, TrainArgs* out)
 {
     const int V = c.N - 1;
     float* rt = reinterpret_cast<float*>(wsb + ws.rt);
@@ -548,14 +574,14 @@ static int prepare(const TrainCall& c, uint8_t* wsb, const TrainWorkspace& ws, f
     a.hypos = c.hypos; a.per_pixel = c.per_pixel; a.V = V; a.B = c.B; a.D = c.D; a.H = c.H; a.W = c.W;
     const size_t total = (size_t)c.B * c.D * c.H * c.W;
     double* stats = reinterpret_cast<double*>(wsb + ws.stats);
-    if (c.training) {
+    if (c.training && !saved_stats) {
         // batch statistics of z per source view: the TMA-staged gather in its statistics mode (mdf_staged.cuh, MODE 1)
         st = launch_staged_train<1>(G, staged_args(c, wsb, ws, nullptr), staged_buffers(wsb, ws), stream);
         if (st != MDF_OK) return st;
     }
     bn_fold_kernel<<<1, 32, 0, stream>>>(stats, (double)total, V, c.training, c.bn_w, c.bn_b, c.bn_mean, c.bn_var, c.bn_eps,
                                          c.fc_w, c.fc_b, c.conv_w, G, reinterpret_cast<float*>(wsb + ws.bnv),
-                                         reinterpret_cast<float*>(wsb + ws.fc), reinterpret_cast<float*>(wsb + ws.vparams), batch_stats);
+                                         reinterpret_cast<float*>(wsb + ws.fc), reinterpret_cast<float*>(wsb + ws.vparams), batch_stats, saved_stats);
     st = launch_status();
     if (st != MDF_OK) return st;
     *out = a;
@@ -566,18 +592,18 @@ template <int G>
 static int train_fwd(const TrainCall& c, float* cost_volume, float* batch_stats, uint8_t* wsb, const TrainWorkspace& ws, cudaStream_t stream)
 {
     TrainArgs a;
-    int st = prepare<G>(c, wsb, ws, batch_stats, stream, &a);
+    int st = prepare<G>(c, wsb, ws, batch_stats, nullptr, stream, &a);
     if (st != MDF_OK) return st;
     // the forward itself: the TMA-staged kernel with per-view BatchNorm folds (MODE 2)
     return launch_staged_train<2>(G, staged_args(c, wsb, ws, cost_volume), staged_buffers(wsb, ws), stream);
 }
 
 template <int G>
-static int train_bwd(const TrainCall& c, const float* cost_volume, const float* grad_out, float* const* grad_features,
+static int train_bwd(const TrainCall& c, const float* cost_volume, const float* grad_out, const float* saved_stats, float* const* grad_features,
                      float* grad_params, uint8_t* wsb, const TrainWorkspace& ws, cudaStream_t stream)
 {
     BwdArgs a;
-    int st = prepare<G>(c, wsb, ws, nullptr, stream, &a.t);
+    int st = prepare<G>(c, wsb, ws, nullptr, saved_stats, stream, &a.t);
     if (st != MDF_OK) return st;
     a.out = cost_volume; a.gout = grad_out;
     a.bsum = reinterpret_cast<double*>(wsb + ws.bsum);
@@ -589,12 +615,15 @@ static int train_bwd(const TrainCall& c, const float* cost_volume, const float* 
     const size_t total = (size_t)c.B * c.D * c.H * c.W;
     const unsigned blocks = (unsigned)((total + 255) / 256);
     a.za = reinterpret_cast<float*>(wsb + ws.za);
-    bwd_stats_kernel<G><<<blocks, 256, 0, stream>>>(a, reinterpret_cast<double*>(wsb + ws.bsum));      // also in eval mode: it hands z_v, A'_v over
+    bwd_stats_kernel<G><<<blocks, 256, 0, stream>>>(a, reinterpret_cast<double*>(wsb + ws.bsum));      // per-element values for the sweep, batch sums, d fc
     st = launch_status();
     if (st != MDF_OK) return st;
-    bwd_main_kernel<G><<<blocks, 256, 0, stream>>>(a);
-    st = launch_status();
-    if (st != MDF_OK) return st;
+    {
+        const int HWi = c.H * c.W;
+        bwd_sweep_kernel<G><<<dim3((unsigned)((HWi + 255) / 256), (unsigned)(c.B * (c.N - 1) * (G / 8))), 256, 0, stream>>>(a);
+        st = launch_status();
+        if (st != MDF_OK) return st;
+    }
     GradPtrs gp;
     for (int i = 0; i < MDF_MAX_VIEWS; ++i) gp.p[i] = (grad_features && i < c.N) ? grad_features[i] : nullptr;
     const int HW = c.H * c.W;
@@ -603,7 +632,7 @@ static int train_bwd(const TrainCall& c, const float* cost_volume, const float* 
     st = launch_status();
     if (st != MDF_OK) return st;
     if (grad_params) {
-        gparam_to_float_kernel<<<1, 64, 0, stream>>>(a.gparam, grad_params, 4 + G);
+        gparam_to_float_kernel<<<1, 64, 0, stream>>>(a.gparam, a.bsum, c.N - 1, grad_params, 4 + G);
         st = launch_status();
     }
     return st;
@@ -648,8 +677,8 @@ int mdf_cost_volume_bwd(const float* const* features, int N, const float* ref_pr
                         const float* depth_hypos, int hypos_per_pixel, const float* conv_weight, const float* bn_weight,
                         const float* bn_bias, const float* bn_mean, const float* bn_var, float bn_eps, const float* fc_weight,
                         const float* fc_bias, int training, int B, int C, int G, int D, int H, int W, const float* cost_volume,
-                        const float* grad_out, float* const* grad_features, float* grad_params, void* workspace,
-                        size_t workspace_bytes, mdf_stream_t stream)
+                        const float* grad_out, const float* batch_stats, float* const* grad_features, float* grad_params,
+                        void* workspace, size_t workspace_bytes, mdf_stream_t stream)
 {
     const TrainCall c = {features, N, ref_proj, src_projs, depth_hypos, hypos_per_pixel, conv_weight, bn_weight, bn_bias, bn_mean,
                          bn_var, bn_eps, fc_weight, fc_bias, training, B, C, G, D, H, W};
@@ -660,9 +689,10 @@ int mdf_cost_volume_bwd(const float* const* features, int N, const float* ref_pr
     if (st != MDF_OK) return st;
     if ((size_t)B * D * H * W == 0) return MDF_ERR_INVALID_SHAPE;
     {
-        const void* ptrs[MDF_MAX_VIEWS + 2];
+        const void* ptrs[MDF_MAX_VIEWS + 3];
         int n = 0;
         ptrs[n++] = grad_out;
+        if (batch_stats) ptrs[n++] = batch_stats;
         if (grad_params) ptrs[n++] = grad_params;
         if (grad_features)
             for (int i = 0; i < N; ++i)
@@ -673,9 +703,9 @@ int mdf_cost_volume_bwd(const float* const* features, int N, const float* ref_pr
     DeviceGuard guard(dev);
     uint8_t* wsb = static_cast<uint8_t*>(workspace);
     cudaStream_t s = (cudaStream_t)stream;
-    if (G == 32) return train_bwd<32>(c, cost_volume, grad_out, grad_features, grad_params, wsb, ws, s);
-    if (G == 16) return train_bwd<16>(c, cost_volume, grad_out, grad_features, grad_params, wsb, ws, s);
-    return train_bwd<8>(c, cost_volume, grad_out, grad_features, grad_params, wsb, ws, s);
+    if (G == 32) return train_bwd<32>(c, cost_volume, grad_out, training ? batch_stats : nullptr, grad_features, grad_params, wsb, ws, s);
+    if (G == 16) return train_bwd<16>(c, cost_volume, grad_out, training ? batch_stats : nullptr, grad_features, grad_params, wsb, ws, s);
+    return train_bwd<8>(c, cost_volume, grad_out, training ? batch_stats : nullptr, grad_features, grad_params, wsb, ws, s);
 }
 
 }  // extern "C"

@@ -481,7 +481,7 @@ def _(features, ref_proj, src_projs, depth_hypos, conv_weight, bn_weight, bn_bia
 def cost_volume_bwd(features: List[Tensor], ref_proj: Tensor, src_projs: List[Tensor], depth_hypos: Tensor,
                     conv_weight: Tensor, bn_weight: Tensor, bn_bias: Tensor, bn_mean: Tensor, bn_var: Tensor,
                     bn_eps: float, fc_weight: Tensor, fc_bias: Tensor, groups: int, training: bool,
-                    cost_volume: Tensor, grad_out: Tensor) -> Tuple[List[Tensor], Tensor]:
+                    cost_volume: Tensor, grad_out: Tensor, batch_stats: Tensor) -> Tuple[List[Tensor], Tensor]:
     """Gradients of `cost_volume_train`: ([d features[i]], (4+G,) = d bn.weight, d bn.bias, d fc.weight, d fc.bias, d conv.weight)."""
     feats, refp, projs, hyp, per_pixel, params, (B, C, D, H, W) = _train_common(
         features, ref_proj, src_projs, depth_hypos, conv_weight, bn_weight, bn_bias, bn_mean, bn_var, fc_weight, fc_bias, groups)
@@ -498,16 +498,17 @@ def cost_volume_bwd(features: List[Tensor], ref_proj: Tensor, src_projs: List[Te
         _cabi.ptr_array([f.data_ptr() for f in feats]), N, refp.data_ptr(), _cabi.ptr_array([p.data_ptr() for p in projs]),
         hyp.data_ptr(), per_pixel, params[0].data_ptr(), params[1].data_ptr(), params[2].data_ptr(), params[3].data_ptr(),
         params[4].data_ptr(), float(bn_eps), params[5].data_ptr(), params[6].data_ptr(), int(training),
-        B, C, groups, D, H, W, cv.data_ptr(), go.data_ptr(), _cabi.ptr_array([g.data_ptr() for g in gfeats]),
-        gparams.data_ptr(), ws.data_ptr(), ws.numel(), _stream(cv))
+        B, C, groups, D, H, W, cv.data_ptr(), go.data_ptr(),
+        _f32c(batch_stats, "batch_stats").data_ptr() if training and batch_stats.numel() else None,
+        _cabi.ptr_array([g.data_ptr() for g in gfeats]), gparams.data_ptr(), ws.data_ptr(), ws.numel(), _stream(cv))
     _cabi.check("mdf_cost_volume_bwd", st)
-    _count(8 if training else 6)
+    _count(7)           # setup, layout pass, fold, per-element pass, plane sweep, finish, parameter gradients
     return gfeats, gparams
 
 
 @cost_volume_bwd.register_fake
 def _(features, ref_proj, src_projs, depth_hypos, conv_weight, bn_weight, bn_bias, bn_mean, bn_var, bn_eps,
-      fc_weight, fc_bias, groups, training, cost_volume, grad_out):
+      fc_weight, fc_bias, groups, training, cost_volume, grad_out, batch_stats):
     return [torch.empty_like(f) for f in features], features[0].new_empty(4 + groups)
 
 
