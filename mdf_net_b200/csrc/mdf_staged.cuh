@@ -717,9 +717,11 @@ static int launch_staged(const StagedArgs& args, const StagedBuffers& buf, cudaS
 // the diagnostic variants (branch-free samples, one reciprocal per group, phase timestamps, ablations) behind
 // algo = 16 + k: every one of them was measured within +-3 % of variant 0 or slower (profiles/r02_*).
 //                         G  PT TH PG  BW  BH MINB CQS
-using CfgG32_0 = StagedCfg<32, 1, 2, 4, 40, 6, 2, true>;     // 256 thr x 2 CTAs; tile 32x2, slab 4 planes; 2 x 30 KiB boxes + 2 x 8 KiB tiles
-using CfgG16_0 = StagedCfg<16, 2, 2, 4, 64, 6, 2, false>;    // 256 thr x 2 CTAs; tile 32x2, slab 8 planes; 2 x 24 KiB boxes
-using CfgG8_0  = StagedCfg<8, 4, 4, 2, 64, 10, 2, false>;    // 256 thr x 2 CTAs; tile 32x4, slab 8 planes; 2 x 20 KiB boxes
+// (round 2: boxes widened 40 -> 48, 64 -> 80, 64 -> 80 texels: fewer retry rounds at silhouettes and wide search ranges;
+//  -3 % at DTU 1600x1152, -5.5 % at 1920x1056 N=7, -5 % with the widest HyposByFit ranges; profiles/r02_box_sweep_*.log)
+using CfgG32_0 = StagedCfg<32, 1, 2, 4, 48, 6, 2, true>;     // 256 thr x 2 CTAs; tile 32x2, slab 4 planes; 2 x 36 KiB boxes + 2 x 8 KiB tiles
+using CfgG16_0 = StagedCfg<16, 2, 2, 4, 80, 6, 2, false>;    // 256 thr x 2 CTAs; tile 32x2, slab 8 planes; 2 x 30 KiB boxes
+using CfgG8_0  = StagedCfg<8, 4, 4, 2, 80, 10, 2, false>;    // 256 thr x 2 CTAs; tile 32x4, slab 8 planes; 2 x 25 KiB boxes
 
 // the configuration of a stage; MODE 1 / 2 = training (batch statistics / per-view BatchNorm folds)
 template <int MODE>
@@ -743,6 +745,15 @@ int launch_staged_eval(int G, const StagedArgs& a, const StagedBuffers& S, cudaS
 using CfgG32_1 = StagedCfg<32, 1, 4, 2, 40, 7, 2, true>;     // tile 32x4, slab 2 planes
 using CfgG32_2 = StagedCfg<32, 1, 4, 2, 40, 7, 2, true, false>;
 using CfgG32_3 = StagedCfg<32, 1, 1, 8, 48, 4, 2, true>;     // tile 32x1, slab 8 planes
+using CfgG32_4 = StagedCfg<32, 1, 2, 4, 40, 6, 2, true>;     // round 1's default box: 2 x 30 KiB
+using CfgG32_5 = StagedCfg<32, 1, 2, 4, 48, 7, 2, true>;     // taller box: 2 x 42 KiB
+using CfgG32_9 = StagedCfg<32, 1, 2, 4, 56, 6, 2, true>;     // wider still: 2 x 42 KiB
+using CfgG16_5 = StagedCfg<16, 2, 2, 4, 64, 8, 2, false>;    // taller box: 2 x 32 KiB
+using CfgG16_7 = StagedCfg<16, 2, 2, 4, 64, 6, 2, false>;    // round 1's default box: 2 x 24 KiB
+using CfgG16_9 = StagedCfg<16, 2, 2, 4, 96, 6, 2, false>;    // wider still: 2 x 36 KiB
+using CfgG8_9x = StagedCfg<8, 4, 4, 2, 64, 10, 2, false>;    // round 1's default box: 2 x 20 KiB
+using CfgG8_9y = StagedCfg<8, 4, 4, 2, 64, 12, 2, false>;    // taller box: 2 x 24 KiB
+using CfgG8_9z = StagedCfg<8, 4, 4, 2, 96, 10, 2, false>;    // wider still: 2 x 30 KiB
 using CfgG16_1 = StagedCfg<16, 2, 4, 2, 64, 8, 2, false>;    // tile 32x4, slab 4 planes
 using CfgG16_2 = StagedCfg<16, 2, 4, 2, 48, 8, 2, false>;    // narrower box
 using CfgG16_3 = StagedCfg<16, 2, 1, 8, 80, 4, 2, false>;    // tile 32x1, slab 16 planes
@@ -752,31 +763,32 @@ using CfgG8_3  = StagedCfg<8, 2, 2, 4, 64, 6, 3, false>;     // tile 32x2, slab 
 using CfgG16_4 = StagedCfg<16, 2, 2, 4, 64, 6, 2, false, true, true>;          // branch-free samples
 using CfgG8_4  = StagedCfg<8, 4, 4, 2, 64, 10, 2, false, true, true>;
 using CfgG8_5  = StagedCfg<8, 2, 4, 2, 64, 10, 3, false, true, true>;
-using CfgG32_6 = StagedCfg<32, 1, 2, 4, 40, 6, 2, true, true, false, true>;    // one reciprocal per group
+using CfgG32_6 = StagedCfg<32, 1, 2, 4, 48, 6, 2, true, true, false, true>;    // one reciprocal per group
 using CfgG16_6 = StagedCfg<16, 2, 2, 4, 64, 6, 2, false, true, false, true>;
 using CfgG8_6  = StagedCfg<8, 4, 4, 2, 64, 10, 2, false, true, false, true>;
 using CfgG8_7  = StagedCfg<8, 2, 4, 2, 64, 10, 3, false, true, false, true>;
-template <int ABL> using CfgG32_A = StagedCfg<32, 1, 2, 4, 40, 6, 2, true, true, false, false, false, ABL>;   // ablations
-template <int ABL> using CfgG16_A = StagedCfg<16, 2, 2, 4, 64, 6, 2, false, true, false, false, false, ABL>;
-template <int ABL> using CfgG8_A  = StagedCfg<8, 4, 4, 2, 64, 10, 2, false, true, false, false, false, ABL>;
-using CfgG32_T = StagedCfg<32, 1, 2, 4, 40, 6, 2, true, true, false, false, true>;    // phase timestamps
-using CfgG16_T = StagedCfg<16, 2, 2, 4, 64, 6, 2, false, true, false, false, true>;
-using CfgG8_T  = StagedCfg<8, 4, 4, 2, 64, 10, 2, false, true, false, false, true>;
+template <int ABL> using CfgG32_A = StagedCfg<32, 1, 2, 4, 48, 6, 2, true, true, false, false, false, ABL>;   // ablations
+template <int ABL> using CfgG16_A = StagedCfg<16, 2, 2, 4, 80, 6, 2, false, true, false, false, false, ABL>;
+template <int ABL> using CfgG8_A  = StagedCfg<8, 4, 4, 2, 80, 10, 2, false, true, false, false, false, ABL>;
+using CfgG32_T = StagedCfg<32, 1, 2, 4, 48, 6, 2, true, true, false, false, true>;    // phase timestamps
+using CfgG16_T = StagedCfg<16, 2, 2, 4, 80, 6, 2, false, true, false, false, true>;
+using CfgG8_T  = StagedCfg<8, 4, 4, 2, 80, 10, 2, false, true, false, false, true>;
 
-// algo = 16 + variant: 0 default, 1-3 shapes, 4-5 branch-free, 6-7 one reciprocal per group, 8-13 ablations
+// algo = 16 + variant: 0 default, 1-3 tile shapes, 4 / 5 / 7 / 12 / 14 / 16 box shapes (4, 7 at G16, 14 at G8: round 1's defaults),
+// 4-5 (G16 4, G8 4-5) branch-free, 6-7 one reciprocal per group, 8-13 ablations
 // (no MUFU / no tap loads / no stores / cheap positions / no cq loads / all of them), 15 phase timestamps
 static int launch_staged_variant(int G, int variant, const StagedArgs& a, const StagedBuffers& S, cudaStream_t stream, const HotEvents& ev)
 {
 #define MDF_V(k, Cfg) case k: return launch_staged<Cfg>(a, S, stream, ev)
     if (G == 32) {
         switch (variant) {
-            MDF_V(0, CfgG32_0); MDF_V(1, CfgG32_1); MDF_V(2, CfgG32_2); MDF_V(3, CfgG32_3); MDF_V(6, CfgG32_6);
+            MDF_V(0, CfgG32_0); MDF_V(1, CfgG32_1); MDF_V(2, CfgG32_2); MDF_V(3, CfgG32_3); MDF_V(4, CfgG32_4); MDF_V(5, CfgG32_5); MDF_V(14, CfgG32_9); MDF_V(6, CfgG32_6);
             MDF_V(8, CfgG32_A<1>); MDF_V(9, CfgG32_A<2>); MDF_V(10, CfgG32_A<4>); MDF_V(11, CfgG32_A<8>); MDF_V(12, CfgG32_A<16>);
             MDF_V(13, CfgG32_A<31>); MDF_V(15, CfgG32_T);
         }
     } else if (G == 16) {
         switch (variant) {
-            MDF_V(0, CfgG16_0); MDF_V(1, CfgG16_1); MDF_V(2, CfgG16_2); MDF_V(3, CfgG16_3); MDF_V(4, CfgG16_4); MDF_V(6, CfgG16_6);
+            MDF_V(0, CfgG16_0); MDF_V(1, CfgG16_1); MDF_V(2, CfgG16_2); MDF_V(3, CfgG16_3); MDF_V(4, CfgG16_4); MDF_V(5, CfgG16_5); MDF_V(6, CfgG16_6); MDF_V(7, CfgG16_7); MDF_V(14, CfgG16_9);
             MDF_V(8, CfgG16_A<1>); MDF_V(9, CfgG16_A<2>); MDF_V(10, CfgG16_A<4>); MDF_V(11, CfgG16_A<8>); MDF_V(13, CfgG16_A<15>);
             MDF_V(15, CfgG16_T);
         }
@@ -785,7 +797,7 @@ static int launch_staged_variant(int G, int variant, const StagedArgs& a, const 
             MDF_V(0, CfgG8_0); MDF_V(1, CfgG8_1); MDF_V(2, CfgG8_2); MDF_V(3, CfgG8_3); MDF_V(4, CfgG8_4); MDF_V(5, CfgG8_5);
             MDF_V(6, CfgG8_6); MDF_V(7, CfgG8_7);
             MDF_V(8, CfgG8_A<1>); MDF_V(9, CfgG8_A<2>); MDF_V(10, CfgG8_A<4>); MDF_V(11, CfgG8_A<8>); MDF_V(13, CfgG8_A<15>);
-            MDF_V(15, CfgG8_T);
+            MDF_V(15, CfgG8_T); MDF_V(14, CfgG8_9x); MDF_V(12, CfgG8_9y); MDF_V(16, CfgG8_9z);
         }
     }
 #undef MDF_V
