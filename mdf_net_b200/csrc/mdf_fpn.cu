@@ -22,9 +22,10 @@
 
 namespace mdf {
 
-// One thread = one pixel, all 2G output channels in registers; the weights sit in shared memory as [o][Cin] and are
-// fetched four input channels at a time (LDS.128 broadcast), the inputs are 128-byte coalesced rows of the NCHW planes.
-template <int G>
+// One thread = PX pixels (PX consecutive rows of 256 pixels apart: every load stays a 128-byte coalesced row), all 2G output
+// channels of each in registers; the weights sit in shared memory as [o][Cin] and are fetched four input channels at a time
+// (LDS.128 broadcast) -- one fetch serves PX pixels --, the inputs of eight channels are requested before the first FMA.
+template <int G, int PX>
 __global__ void __launch_bounds__(256)
 fpn_out_prepped_kernel(const float* __restrict__ x, const float* __restrict__ w, int Cin, int HW, const float* __restrict__ conv_w,
                        float4* __restrict__ S4, float4* __restrict__ Q4, float4* __restrict__ CQ4)
@@ -34,42 +35,60 @@ fpn_out_prepped_kernel(const float* __restrict__ x, const float* __restrict__ w,
     const int q4 = Cin / 4;
     for (int k = threadIdx.x; k < C * q4; k += blockDim.x) w_s[k] = __ldg(reinterpret_cast<const float4*>(w) + k);
     __syncthreads();
-    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    const int pix0 = blockIdx.x * (blockDim.x * PX) + threadIdx.x;
     const int b = blockIdx.y;
-    if (pix >= HW) return;
-    const float* __restrict__ xp = x + (size_t)b * Cin * HW + pix;
-    float acc[C];
+    if (pix0 >= HW) return;
+    const float* __restrict__ xp = x + (size_t)b * Cin * HW;
+    int pix[PX];
 #pragma unroll
-    for (int o = 0; o < C; ++o) acc[o] = 0.0f;
-    for (int c4 = 0; c4 < q4; ++c4) {
-        const float x0 = __ldg(xp + (size_t)(4 * c4 + 0) * HW), x1 = __ldg(xp + (size_t)(4 * c4 + 1) * HW);
-        const float x2 = __ldg(xp + (size_t)(4 * c4 + 2) * HW), x3 = __ldg(xp + (size_t)(4 * c4 + 3) * HW);
+    for (int u = 0; u < PX; ++u) pix[u] = min(pix0 + u * (int)blockDim.x, HW - 1);       // a clamped duplicate is not stored
+    float acc[PX][C];
 #pragma unroll
-        for (int o = 0; o < C; ++o) {
-            const float4 wv = w_s[o * q4 + c4];
-            acc[o] = fmaf(wv.w, x3, fmaf(wv.z, x2, fmaf(wv.y, x1, fmaf(wv.x, x0, acc[o]))));
+    for (int u = 0; u < PX; ++u)
+#pragma unroll
+        for (int o = 0; o < C; ++o) acc[u][o] = 0.0f;
+    for (int c8 = 0; c8 + 1 < q4 + 1; c8 += 2) {
+        float xv[PX][8];
+#pragma unroll
+        for (int u = 0; u < PX; ++u)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) xv[u][k] = (4 * c8 + k) < Cin ? __ldg(xp + (size_t)(4 * c8 + k) * HW + pix[u]) : 0.0f;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (c8 + h >= q4) break;
+#pragma unroll
+            for (int o = 0; o < C; ++o) {
+                const float4 wv = w_s[o * q4 + c8 + h];
+#pragma unroll
+                for (int u = 0; u < PX; ++u)
+                    acc[u][o] = fmaf(wv.w, xv[u][4 * h + 3], fmaf(wv.z, xv[u][4 * h + 2], fmaf(wv.y, xv[u][4 * h + 1], fmaf(wv.x, xv[u][4 * h], acc[u][o]))));
+            }
         }
     }
-    if (S4 != nullptr) {                                   // a source view
-        float4* __restrict__ dst = S4 + (size_t)b * J * HW + pix;
 #pragma unroll
-        for (int j = 0; j < J; ++j) {
-            float d[4];
+    for (int u = 0; u < PX; ++u) {
+        if (pix0 + u * (int)blockDim.x >= HW) break;
+        if (S4 != nullptr) {                                   // a source view
+            float4* __restrict__ dst = S4 + (size_t)b * J * HW + pix[u];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) d[k] = (acc[2 * (4 * j + k) + 1] - acc[2 * (4 * j + k)]) * kLog2e;
-            dst[(size_t)j * HW] = make_float4(d[0], d[1], d[2], d[3]);
-        }
-    } else {                                               // the reference view
-        float4* __restrict__ qd = Q4 + (size_t)b * J * HW + pix;
-        float4* __restrict__ cd = CQ4 + (size_t)b * J * HW + pix;
+            for (int j = 0; j < J; ++j) {
+                float d[4];
 #pragma unroll
-        for (int j = 0; j < J; ++j) {
-            float d[4];
+                for (int k = 0; k < 4; ++k) d[k] = (acc[u][2 * (4 * j + k) + 1] - acc[u][2 * (4 * j + k)]) * kLog2e;
+                dst[(size_t)j * HW] = make_float4(d[0], d[1], d[2], d[3]);
+            }
+        } else {                                               // the reference view
+            float4* __restrict__ qd = Q4 + (size_t)b * J * HW + pix[u];
+            float4* __restrict__ cd = CQ4 + (size_t)b * J * HW + pix[u];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) d[k] = 2.0f / (1.0f + expf(acc[2 * (4 * j + k) + 1] - acc[2 * (4 * j + k)])) - 1.0f;
-            const float w0 = __ldg(conv_w + 4 * j), w1 = __ldg(conv_w + 4 * j + 1), w2 = __ldg(conv_w + 4 * j + 2), w3 = __ldg(conv_w + 4 * j + 3);
-            qd[(size_t)j * HW] = make_float4(d[0], d[1], d[2], d[3]);
-            cd[(size_t)j * HW] = make_float4(w0 * d[0], w1 * d[1], w2 * d[2], w3 * d[3]);
+            for (int j = 0; j < J; ++j) {
+                float d[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) d[k] = 2.0f / (1.0f + expf(acc[u][2 * (4 * j + k) + 1] - acc[u][2 * (4 * j + k)])) - 1.0f;
+                const float w0 = __ldg(conv_w + 4 * j), w1 = __ldg(conv_w + 4 * j + 1), w2 = __ldg(conv_w + 4 * j + 2), w3 = __ldg(conv_w + 4 * j + 3);
+                qd[(size_t)j * HW] = make_float4(d[0], d[1], d[2], d[3]);
+                cd[(size_t)j * HW] = make_float4(w0 * d[0], w1 * d[1], w2 * d[2], w3 * d[3]);
+            }
         }
     }
 }
@@ -79,9 +98,10 @@ static int launch_fpn(const float* x, const float* w, int Cin, int B, int HW, co
                       cudaStream_t stream)
 {
     const size_t smem = (size_t)2 * G * Cin * sizeof(float);
-    auto kern = fpn_out_prepped_kernel<G>;
+    constexpr int PX = G == 32 ? 1 : 2;          // G16: 64 accumulators per thread; G8: 32 (4 pixels per thread leave too few blocks: 67 vs 58 us)
+    auto kern = fpn_out_prepped_kernel<G, PX>;
     if (smem > 48 * 1024) MDF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<dim3((unsigned)((HW + 255) / 256), (unsigned)B), 256, smem, stream>>>(x, w, Cin, HW, conv_w, S4, Q4, CQ4);
+    kern<<<dim3((unsigned)((HW + 256 * PX - 1) / (256 * PX)), (unsigned)B), 256, smem, stream>>>(x, w, Cin, HW, conv_w, S4, Q4, CQ4);
     return launch_status();
 }
 

@@ -160,16 +160,20 @@ static inline unsigned prep_zsplit(int threads_x, int images, int G)
 // configuration
 //   G      groups (channels of the difference map): 32 / 16 / 8 at the three stages
 //   PT     depth planes walked by one thread (accumulators: PT*G registers)
-//   TH     tile height in pixels (tile width is one warp = 32 pixels: 128-byte output rows)
+//   TH     tile height in warps (a warp covers WX x WY pixels, 32 x 1 by default: 128-byte output rows; tile = WX x TH*WY pixels)
 //   PG     plane groups per CTA -> the CTA's slab is PT*PG planes, blockDim = (32, TH, PG)
 //   BW,BH  box (texels) of one source difference map staged per TMA load: [G/4][BH][BW] float4
 //   MINB   CTAs per SM the register allocation aims at
 //   CQS    keep the per-pixel similarity weights cq_g = conv_w[g]*q_g in shared memory instead of registers
 // ------------------------------------------------------------------------------------------------
-template <int G_, int PT_, int TH_, int PG_, int BW_, int BH_, int MINB_, bool CQS_, bool EARLY_ = true, bool BF_ = false, bool RCP2_ = false, bool TRACE_ = false, int ABL_ = 0>
+template <int G_, int PT_, int TH_, int PG_, int BW_, int BH_, int MINB_, bool CQS_, bool EARLY_ = true, bool BF_ = false, bool RCP2_ = false, bool TRACE_ = false, int ABL_ = 0, int WX_ = 32>
 struct StagedCfg {
     static constexpr int G = G_, PT = PT_, TH = TH_, PG = PG_, BW = BW_, BH = BH_, MINB = MINB_;
     static constexpr bool RCP2 = RCP2_, TRACE = TRACE_;
+    // a warp covers WX x WY reference pixels (WX * WY = 32): 32 x 1 rows by default; 8 x 4 / 16 x 2 where the map width is not a
+    // multiple of 32 (W = 200 at stage 0 of DTU fills 6.25 warps of 32: one lane in nine idles), see pick_warp_width()
+    static constexpr int WX = WX_, WY = 32 / WX_;
+    static_assert(WX_ == 32 || WX_ == 16 || WX_ == 8, "warp footprint");
     static constexpr int ABL = ABL_;   // ablation study (wrong results): 1 no MUFU, 2 no tap loads, 4 no stores, 8 cheap positions, 16 no cq loads
     static constexpr bool CQS = CQS_, EARLY = EARLY_, BF = BF_;   // BF: branch-free sample bodies (samples of a thread interleave)
     static constexpr int J = G / 4;
@@ -260,7 +264,7 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
     const int b = it / a.slabs;
 
     const int H = a.H, W = a.W, D = a.D;
-    const int px = tile_x * 32 + lane, py = tile_y * TH + ty;
+    const int px = tile_x * Cfg::WX + (lane % Cfg::WX), py = (tile_y * TH + ty) * Cfg::WY + lane / Cfg::WX;
     const bool pix_ok = (px < W) && (py < H);
     const int d0 = slab * Cfg::SLAB + pg * PT;
     const size_t HW = (size_t)H * W;
@@ -279,8 +283,9 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
         fence_barrier_init();
         // q and cq = conv_w * q of the tile's pixels: two TMA tile loads (zero fill beyond the image)
         mbar_expect_tx(bar0 + 24, 2 * Cfg::TILE_BYTES);
-        tma_load_3d(box0 + Cfg::OFF_Q, &maps.q4, bar0 + 24, tile_x * 64, tile_y * TH, b * J);
-        tma_load_3d(box0 + Cfg::OFF_CQ, &maps.cq4, bar0 + 24, tile_x * 64, tile_y * TH, b * J);
+        // (the tile lands as [j][TH*WY rows][WX] float4: row-major over the tile = (ty * 32 + lane), whatever the warp footprint)
+        tma_load_3d(box0 + Cfg::OFF_Q, &maps.q4, bar0 + 24, tile_x * Cfg::WX * 2, tile_y * TH * Cfg::WY, b * J);
+        tma_load_3d(box0 + Cfg::OFF_CQ, &maps.cq4, bar0 + 24, tile_x * Cfg::WX * 2, tile_y * TH * Cfg::WY, b * J);
     }
     // rot | trans of every source view of this batch item -> shared memory
     for (int k = tid; k < a.V * 12; k += THREADS) {
@@ -694,15 +699,15 @@ static int launch_staged(const StagedArgs& args, const StagedBuffers& buf, cudaS
 {
     StagedMaps maps;
     int st = encode_planes(&maps.s4, buf.S4, args.W, args.H, (long long)args.V * args.B * Cfg::J, Cfg::BW, Cfg::BH, Cfg::J);
-    if (st == MDF_OK) st = encode_planes(&maps.q4, buf.Q4, args.W, args.H, (long long)args.B * Cfg::J, 32, Cfg::TH, Cfg::J);
-    if (st == MDF_OK) st = encode_planes(&maps.cq4, buf.CQ4, args.W, args.H, (long long)args.B * Cfg::J, 32, Cfg::TH, Cfg::J);
+    if (st == MDF_OK) st = encode_planes(&maps.q4, buf.Q4, args.W, args.H, (long long)args.B * Cfg::J, Cfg::WX, Cfg::TH * Cfg::WY, Cfg::J);
+    if (st == MDF_OK) st = encode_planes(&maps.cq4, buf.CQ4, args.W, args.H, (long long)args.B * Cfg::J, Cfg::WX, Cfg::TH * Cfg::WY, Cfg::J);
     if (st != MDF_OK) return st;
     auto kern = cost_volume_staged_kernel<Cfg, MODE>;
     MDF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     StagedArgs a = args;
     a.gn = make_grid_norm(a.H, a.W);
-    a.tiles_x = (a.W + 31) / 32;
-    a.tiles_y = (a.H + Cfg::TH - 1) / Cfg::TH;
+    a.tiles_x = (a.W + Cfg::WX - 1) / Cfg::WX;
+    a.tiles_y = (a.H + Cfg::TH * Cfg::WY - 1) / (Cfg::TH * Cfg::WY);
     a.slabs = (a.D + Cfg::SLAB - 1) / Cfg::SLAB;
     const long long items = (long long)a.tiles_x * a.tiles_y * a.slabs * a.B;
     if (items <= 0) return MDF_OK;
@@ -723,10 +728,34 @@ using CfgG32_0 = StagedCfg<32, 1, 2, 4, 48, 6, 2, true>;     // 256 thr x 2 CTAs
 using CfgG16_0 = StagedCfg<16, 2, 2, 4, 80, 6, 2, false>;    // 256 thr x 2 CTAs; tile 32x2, slab 8 planes; 2 x 30 KiB boxes
 using CfgG8_0  = StagedCfg<8, 4, 4, 2, 80, 10, 2, false>;    // 256 thr x 2 CTAs; tile 32x4, slab 8 planes; 2 x 25 KiB boxes
 
+// the same with narrower, taller warp footprints (eval mode only): tile 8 x 8 / 16 x 4 pixels, boxes of the same bytes
+using CfgG32_W8  = StagedCfg<32, 1, 2, 4, 24, 12, 2, true, true, false, false, false, 0, 8>;
+using CfgG16_W16 = StagedCfg<16, 2, 2, 4, 56, 8, 2, false, true, false, false, false, 0, 16>;
+using CfgG16_W8  = StagedCfg<16, 2, 2, 4, 40, 12, 2, false, true, false, false, false, 0, 8>;
+
+// lanes that fall beyond the right edge of the map, per warp width
+static inline int pick_warp_width(int W, bool has16, bool has8)
+{
+    auto waste = [&](int wx) { return (W + wx - 1) / wx * wx - W; };
+    int best = 32;
+    if (has16 && waste(16) < waste(best)) best = 16;
+    if (has8 && waste(8) < waste(best)) best = 8;
+    // a narrower footprint only where it recovers more than 3 % of the lanes
+    return (waste(32) - waste(best)) * 100 > 3 * W ? best : 32;
+}
+
 // the configuration of a stage; MODE 1 / 2 = training (batch statistics / per-view BatchNorm folds)
 template <int MODE>
 static int launch_staged_default(int G, const StagedArgs& a, const StagedBuffers& S, cudaStream_t stream, const HotEvents& ev = HotEvents())
 {
+    if (MODE == 0) {
+        if (G == 32 && pick_warp_width(a.W, false, true) == 8) return launch_staged<CfgG32_W8, 0>(a, S, stream, ev);
+        if (G == 16) {
+            const int wx = pick_warp_width(a.W, true, true);
+            if (wx == 16) return launch_staged<CfgG16_W16, 0>(a, S, stream, ev);
+            if (wx == 8) return launch_staged<CfgG16_W8, 0>(a, S, stream, ev);
+        }
+    }
     if (G == 32) return launch_staged<CfgG32_0, MODE>(a, S, stream, ev);
     if (G == 16) return launch_staged<CfgG16_0, MODE>(a, S, stream, ev);
     if (G == 8) return launch_staged<CfgG8_0, MODE>(a, S, stream, ev);

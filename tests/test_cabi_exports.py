@@ -85,6 +85,24 @@ def test_argument_validation_without_a_device(libpath):
     assert lib.mdf_prob_head_fwd(P, P, P, 0, 1, 8, 8, 4, 4, None, None, None, None, 4, 1, 2, 2, 0, None, None) == -3  # no output
     assert lib.mdf_prob_head_fwd(P, P, P, 0, 1, 8, 8, 4, 4, None, None, P, None, 4, 1, 2, 2, 2, None, None) == -3     # curve without s
     assert lib.mdf_prob_head_fwd(None, None, None, 0, 0, 8, 8, 4, 4, None, None, None, None, 4, 1, 2, 2, 0, None, None) == 0
+    # FPN hand-off (optional fast entry)
+    assert lib.mdf_fpn_out_prepped_fwd(P, P, 1, 64, 12, 4, 4, None, P, None, None, None) == -2              # G not in {8,16,32}
+    assert lib.mdf_fpn_out_prepped_fwd(P, P, 1, 62, 8, 4, 4, None, P, None, None, None) == -2               # Cin % 4
+    assert lib.mdf_fpn_out_prepped_fwd(P, P, 1, 64, 8, 4, 4, None, None, P, None, None) == -3               # reference view without cq4 / conv weight
+    assert lib.mdf_fpn_out_prepped_fwd(P, P, 1, 64, 8, 4, 4, None, P, P, None, None) == -3                  # source view with q4
+    assert lib.mdf_fpn_out_prepped_fwd(None, None, 0, 64, 8, 4, 4, None, None, None, None, None) == 0       # empty batch
+    assert lib.mdf_cost_volume_prepped_workspace_bytes(1, 5) % 256 == 0 and lib.mdf_cost_volume_prepped_workspace_bytes(1, 1) == 0
+    assert lib.mdf_cost_volume_fwd_prepped(P, P, P, 1, None, None, None, 0, None, None, None, None, None, 1e-5, None, None,
+                                           1, 8, 8, 4, 4, None, None, 0, None) == -1                        # N < 2
+    assert lib.mdf_cost_volume_fwd_prepped(P, P, P, 3, None, None, None, 0, None, None, None, None, None, 1e-5, None, None,
+                                           1, 12, 8, 4, 4, None, None, 0, None) == -2                       # G not in {8,16,32}
+    assert lib.mdf_cost_volume_fwd_prepped(P, P, P, 3, None, None, None, 0, None, None, None, None, None, 1e-5, None, None,
+                                           1, 8, 8, 4, 4, None, None, 0, None) == -3                        # null pointers
+    # the debug entry: both timing events or none
+    assert lib.mdf_cost_volume_fwd_ex(None, 1, None, None, None, 0, None, None, None, None, None, 1e-5, None, None,
+                                      1, 16, 8, 8, 4, 4, None, None, 0, 0, None, None, None) == -1          # N < 2
+    assert lib.mdf_cost_volume_fwd_ex(None, 3, None, None, None, 0, None, None, None, None, None, 1e-5, None, None,
+                                      1, 16, 8, 8, 4, 4, None, None, 0, 16, None, None, None) in (-2, -3)   # tuning variants: not in the product build
     # geometric filter
     assert lib.mdf_geo_filter_workspace_bytes(4) >= (20 + 4 * 64) * 4
     assert lib.mdf_geo_filter_fwd(P, P, P, None, None, None, 33, 4, 4, None, 0.8, 5, 4.0, 1300.0, None, None, P, None, None, None,
