@@ -237,6 +237,13 @@ def pipeline(device, h0: int, w0: int, nviews: int, reps: int = 3):
                 "note": "whole eval forward of config.model (eval.py:23-31: FPN x N, 3 x (hypotheses, cost volume, 3-D CNN, regression), "
                         "refine, confidence) vs the same weights with mdf_net_b200's VectorAggregate / HyposByFit / regress / fused "
                         "CoreNet tails injected; CUDA events, eager, median"})
+            # the reference out of the box: config.py never touches allow_tf32, so its cuDNN convolutions take PyTorch's default
+            # (TF32 tensor cores allowed).  The units of this package compute in fp32 either way; only the clock is reported here.
+            torch.backends.cudnn.allow_tf32 = True
+            out["tf32_convolutions"] = {"whole_view_reference_ms": med(lambda: model(*args)), "whole_view_dropin_ms": med(lambda: ours(*args)),
+                                        "fpn_ms": med(lambda: [model.Backbone(v) for v in views]),
+                                        "note": "torch.backends.cudnn.allow_tf32 = True (PyTorch's default, which config.py leaves alone): "
+                                                "the FPN and the 3-D CNN run on TF32 tensor cores in both arms"}
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
     return out
