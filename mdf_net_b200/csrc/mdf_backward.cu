@@ -27,6 +27,8 @@
 #include "mdf_common.cuh"
 #include "mdf_host.cuh"
 #include "mdf_setup.cuh"
+#include <stdlib.h>
+
 #include "mdf_staged.cuh"   // FeaPtrs, prep_kernel
 
 namespace mdf {
@@ -152,7 +154,7 @@ __device__ __forceinline__ void block_accumulate(double (&val)[N], double* __res
 // the unbiased variance (momentum update of the running statistics happens on the host side of the ABI).
 // `stats` come from the staged kernel's statistics pass: sums of ITS z = sum_g cw_g q_g (p_g - 0.5) = true z - hcw with
 // hcw = 0.5 * sum_g cw_g (the variance does not see the shift, the mean gets it back here).  `vparams` [V][4] are the
-// folds that kernel's forward pass uses: alpha_v, beta_v + alpha_v * hcw, the weight of an out-of-image sample.
+// folds that kernel's forward pass uses: alpha_v, beta_v + alpha_v * hcw, the weight of an out-of-image sample, hcw.
 __global__ void bn_fold_kernel(const double* __restrict__ stats, double count, int V, int training,
                                const float* __restrict__ bn_w, const float* __restrict__ bn_b,
                                const float* __restrict__ bn_mean, const float* __restrict__ bn_var, float eps,
@@ -193,7 +195,7 @@ __global__ void bn_fold_kernel(const double* __restrict__ stats, double count, i
         vparams[4 * v + 0] = (float)alpha;
         vparams[4 * v + 1] = betap;
         vparams[4 * v + 2] = 1.0f / (1.0f + expf(-hv));
-        vparams[4 * v + 3] = 0.0f;
+        vparams[4 * v + 3] = (float)hcw;
     }
 }
 
@@ -286,6 +288,61 @@ bwd_stats_kernel(const BwdArgs a, double* __restrict__ bsum)
     block_accumulate<2>(gfc, a.gparam + 2);
 }
 
+// phase 1b: the staged gather (mdf_staged.cuh, MODE 3) left A'_v and its z_v (= true z - hcw) of every (element, view) in za
+// and go = sum_g gout_g out_g; one thread per element turns them into what the sweep wants -- dh_v, the true z_v, w_v / sum w --
+// and reduces what only needs per-element values: the batch sums sum dh_v, sum dh_v * zhat_v per view (train-mode BatchNorm
+// backward; d gamma / d beta in both modes) and d fc.weight, d fc.bias.
+__global__ void __launch_bounds__(256)
+bwd_finalize_kernel(const BwdArgs a, const float* __restrict__ vparams, const float* __restrict__ go_all, double* __restrict__ bsum)
+{
+    const TrainArgs& t = a.t;
+    const size_t total = (size_t)t.B * t.D * t.H * t.W, idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool ok = idx < total;
+    const size_t i = ok ? idx : 0;
+    const float fcw = __ldg(t.fc), fcb = __ldg(t.fc + 1);
+    auto weight_of = [&](int v, float zs, float& h) {
+        h = fmaf(zs, __ldg(vparams + 4 * v), __ldg(vparams + 4 * v + 1));
+        return 1.0f / (1.0f + expf(-fmaf(fmaxf(h, 0.0f), fcw, fcb)));
+    };
+    float wsum = 0.0f;
+    for (int v = 0; v < t.V; ++v) {
+        float h;
+        wsum += weight_of(v, a.za[(size_t)(3 * v + 1) * total + i], h);
+    }
+    const float go = __ldg(go_all + i);
+    double gfc[2] = {0.0, 0.0};
+    for (int v = 0; v < t.V; ++v) {
+        double s[2] = {0.0, 0.0};
+        if (ok) {
+            const float zs = a.za[(size_t)(3 * v + 1) * total + i], aprime = a.za[(size_t)(3 * v) * total + i];
+            float h, dact;
+            const float w = weight_of(v, zs, h);
+            const float dh = dh_of(a, aprime, go, wsum, w, h, &dact);
+            const float z = zs + __ldg(vparams + 4 * v + 3);
+            const float zhat = (z - __ldg(t.bnv + 4 * v + 3)) * __ldg(t.bnv + 4 * v + 2);
+            s[0] = dh; s[1] = (double)dh * zhat;
+            gfc[0] += (double)dact * fmaxf(h, 0.0f);
+            gfc[1] += dact;
+            a.za[(size_t)(3 * v) * total + i] = dh;
+            a.za[(size_t)(3 * v + 1) * total + i] = z;
+            a.za[(size_t)(3 * v + 2) * total + i] = w / wsum;
+        }
+        block_accumulate<2>(s, bsum + 2 * v);
+    }
+    block_accumulate<2>(gfc, a.gparam + 2);
+}
+
+// predicated 16-byte read-only load at p + OFF bytes (zero when the predicate is off): keeps ONE address register pair per
+// row of the cell instead of an index -> pointer computation per tap
+template <int OFF>
+__device__ __forceinline__ float4 ldg4_if(const float4* p, bool pred)
+{
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t@q ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4+%6];\n\t}"
+        : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w) : "l"(p), "r"((int)pred), "n"(OFF));
+    return v;
+}
+
 __device__ __forceinline__ void red_add_v4(float4* addr, float4 v)
 {
     asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
@@ -316,20 +373,26 @@ bwd_sweep_kernel(const BwdArgs a)
     const size_t total = (size_t)t.B * t.D * HW;
     const size_t gstride = (size_t)t.D * HW;
     __shared__ double dcw_s[GS];
-    if (threadIdx.x < GS) dcw_s[threadIdx.x] = 0.0;
+    __shared__ float cw_s[GS];                        // the slice's conv weights: read per use (8 registers the plane loop needs more)
+    if (threadIdx.x < GS) { dcw_s[threadIdx.x] = 0.0; cw_s[threadIdx.x] = __ldg(t.cw + s * GS + threadIdx.x); }
     __syncthreads();
-    const float* rt = t.rt + ((size_t)v * t.B + b) * 12;
+    float rt[12];                                     // registers: the reductions below clobber memory, a pointer would be re-read per plane
+#pragma unroll
+    for (int k = 0; k < 12; ++k) rt[k] = __ldg(t.rt + ((size_t)v * t.B + b) * 12 + k);
     const RotXYZ r = rot_xyz(rt, (float)x, (float)y);
-    float q[GS], cw[GS];
+    float q[GS];
 #pragma unroll
     for (int jj = 0; jj < JS; ++jj) {
         const float4 qq = __ldg(t.Q4 + ((size_t)b * J + s * JS + jj) * HW + pix);
         q[4 * jj] = qq.x; q[4 * jj + 1] = qq.y; q[4 * jj + 2] = qq.z; q[4 * jj + 3] = qq.w;
     }
-#pragma unroll
-    for (int k = 0; k < GS; ++k) cw[k] = __ldg(t.cw + s * GS + k);
-    const float invstd = __ldg(t.bnv + 4 * v + 2), mean = __ldg(t.bnv + 4 * v + 3), alpha = __ldg(t.bnv + 4 * v);
-    const float m1 = a.training ? (float)(a.bsum[2 * v] / a.count) : 0.0f, m2 = a.training ? (float)(a.bsum[2 * v + 1] / a.count) : 0.0f;
+    // dz = alpha (dh - m1 - zhat m2), zhat = (z - mean) invstd  (train-mode BatchNorm backward; eval: m1 = m2 = 0)  =  kA dh + kB z + kC
+    float kA, kB, kC;
+    {
+        const float invstd = __ldg(t.bnv + 4 * v + 2), mean = __ldg(t.bnv + 4 * v + 3), alpha = __ldg(t.bnv + 4 * v);
+        const float m1 = a.training ? (float)(a.bsum[2 * v] / a.count) : 0.0f, m2 = a.training ? (float)(a.bsum[2 * v + 1] / a.count) : 0.0f;
+        kA = alpha; kB = -alpha * m2 * invstd; kC = -alpha * m1 - kB * mean;
+    }
     const float4* Sv = t.S4 + (((size_t)v * t.B + b) * J + s * JS) * HW;
     float4* dSv = a.dS4 + (((size_t)v * t.B + b) * J + s * JS) * HW;
     float dq[GS], dcw[GS];
@@ -350,13 +413,15 @@ bwd_sweep_kernel(const BwdArgs a)
             if (east && x1in && y1in) red_add_v4(d + t.W + 1, make_float4(gse[4 * jj], gse[4 * jj + 1], gse[4 * jj + 2], gse[4 * jj + 3]));
         }
     };
-    for (int d = 0; d < t.D; ++d) {
-        const size_t idx = ((size_t)b * t.D + d) * HW + pix;
-        const float dh = __ldg(a.za + (size_t)(3 * v) * total + idx), z = __ldg(a.za + (size_t)(3 * v + 1) * total + idx);
-        const float wn = __ldg(a.za + (size_t)(3 * v + 2) * total + idx);
-        const float zhat = (z - mean) * invstd;
-        const float dz = a.training ? alpha * (dh - m1 - zhat * m2) : alpha * dh;
-        const float depth = t.per_pixel ? __ldg(t.hypos + idx) : __ldg(t.hypos + (size_t)b * t.D + d);
+    // running pointers of the per-plane operands (one 64-bit add per plane instead of the index arithmetic)
+    const float* zap = a.za + (size_t)(3 * v) * total + (size_t)b * t.D * HW + pix;
+    const float* hyp = t.per_pixel ? t.hypos + (size_t)b * t.D * HW + pix : t.hypos + (size_t)b * t.D;
+    const size_t hstep = t.per_pixel ? HW : 1;
+    const float* gp = a.gout + (size_t)b * G * gstride + pix + (size_t)(s * GS) * gstride;
+    for (int d = 0; d < t.D; ++d, zap += HW, hyp += hstep, gp += HW) {
+        const float dh = __ldg(zap), z = __ldg(zap + total), wn = __ldg(zap + 2 * total);
+        const float dz = fmaf(kA, dh, fmaf(kB, z, kC));
+        const float depth = __ldg(hyp);
         float ix, iy;
         sample_position_fast(r, rt, depth, gn, ix, iy);
         const Taps tp = make_taps(ix, iy, gn.g);
@@ -377,18 +442,24 @@ bwd_sweep_kernel(const BwdArgs a)
             }
             cx = tp.x0; cy = tp.y0;
         }
-        const float* gp = a.gout + ((size_t)b * G * t.D + d) * HW + pix + (size_t)(s * GS) * gstride;
+        // the four taps of the cell: one address per plane, the bounds once (zero padding: a tap outside reads as 0)
+        const float4* pn = Sv + ((ptrdiff_t)tp.y0 * t.W + tp.x0);
+        const float4* ps = pn + t.W;
+        const bool x0in = tp.valid && (unsigned)tp.x0 < (unsigned)t.W, x1in = tp.valid && (unsigned)(tp.x0 + 1) < (unsigned)t.W;
+        const bool y0in = (unsigned)tp.y0 < (unsigned)t.H, y1in = (unsigned)(tp.y0 + 1) < (unsigned)t.H;
+        const bool inw = x0in && y0in, ine = x1in && y0in, isw = x0in && y1in, ise = x1in && y1in;
 #pragma unroll
-        for (int jj = 0; jj < JS; ++jj) {
-            float4 tt = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (tp.valid) tt = sample4(Sv + (size_t)jj * HW, t.H, t.W, tp);
-            const float tv[4] = {tt.x, tt.y, tt.z, tt.w};
+        for (int jj = 0; jj < JS; ++jj, pn += HW, ps += HW) {
+            const float4 nw = ldg4_if<0>(pn, inw), ne = ldg4_if<16>(pn, ine);
+            const float4 sw = ldg4_if<0>(ps, isw), se = ldg4_if<16>(ps, ise);
+            const float tv[4] = {blend4(nw.x, ne.x, sw.x, se.x, tp), blend4(nw.y, ne.y, sw.y, se.y, tp),
+                                 blend4(nw.z, ne.z, sw.z, se.z, tp), blend4(nw.w, ne.w, sw.w, se.w, tp)};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int gl = 4 * jj + k;
                 const float p = sigm2(tv[k]);
                 const float sim = fmaf(q[gl], p - 0.5f, 0.5f);
-                const float dsim = fmaf(__ldg(gp + (size_t)gl * gstride), wn, dz * cw[gl]);
+                const float dsim = fmaf(__ldg(gp + (size_t)gl * gstride), wn, dz * cw_s[gl]);
                 dcw[gl] = fmaf(dz, sim, dcw[gl]);
                 dq[gl] = fmaf(dsim, p - 0.5f, dq[gl]);
                 const float dt = -kLn2 * p * (1.0f - p) * (dsim * q[gl]);      // dp/dt = -ln2 p (1-p)
@@ -467,8 +538,12 @@ __global__ void gparam_to_float_kernel(const double* __restrict__ src, const dou
 // ------------------------------------------------------------------------------------------------
 // workspace
 // ------------------------------------------------------------------------------------------------
+// diagnostic switch (environment MDF_B200_BWD_DIRECT=1 at library load): phase 1 of the backward through the
+// one-thread-per-element kernel instead of the staged gather
+static const bool g_bwd_phase1_direct = [] { const char* e = getenv("MDF_B200_BWD_DIRECT"); return e && e[0] == '1'; }();
+
 struct TrainWorkspace {
-    size_t rt, dwp, q, s, cq, bnv, vparams, fc, za, stats, bsum, gparam, dq, ds, total;
+    size_t rt, dwp, q, s, cq, bnv, vparams, fc, za, go, stats, bsum, gparam, dq, ds, total;
 };
 
 static TrainWorkspace make_train_workspace(int B, int N, int G, int D, int H, int W)
@@ -486,6 +561,7 @@ static TrainWorkspace make_train_workspace(int B, int N, int G, int D, int H, in
     w.vparams = take(kMaxSrcViews * 4 * sizeof(float));
     w.fc = take(2 * sizeof(float));
     w.za = take(V * 3 * (size_t)B * D * H * W * sizeof(float));      // dh_v, z_v, w_v / sum w of every element (backward phase 1 -> 2)
+    w.go = take((size_t)B * D * H * W * sizeof(float));               // sum_g gout_g out_g of every element (phase 1a -> 1b)
     w.stats = take(kMaxSrcViews * 2 * sizeof(double));      // stats | bsum | gparam are contiguous: one memset
     w.bsum = take(kMaxSrcViews * 2 * sizeof(double));
     w.gparam = take((4 + 32) * sizeof(double));
@@ -615,9 +691,21 @@ static int train_bwd(const TrainCall& c, const float* cost_volume, const float* 
     const size_t total = (size_t)c.B * c.D * c.H * c.W;
     const unsigned blocks = (unsigned)((total + 255) / 256);
     a.za = reinterpret_cast<float*>(wsb + ws.za);
-    bwd_stats_kernel<G><<<blocks, 256, 0, stream>>>(a, reinterpret_cast<double*>(wsb + ws.bsum));      // per-element values for the sweep, batch sums, d fc
-    st = launch_status();
-    if (st != MDF_OK) return st;
+    if (g_bwd_phase1_direct) {
+        bwd_stats_kernel<G><<<blocks, 256, 0, stream>>>(a, reinterpret_cast<double*>(wsb + ws.bsum));      // per-element values for the sweep, batch sums, d fc
+        st = launch_status();
+        if (st != MDF_OK) return st;
+    } else {
+        // phase 1 on the TMA-staged gather (MODE 3), then the per-element pass
+        StagedArgs sa = staged_args(c, wsb, ws, nullptr);
+        sa.gout = grad_out; sa.fwd_out = cost_volume; sa.za = a.za; sa.go = reinterpret_cast<float*>(wsb + ws.go);
+        st = launch_staged_train<3>(G, sa, staged_buffers(wsb, ws), stream);
+        if (st != MDF_OK) return st;
+        bwd_finalize_kernel<<<blocks, 256, 0, stream>>>(a, reinterpret_cast<const float*>(wsb + ws.vparams), sa.go,
+                                                        reinterpret_cast<double*>(wsb + ws.bsum));
+        st = launch_status();
+        if (st != MDF_OK) return st;
+    }
     {
         const int HWi = c.H * c.W;
         bwd_sweep_kernel<G><<<dim3((unsigned)((HWi + 255) / 256), (unsigned)(c.B * (c.N - 1) * (G / 8))), 256, 0, stream>>>(a);

@@ -202,6 +202,12 @@ struct StagedArgs {
     double* stats;        // MODE 1: [V][2] sum z, sum z^2 of the kernel's z (= true z - 0.5*sum(conv_w)) over (B,D,H,W)
     const float* hypos;
     float* out;           // (B,G,D,H,W)
+    // MODE 3 (backward, phase 1 on the staged gather): upstream gradient and saved forward output (B,G,D,H,W) in;
+    // za [V][3][B*D*H*W]: slot 3v <- A'_v = sum_g gout_g sim_vg, slot 3v+1 <- the kernel's z_v;  go [B*D*H*W] <- sum_g gout_g out_g
+    const float* gout = nullptr;
+    const float* fwd_out = nullptr;
+    float* za = nullptr;
+    float* go = nullptr;
     GridNorm gn;
     int per_pixel, V, B, D, H, W, tiles_x, tiles_y, slabs;
 };
@@ -232,6 +238,8 @@ enum { kMinX = 0, kMinY = 1, kCount = 2, kSetStride = 4, kRetry = 8 /* [2][2] */
 // MODE 0: eval (one BatchNorm fold for all views).  The training path (mdf_backward.cu) runs the same kernel twice:
 // MODE 1 gathers and only accumulates the batch statistics of z per source view (train-mode BatchNorm3d normalises each
 // view's z over (B,D,H,W), homoaggregate.py:40 + base.py:50-68), MODE 2 is the forward with per-view folds.
+// MODE 3 is phase 1 of the backward on the same gather: the accumulator registers hold gout_g * q_g instead, and every
+// (sample, view) leaves its z_v and A'_v = sum_g gout_g sim_vg behind for the per-element pass and the sweep of mdf_backward.cu.
 template <class Cfg, int MODE = 0>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB)
 cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedArgs a)
@@ -311,6 +319,9 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
     float w_void_view = 0.0f;                    // MODE 2: weight of an out-of-image sample of the view being prepared
     float wvoid[MODE == 2 ? PT : 1];             // MODE 2: sum over the views of those weights, per plane
     float zs1 = 0.0f, zs2 = 0.0f;                // MODE 1: sum z, sum z^2 of the (at most PT) samples this thread gathered for one view
+    float a_base[MODE == 3 ? PT : 1], a_void[MODE == 3 ? PT : 1];   // MODE 3: A' = a_base + sum_g (gout_g q_g) p_g; A' of an out-of-image sample
+    const size_t total = (size_t)a.B * D * HW;
+    const size_t e0 = ((size_t)b * D + d0) * HW + (size_t)py * W + px;      // element of plane d0 (+ i * HW)
     __shared__ double stats_s[MODE == 1 ? 2 * kMaxSrcViews : 2];
     if (MODE == 2) {
 #pragma unroll
@@ -356,7 +367,7 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
         for (int k = 0; k < 12; ++k) rt[k] = lds32(rt_s + (uint32_t)(v * 12 + k) * 4u);
     };
     // sample positions of my planes; returns the mask of samples with at least one tap in bounds
-    auto positions = [&](const float (&rt)[12], float (&ix)[PT], float (&iy)[PT], bool count_void) -> uint32_t {
+    auto positions = [&](int v, const float (&rt)[12], float (&ix)[PT], float (&iy)[PT], bool count_void) -> uint32_t {
         uint32_t todo = 0;
         const RotXYZ r = rot_xyz(rt, (float)px, (float)py);
         // all planes through the branch-free fast chain first (PT independent dependency chains in one basic
@@ -380,7 +391,11 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
                 if (inside) todo |= 1u << i;
                 else if (count_void) {
                     if (MODE == 2) wvoid[i] += w_void_view;
-                    else n_void += 1ull << (8 * i);
+                    else if (MODE == 3) {
+                        // every similarity is 0.5: z (shifted) = 0, A' = 0.5 * sum_g gout_g
+                        a.za[(size_t)(3 * v) * total + e0 + (size_t)i * HW] = a_void[MODE == 3 ? i : 0];
+                        a.za[(size_t)(3 * v + 1) * total + e0 + (size_t)i * HW] = 0.0f;
+                    } else n_void += 1ull << (8 * i);
                 }
             }
         }
@@ -422,7 +437,7 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
     auto ex2_approx = [](float x) -> float { return (Cfg::ABL & 1) ? fmaf(x, 0.5f, 1.0f) : mdf::ex2_approx(x); };
     auto rcp_approx = [](float x) -> float { return (Cfg::ABL & 1) ? x * 0.25f : mdf::rcp_approx(x); };
     // gather the samples of `todo` that lie inside the box with origin (ox, oy); returns the rest
-    auto gather = [&](uint32_t box, int ox, int oy, const float (&ix)[PT], const float (&iy)[PT], uint32_t todo) -> uint32_t {
+    auto gather = [&](int v, uint32_t box, int ox, int oy, const float (&ix)[PT], const float (&iy)[PT], uint32_t todo) -> uint32_t {
 #pragma unroll
         for (int i = 0; i < PT; ++i) {
             const bool act = (todo >> i) & 1u;
@@ -492,6 +507,14 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
             }
             const float z = (Cfg::BF && !inb) ? 0.0f : z2.x + z2.y;
             if (MODE == 1) { zs1 += z; zs2 = fmaf(z, z, zs2); continue; }     // statistics pass: z is all it wants
+            if (MODE == 3) {
+                float2 ap2 = make_float2(a_base[MODE == 3 ? i : 0], 0.0f);
+#pragma unroll
+                for (int g = 0; g < G / 2; ++g) ap2 = __ffma2_rn(acc[i][g], p[g], ap2);
+                a.za[(size_t)(3 * v) * total + e0 + (size_t)i * HW] = ap2.x + ap2.y;
+                a.za[(size_t)(3 * v + 1) * total + e0 + (size_t)i * HW] = z;
+                continue;
+            }
             float h = fmaf(z, alpha, betap);              // BatchNorm3d (eval fold, or this view's batch statistics)
             h = fmaxf(h, 0.0f);                           // ReLU
             h = fmaf(h, fcw, fcb);                        // Conv3d(1,1,1)
@@ -505,13 +528,43 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
         return todo;
     };
 
+    if (MODE == 3) {
+        // upstream gradient of my planes: acc <- gout_g * q_g, go = sum_g gout_g out_g (homoaggregate.py:46 backward),
+        // a_void = 0.5 sum_g gout_g, a_base = a_void - 0.5 sum_g gout_g q_g   (sim = 0.5 + q (p - 0.5))
+        mbar_wait(bar0 + 24, 0);                 // q tile
+        const size_t gstride = (size_t)D * HW;
+#pragma unroll
+        for (int i = 0; i < PT; ++i) {
+            a_base[MODE == 3 ? i : 0] = 0.0f; a_void[MODE == 3 ? i : 0] = 0.0f;
+            if (!((ok_mask >> i) & 1u)) continue;
+            const size_t o = (((size_t)b * G) * D + (d0 + i)) * HW + (size_t)py * W + px;
+            float go = 0.0f, sg = 0.0f, sgq = 0.0f;
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                const float4 q = lds128(q_s + (uint32_t)j * TJ);
+                const float* gp = a.gout + o + (size_t)(4 * j) * gstride;
+                const float* fp = a.fwd_out + o + (size_t)(4 * j) * gstride;
+                const float g0 = __ldg(gp), g1 = __ldg(gp + gstride), g2 = __ldg(gp + 2 * gstride), g3 = __ldg(gp + 3 * gstride);
+                go = fmaf(g0, __ldg(fp), go); go = fmaf(g1, __ldg(fp + gstride), go);
+                go = fmaf(g2, __ldg(fp + 2 * gstride), go); go = fmaf(g3, __ldg(fp + 3 * gstride), go);
+                acc[i][2 * j] = make_float2(g0 * q.x, g1 * q.y);
+                acc[i][2 * j + 1] = make_float2(g2 * q.z, g3 * q.w);
+                sg += (g0 + g1) + (g2 + g3);
+                sgq += (acc[i][2 * j].x + acc[i][2 * j].y) + (acc[i][2 * j + 1].x + acc[i][2 * j + 1].y);
+            }
+            a_void[MODE == 3 ? i : 0] = 0.5f * sg;
+            a_base[MODE == 3 ? i : 0] = 0.5f * (sg - sgq);
+            a.go[e0 + (size_t)i * HW] = go;
+        }
+    }
+
     float ix[PT], iy[PT];
     uint32_t todo;
     {
         float rt[12];
         load_rt(0, rt);
         set_void_view(0);
-        todo = positions(rt, ix, iy, true);
+        todo = positions(0, rt, ix, iy, true);
     }
     stamp();                                     // 3: positions of view 0 done (the hypotheses have arrived)
     announce(0, ix, iy, todo);
@@ -538,7 +591,7 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
             float rt[12];
             load_rt(v + 1, rt);
             set_void_view(v + 1);
-            ntodo = positions(rt, nx, ny, true);
+            ntodo = positions(v + 1, rt, nx, ny, true);
             announce(v + 1, nx, ny, ntodo);
         }
         stamp();                                 // 6 + 3v: next view prepared, waiting for this view's box
@@ -546,7 +599,7 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
         stamp();                                 // 7 + 3v: box landed
         const int ox = ctl[kOrg + 2 * v], oy = ctl[kOrg + 2 * v + 1];
         set_view(v);
-        todo = gather(box0 + (uint32_t)(v & 1) * Cfg::BOX_BYTES, ox, oy, ix, iy, todo);
+        todo = gather(v, box0 + (uint32_t)(v & 1) * Cfg::BOX_BYTES, ox, oy, ix, iy, todo);
         flush_stats(v);
         stamp();                                 // 8 + 3v: gathered
         if (todo != 0u) left |= 1u << v;
@@ -584,7 +637,7 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
 
     // Warps whose samples all fitted write their results before the CTA-wide vote (their stores overlap the tail
     // of the slower warps); the others write after the retry rounds.
-    const bool early = MODE != 1 && Cfg::EARLY && __all_sync(0xffffffffu, left == 0u);
+    const bool early = MODE != 1 && MODE != 3 && Cfg::EARLY && __all_sync(0xffffffffu, left == 0u);
     if (early) epilogue();
     stamp();                                     // early epilogue done
 
@@ -602,7 +655,7 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
             {
                 float rt[12];
                 load_rt(v, rt);
-                todo = positions(rt, ix, iy, false);
+                todo = positions(v, rt, ix, iy, false);
             }
             set_view(v);
             {   // drop what round 0 already gathered
@@ -642,7 +695,7 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
                 }
                 mbar_wait(bar0 + 16, riter & 1u);
                 ++riter;
-                todo = gather(box0, ox, oy, ix, iy, todo);
+                todo = gather(v, box0, ox, oy, ix, iy, todo);
             }
             flush_stats(v);
         }
@@ -653,6 +706,7 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
         if (tid < 2 * a.V && stats_s[tid] != 0.0) atomicAdd(a.stats + tid, stats_s[tid]);
         return;
     }
+    if (MODE == 3) return;
     if (!early) epilogue();
     stamp();                                     // end
 #ifdef MDF_TUNING
