@@ -149,6 +149,14 @@ MDF_API int mdf_cost_volume_bwd(const float *const *features, int N, const float
                                 float *const *grad_features, float *grad_params,
                                 void *workspace, size_t workspace_bytes, mdf_stream_t stream);
 
+/* The momentum update of BatchNorm3d's running statistics after a train-mode forward (base.py:50-68 inside
+ * homoaggregate.py:40: one application per source view => V sequential updates in view order): `batch_stats` is what
+ * mdf_cost_volume_train_fwd returned, `momentum` < 0 means momentum=None (cumulative moving average over
+ * num_batches_tracked); running_mean / running_var (1 float each) and num_batches_tracked (1 int64, may be NULL) are
+ * updated in place.  One launch. */
+MDF_API int mdf_bn_running_update(const float *batch_stats, int V, float momentum, float *running_mean, float *running_var,
+                                  long long *num_batches_tracked, mdf_stream_t stream);
+
 /* ---- homo_aggregate_by_variance -> (B,C,D,H,W) ---------------------------------------------- */
 MDF_API size_t mdf_variance_volume_workspace_bytes(int B, int N, int C, int D, int H, int W);
 

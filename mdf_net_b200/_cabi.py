@@ -50,6 +50,7 @@ SIGNATURES = {
                                        _I, _I, _I, _I, _I, _I, _P, _P, _P, c_size_t, _P]),
     "mdf_cost_volume_bwd": (_I, [_P, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P, c_float, _P, _P, _I,
                                  _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "mdf_bn_running_update": (_I, [_P, _I, c_float, _P, _P, _P, _P]),
     "mdf_hypos_fit_fwd": (_I, [_P, _P, _I, _P, _I, _I, _I, _I, _I, _P, _P]),
     "mdf_hypos_generate_fwd": (_I, [_P, _P, _P, _I, c_float, _I, _I, _I, _I, _I, _P, _P]),
     "mdf_geo_filter_workspace_bytes": (c_size_t, [_I]),

@@ -22,9 +22,11 @@ class _VectorAggregateFn(torch.autograd.Function):
         features, src_projs = list(tensors[:n_feats]), list(tensors[n_feats:])
         out, stats = ops.cost_volume_train(features, ref_proj, src_projs, depth_hypos, conv_w, bn_w, bn_b, bn_mean, bn_var,
                                            bn_eps, fc_w, fc_b, groups, training)
-        # the running statistics may be updated in place after this call: keep the values the forward saw
-        # (`stats`: the batch statistics per source view go back into the backward, which then skips its own statistics sweep)
-        ctx.save_for_backward(ref_proj, depth_hypos, conv_w, bn_w, bn_b, bn_mean.clone(), bn_var.clone(), fc_w, fc_b, out, stats, *tensors)
+        # `stats`: the batch statistics per source view go back into the backward, which then skips its own statistics sweep.
+        # The running statistics are updated in place right after a train-mode forward (the backward does not read them then);
+        # they are buffers, not autograd inputs: plain attributes, no version check.
+        ctx.save_for_backward(ref_proj, depth_hypos, conv_w, bn_w, bn_b, fc_w, fc_b, out, stats, *tensors)
+        ctx.running = (bn_mean, bn_var)
         ctx.meta = (n_feats, groups, training, bn_eps)
         ctx.mark_non_differentiable(stats)
         return out, stats
@@ -32,8 +34,9 @@ class _VectorAggregateFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out, _grad_stats):
         n_feats, groups, training, bn_eps = ctx.meta
-        ref_proj, depth_hypos, conv_w, bn_w, bn_b, bn_mean, bn_var, fc_w, fc_b, out, stats = ctx.saved_tensors[:11]
-        tensors = ctx.saved_tensors[11:]
+        ref_proj, depth_hypos, conv_w, bn_w, bn_b, fc_w, fc_b, out, stats = ctx.saved_tensors[:9]
+        bn_mean, bn_var = ctx.running
+        tensors = ctx.saved_tensors[9:]
         features, src_projs = list(tensors[:n_feats]), list(tensors[n_feats:])
         gfeats, gp = ops.cost_volume_bwd(features, ref_proj, src_projs, depth_hypos, conv_w, bn_w, bn_b, bn_mean, bn_var,
                                          bn_eps, fc_w, fc_b, groups, training, out, grad_out.contiguous(), stats)
@@ -50,17 +53,8 @@ def vector_aggregate_train(module, features: List[torch.Tensor], ref_proj, src_p
                                           cbr.conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var,
                                           fc.weight, fc.bias, *features, *src_projs)
     if training and bn.track_running_stats:
-        # BatchNorm3d is applied once per source view: V sequential momentum updates, folded into one expression
+        # BatchNorm3d is applied once per source view: V sequential momentum updates in view order, one launch
         with torch.no_grad():
-            V = stats.shape[0]
-            bn.num_batches_tracked += V
-            if bn.momentum is None:      # cumulative moving average
-                n0 = (bn.num_batches_tracked - V).to(stats.dtype)
-                bn.running_mean.copy_((bn.running_mean * n0 + stats[:, 0].sum()) / (n0 + V))
-                bn.running_var.copy_((bn.running_var * n0 + stats[:, 1].sum()) / (n0 + V))
-            else:
-                m = float(bn.momentum)
-                decay = (1.0 - m) ** torch.arange(V - 1, -1, -1, device=stats.device, dtype=stats.dtype)
-                bn.running_mean.mul_((1.0 - m) ** V).add_(m * (decay * stats[:, 0]).sum())
-                bn.running_var.mul_((1.0 - m) ** V).add_(m * (decay * stats[:, 1]).sum())
+            ops.bn_running_update(stats, -1.0 if bn.momentum is None else float(bn.momentum), bn.running_mean, bn.running_var,
+                                  bn.num_batches_tracked)
     return out

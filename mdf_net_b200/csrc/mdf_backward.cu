@@ -12,23 +12,25 @@
 //   sim_vg = 0.5 + q_g (p_vg - 0.5)      z_v = sum_g cw_g sim_vg     h_v = a_v z_v + b_v   (BatchNorm)
 //   w_v = sigmoid(fcw*relu(h_v) + fcb)   out_g = sum_v w_v sim_vg / sum_v w_v
 //
-// The train-mode FORWARD runs the tuned TMA-staged kernel of mdf_staged.cuh twice: in its statistics mode (sum z, sum z^2
-// per source view) and, after the per-view BatchNorm folds (bn_fold_kernel), in its per-view-fold mode.  The BACKWARD is
-// two sweeps with taps through L1/L2 straight from the planar-float4 maps the prep kernel writes: phase 1, one thread per
-// (b,d,y,x), computes what needs all views of an element (dh_v, z_v, w_v / sum w, the batch sums, d fc); phase 2, one thread
-// per (pixel, view, group slice), walks the depth planes and scatters the feature gradient with 128-bit vector reductions
-// (red.global.add.v4.f32) into a difference-gradient map dS4 -- half the atomics of scattering into both channels of a
-// pair, and only when the sample leaves its source cell (the scatter is what bounds the backward) -- and a finishing
-// kernel turns dS4 / dQ4 into NCHW feature gradients.  The forward's batch statistics come back in through the ABI, so
-// the backward does not repeat the statistics sweep.
+// The train-mode FORWARD runs the tuned TMA-staged kernel of mdf_staged.cuh twice: in its statistics mode (MODE 1: sum z,
+// sum z^2 per source view) and, after the per-view BatchNorm folds (bn_fold_kernel), in its per-view-fold mode (MODE 2).
+// The BACKWARD:
+//   phase 1a  the same staged gather once more (MODE 3): its accumulator registers hold gout_g q_g, and every (element, view)
+//             leaves z_v and A'_v = sum_g gout_g sim_vg behind, every element go = sum_g gout_g out_g;
+//   phase 1b  bwd_finalize_kernel, one thread per element: what needs all views of an element (dh_v, w_v / sum w), the batch
+//             sums of train-mode BatchNorm's backward, d fc;
+//   phase 2   bwd_sweep_kernel, one thread per (pixel, view, slice of 8 groups), walks the depth planes with the taps through
+//             L1/L2 and scatters the feature gradient with 128-bit vector reductions (red.global.add.v4.f32) into a
+//             difference-gradient map dS4 -- half the atomics of scattering into both channels of a pair, and only when the
+//             sample leaves its source cell (the scatter is what bounds the backward);
+//   finish    dS4 / dQ4 -> NCHW feature gradients.
+// The forward's batch statistics come back in through the ABI, so the backward does not repeat the statistics sweep.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "mdf_common.cuh"
 #include "mdf_host.cuh"
 #include "mdf_setup.cuh"
-#include <stdlib.h>
-
 #include "mdf_staged.cuh"   // FeaPtrs, prep_kernel
 
 namespace mdf {
@@ -46,86 +48,8 @@ struct TrainArgs {
     int per_pixel, V, B, D, H, W;
 };
 
-__device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
-
-// bilinear sample of one float4 plane with zero padding, per component in the reference's tap order
-__device__ __forceinline__ float4 sample4(const float4* __restrict__ plane, int H, int W, const Taps& t)
-{
-    const bool x0in = (unsigned)t.x0 < (unsigned)W, x1in = (unsigned)(t.x0 + 1) < (unsigned)W;
-    const bool y0in = (unsigned)t.y0 < (unsigned)H, y1in = (unsigned)(t.y0 + 1) < (unsigned)H;
-    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4* p = plane + (ptrdiff_t)t.y0 * W + t.x0;
-    const float4 nw = (x0in && y0in) ? ldg4(p) : zero, ne = (x1in && y0in) ? ldg4(p + 1) : zero;
-    const float4 sw = (x0in && y1in) ? ldg4(p + W) : zero, se = (x1in && y1in) ? ldg4(p + W + 1) : zero;
-    return make_float4(blend4(nw.x, ne.x, sw.x, se.x, t), blend4(nw.y, ne.y, sw.y, se.y, t),
-                       blend4(nw.z, ne.z, sw.z, se.z, t), blend4(nw.w, ne.w, sw.w, se.w, t));
-}
-
 // 1/(1+2^t) with the same MUFU approximations (<= 2 ulp each) as the forward kernel it differentiates
 __device__ __forceinline__ float sigm2(float t) { return rcp_approx(1.0f + ex2_approx(fminf(t, 126.0f))); }
-
-struct Elem { int x, y, d, b; size_t pix; float depth; bool ok; };
-
-__device__ __forceinline__ Elem decode(const TrainArgs& a)
-{
-    Elem e;
-    const size_t HW = (size_t)a.H * a.W;
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    e.ok = idx < (size_t)a.B * a.D * HW;
-    const size_t i = e.ok ? idx : 0;
-    e.x = (int)(i % a.W);
-    e.y = (int)((i / a.W) % a.H);
-    e.d = (int)((i / HW) % a.D);
-    e.b = (int)(i / (HW * a.D));
-    e.pix = (size_t)e.y * a.W + e.x;
-    e.depth = a.per_pixel ? __ldg(a.hypos + ((size_t)e.b * a.D + e.d) * HW + e.pix) : __ldg(a.hypos + (size_t)e.b * a.D + e.d);
-    return e;
-}
-
-// footprint of element e in source view v: the same bit-exact position as the forward (mdf_common.cuh: shared-reciprocal
-// divisions where they are exact, the IEEE chain otherwise)
-__device__ __forceinline__ Taps taps_of(const TrainArgs& a, const Elem& e, int v, const GridNormFast& gf)
-{
-    const float* rt = a.rt + ((size_t)v * a.B + e.b) * 12;
-    float ix, iy;
-    sample_position_fast(rot_xyz(rt, (float)e.x, (float)e.y), rt, e.depth, gf, ix, iy);
-    return make_taps(ix, iy, gf.g);
-}
-
-// z_v of one element (and optionally A'_v = sum_g gout_g sim_vg)
-template <int G>
-__device__ __forceinline__ float view_z(const TrainArgs& a, const Elem& e, int v, const Taps& t, const float4* __restrict__ q4,
-                                        const float* __restrict__ gout /* registers or nullptr */, float* aprime)
-{
-    constexpr int J = G / 4;
-    const size_t HW = (size_t)a.H * a.W;
-    const float4* Sv = a.S4 + ((size_t)v * a.B + e.b) * J * HW;
-    float z = 0.0f, ap = 0.0f;
-#pragma unroll
-    for (int j = 0; j < J; ++j) {
-        float4 tt = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (t.valid) tt = sample4(Sv + (size_t)j * HW, a.H, a.W, t);
-        const float4 q = q4[j];
-        const float s0 = fmaf(q.x, sigm2(tt.x) - 0.5f, 0.5f), s1 = fmaf(q.y, sigm2(tt.y) - 0.5f, 0.5f);
-        const float s2 = fmaf(q.z, sigm2(tt.z) - 0.5f, 0.5f), s3 = fmaf(q.w, sigm2(tt.w) - 0.5f, 0.5f);
-        z = fmaf(__ldg(a.cw + 4 * j + 0), s0, z); z = fmaf(__ldg(a.cw + 4 * j + 1), s1, z);
-        z = fmaf(__ldg(a.cw + 4 * j + 2), s2, z); z = fmaf(__ldg(a.cw + 4 * j + 3), s3, z);
-        if (gout) {
-            ap = fmaf(gout[4 * j + 0], s0, ap); ap = fmaf(gout[4 * j + 1], s1, ap);
-            ap = fmaf(gout[4 * j + 2], s2, ap); ap = fmaf(gout[4 * j + 3], s3, ap);
-        }
-    }
-    if (aprime) *aprime = ap;
-    return z;
-}
-
-__device__ __forceinline__ float view_weight(const TrainArgs& a, int v, float z, float* h_out)
-{
-    const float h = fmaf(z, __ldg(a.bnv + 4 * v), __ldg(a.bnv + 4 * v + 1));
-    if (h_out) *h_out = h;
-    const float act = fmaf(fmaxf(h, 0.0f), __ldg(a.fc), __ldg(a.fc + 1));
-    return 1.0f / (1.0f + expf(-act));
-}
 
 // block-wide sum of `n` doubles per thread -> atomicAdd into dst (one atomic per block and value)
 template <int N>
@@ -222,72 +146,6 @@ __device__ __forceinline__ float dh_of(const BwdArgs& a, float aprime, float go,
     return h > 0.0f ? dact * __ldg(a.t.fc) : 0.0f;      // Conv3d(1,1,1) then ReLU
 }
 
-// phase 1: z_v and A'_v of every element (handed to phase 2) and, in train mode, the sums over the elements of dh_v and
-// dh_v * zhat_v per view.  q and the upstream gradients are streamed per group quad instead of being held in registers
-// (they come from L1 after the first view), which keeps the kernel at four blocks per SM.
-template <int G>
-__global__ void __launch_bounds__(256, 4)
-bwd_stats_kernel(const BwdArgs a, double* __restrict__ bsum)
-{
-    constexpr int J = G / 4;
-    const TrainArgs& t = a.t;
-    const Elem e = decode(t);
-    const GridNormFast gn = make_grid_norm_fast(t.H, t.W);
-    const size_t HW = (size_t)t.H * t.W;
-    const size_t gstride = (size_t)t.D * HW;
-    const size_t o0 = ((size_t)e.b * G * t.D + e.d) * HW + e.pix;
-    float go = 0.0f;
-#pragma unroll 8
-    for (int g = 0; g < G; ++g)
-        go = fmaf(e.ok ? __ldg(a.gout + o0 + (size_t)g * gstride) : 0.0f, e.ok ? __ldg(a.out + o0 + (size_t)g * gstride) : 0.0f, go);
-    float zv[kMaxSrcViews], wv[kMaxSrcViews], hv[kMaxSrcViews], av[kMaxSrcViews];
-    float wsum = 0.0f;
-    for (int v = 0; v < t.V; ++v) {
-        const Taps tp = taps_of(t, e, v, gn);
-        const float4* Sv = t.S4 + ((size_t)v * t.B + e.b) * J * HW;
-        float z = 0.0f, ap = 0.0f;
-#pragma unroll 2
-        for (int j = 0; j < J; ++j) {
-            float4 tt = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (tp.valid) tt = sample4(Sv + (size_t)j * HW, t.H, t.W, tp);
-            const float4 q = __ldg(t.Q4 + ((size_t)e.b * J + j) * HW + e.pix);
-            const float s0 = fmaf(q.x, sigm2(tt.x) - 0.5f, 0.5f), s1 = fmaf(q.y, sigm2(tt.y) - 0.5f, 0.5f);
-            const float s2 = fmaf(q.z, sigm2(tt.z) - 0.5f, 0.5f), s3 = fmaf(q.w, sigm2(tt.w) - 0.5f, 0.5f);
-            z = fmaf(__ldg(t.cw + 4 * j + 0), s0, z); z = fmaf(__ldg(t.cw + 4 * j + 1), s1, z);
-            z = fmaf(__ldg(t.cw + 4 * j + 2), s2, z); z = fmaf(__ldg(t.cw + 4 * j + 3), s3, z);
-            const float* gp = a.gout + o0 + (size_t)(4 * j) * gstride;
-            ap = fmaf(e.ok ? __ldg(gp) : 0.0f, s0, ap); ap = fmaf(e.ok ? __ldg(gp + gstride) : 0.0f, s1, ap);
-            ap = fmaf(e.ok ? __ldg(gp + 2 * gstride) : 0.0f, s2, ap); ap = fmaf(e.ok ? __ldg(gp + 3 * gstride) : 0.0f, s3, ap);
-        }
-        zv[v] = z;
-        av[v] = ap;
-        wv[v] = view_weight(t, v, zv[v], &hv[v]);
-        wsum += wv[v];
-    }
-    // hand dh_v, z_v and the normalised view weight over to the main sweep (one thread of which walks the planes of a
-    // (pixel, view) pair: it cannot see the other views of an element), and reduce what only needs per-element values:
-    // the batch sums sum dh_v, sum dh_v*zhat_v per view (train-mode BatchNorm backward; d gamma / d beta in both modes)
-    // and d fc.weight, d fc.bias
-    const size_t total = (size_t)t.B * t.D * HW, idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    double gfc[2] = {0.0, 0.0};
-    for (int v = 0; v < t.V; ++v) {
-        double s[2] = {0.0, 0.0};
-        if (e.ok) {
-            float dact;
-            const float dh = dh_of(a, av[v], go, wsum, wv[v], hv[v], &dact);
-            const float zhat = (zv[v] - __ldg(t.bnv + 4 * v + 3)) * __ldg(t.bnv + 4 * v + 2);
-            s[0] = dh; s[1] = (double)dh * zhat;
-            gfc[0] += (double)dact * fmaxf(hv[v], 0.0f);
-            gfc[1] += dact;
-            a.za[(size_t)(3 * v) * total + idx] = dh;
-            a.za[(size_t)(3 * v + 1) * total + idx] = zv[v];
-            a.za[(size_t)(3 * v + 2) * total + idx] = wv[v] / wsum;
-        }
-        block_accumulate<2>(s, bsum + 2 * v);
-    }
-    block_accumulate<2>(gfc, a.gparam + 2);
-}
-
 // phase 1b: the staged gather (mdf_staged.cuh, MODE 3) left A'_v and its z_v (= true z - hcw) of every (element, view) in za
 // and go = sum_g gout_g out_g; one thread per element turns them into what the sweep wants -- dh_v, the true z_v, w_v / sum w --
 // and reduces what only needs per-element values: the batch sums sum dh_v, sum dh_v * zhat_v per view (train-mode BatchNorm
@@ -341,6 +199,13 @@ __device__ __forceinline__ float4 ldg4_if(const float4* p, bool pred)
     asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t@q ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4+%6];\n\t}"
         : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w) : "l"(p), "r"((int)pred), "n"(OFF));
     return v;
+}
+
+template <int OFF>
+__device__ __forceinline__ void red_add_v4_if(float4* addr, bool pred, float a, float b, float c, float d)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t@q red.relaxed.gpu.global.add.v4.f32 [%0+%6], {%1, %2, %3, %4};\n\t}"
+                 ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d), "r"((int)pred), "n"(OFF) : "memory");
 }
 
 __device__ __forceinline__ void red_add_v4(float4* addr, float4 v)
@@ -404,13 +269,14 @@ bwd_sweep_kernel(const BwdArgs a)
     auto flush = [&](bool west, bool east) {
         const bool y0in = live && (unsigned)cy < (unsigned)t.H, y1in = live && (unsigned)(cy + 1) < (unsigned)t.H;
         const bool x0in = (unsigned)cx < (unsigned)t.W, x1in = (unsigned)(cx + 1) < (unsigned)t.W;
+        float4* dn = dSv + ((ptrdiff_t)cy * t.W + cx);          // one address per row of the cell, predicated reductions
+        float4* ds = dn + t.W;
 #pragma unroll
-        for (int jj = 0; jj < JS; ++jj) {
-            float4* d = dSv + (size_t)jj * HW + (ptrdiff_t)cy * t.W + cx;
-            if (west && x0in && y0in) red_add_v4(d, make_float4(gnw[4 * jj], gnw[4 * jj + 1], gnw[4 * jj + 2], gnw[4 * jj + 3]));
-            if (west && x0in && y1in) red_add_v4(d + t.W, make_float4(gsw[4 * jj], gsw[4 * jj + 1], gsw[4 * jj + 2], gsw[4 * jj + 3]));
-            if (east && x1in && y0in) red_add_v4(d + 1, make_float4(gne[4 * jj], gne[4 * jj + 1], gne[4 * jj + 2], gne[4 * jj + 3]));
-            if (east && x1in && y1in) red_add_v4(d + t.W + 1, make_float4(gse[4 * jj], gse[4 * jj + 1], gse[4 * jj + 2], gse[4 * jj + 3]));
+        for (int jj = 0; jj < JS; ++jj, dn += HW, ds += HW) {
+            if (west) red_add_v4_if<0>(dn, x0in && y0in, gnw[4 * jj], gnw[4 * jj + 1], gnw[4 * jj + 2], gnw[4 * jj + 3]);
+            if (west) red_add_v4_if<0>(ds, x0in && y1in, gsw[4 * jj], gsw[4 * jj + 1], gsw[4 * jj + 2], gsw[4 * jj + 3]);
+            if (east) red_add_v4_if<16>(dn, x1in && y0in, gne[4 * jj], gne[4 * jj + 1], gne[4 * jj + 2], gne[4 * jj + 3]);
+            if (east) red_add_v4_if<16>(ds, x1in && y1in, gse[4 * jj], gse[4 * jj + 1], gse[4 * jj + 2], gse[4 * jj + 3]);
         }
     };
     // running pointers of the per-plane operands (one 64-bit add per plane instead of the index arithmetic)
@@ -535,13 +401,28 @@ __global__ void gparam_to_float_kernel(const double* __restrict__ src, const dou
     dst[i] = (float)val;
 }
 
+// BatchNorm3d's running statistics after a train-mode forward: the module is applied once per source view, so the reference
+// performs V momentum updates in view order (torch.nn.BatchNorm3d: running = (1 - f) running + f batch, unbiased variance;
+// f = momentum, or 1 / num_batches_tracked when momentum is None).  One thread; in place.
+__global__ void bn_running_update_kernel(const float* __restrict__ batch_stats, int V, float momentum, float* __restrict__ running_mean,
+                                         float* __restrict__ running_var, long long* __restrict__ num_batches_tracked)
+{
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    float rm = running_mean[0], rv = running_var[0];
+    long long n = num_batches_tracked ? num_batches_tracked[0] : 0;
+    for (int v = 0; v < V; ++v) {
+        ++n;
+        const float f = momentum >= 0.0f ? momentum : (float)(1.0 / (double)n);
+        rm = fmaf(f, batch_stats[2 * v] - rm, rm);
+        rv = fmaf(f, batch_stats[2 * v + 1] - rv, rv);
+    }
+    running_mean[0] = rm; running_var[0] = rv;
+    if (num_batches_tracked) num_batches_tracked[0] = n;
+}
+
 // ------------------------------------------------------------------------------------------------
 // workspace
 // ------------------------------------------------------------------------------------------------
-// diagnostic switch (environment MDF_B200_BWD_DIRECT=1 at library load): phase 1 of the backward through the
-// one-thread-per-element kernel instead of the staged gather
-static const bool g_bwd_phase1_direct = [] { const char* e = getenv("MDF_B200_BWD_DIRECT"); return e && e[0] == '1'; }();
-
 struct TrainWorkspace {
     size_t rt, dwp, q, s, cq, bnv, vparams, fc, za, go, stats, bsum, gparam, dq, ds, total;
 };
@@ -691,12 +572,8 @@ static int train_bwd(const TrainCall& c, const float* cost_volume, const float* 
     const size_t total = (size_t)c.B * c.D * c.H * c.W;
     const unsigned blocks = (unsigned)((total + 255) / 256);
     a.za = reinterpret_cast<float*>(wsb + ws.za);
-    if (g_bwd_phase1_direct) {
-        bwd_stats_kernel<G><<<blocks, 256, 0, stream>>>(a, reinterpret_cast<double*>(wsb + ws.bsum));      // per-element values for the sweep, batch sums, d fc
-        st = launch_status();
-        if (st != MDF_OK) return st;
-    } else {
-        // phase 1 on the TMA-staged gather (MODE 3), then the per-element pass
+    {
+        // phase 1 on the TMA-staged gather (MODE 3 of the hot kernel), then the per-element pass
         StagedArgs sa = staged_args(c, wsb, ws, nullptr);
         sa.gout = grad_out; sa.fwd_out = cost_volume; sa.za = a.za; sa.go = reinterpret_cast<float*>(wsb + ws.go);
         st = launch_staged_train<3>(G, sa, staged_buffers(wsb, ws), stream);
@@ -759,6 +636,22 @@ int mdf_cost_volume_train_fwd(const float* const* features, int N, const float* 
     if (G == 32) return train_fwd<32>(c, cost_volume, batch_stats, wsb, ws, s);
     if (G == 16) return train_fwd<16>(c, cost_volume, batch_stats, wsb, ws, s);
     return train_fwd<8>(c, cost_volume, batch_stats, wsb, ws, s);
+}
+
+int mdf_bn_running_update(const float* batch_stats, int V, float momentum, float* running_mean, float* running_var,
+                          long long* num_batches_tracked, mdf_stream_t stream)
+{
+    if (V < 0 || V > kMaxSrcViews) return MDF_ERR_INVALID_SHAPE;
+    if (V == 0) return MDF_OK;
+    if (!batch_stats || !running_mean || !running_var) return MDF_ERR_NULL_POINTER;
+    const int dev = device_of(running_mean);
+    if (dev < 0) return dev;
+    const void* ptrs[4] = {batch_stats, running_mean, running_var, num_batches_tracked};
+    const int st = check_on_device(dev, ptrs, num_batches_tracked ? 4 : 3);
+    if (st != MDF_OK) return st;
+    DeviceGuard guard(dev);
+    bn_running_update_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(batch_stats, V, momentum, running_mean, running_var, num_batches_tracked);
+    return launch_status();
 }
 
 int mdf_cost_volume_bwd(const float* const* features, int N, const float* ref_proj, const float* const* src_projs,

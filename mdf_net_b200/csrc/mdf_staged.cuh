@@ -338,11 +338,11 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
     };
     auto flush_stats = [&](int v) {
         if (MODE == 1) {
-            // a thread's handful of samples in float, everything beyond that (32 lanes, the CTA, the grid) in double
-            double d1 = (double)zs1, d2 = (double)zs2;
+            // a warp's handful of samples (at most 32 * PT) in float, everything beyond that (the CTA, the grid) in double
+            float f1 = zs1, f2 = zs2;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { d1 += __shfl_xor_sync(0xffffffffu, d1, o); d2 += __shfl_xor_sync(0xffffffffu, d2, o); }
-            if (lane == 0 && (d1 != 0.0 || d2 != 0.0)) { atomicAdd(&stats_s[2 * v], d1); atomicAdd(&stats_s[2 * v + 1], d2); }
+            for (int o = 16; o > 0; o >>= 1) { f1 += __shfl_xor_sync(0xffffffffu, f1, o); f2 += __shfl_xor_sync(0xffffffffu, f2, o); }
+            if (lane == 0 && (f1 != 0.0f || f2 != 0.0f)) { atomicAdd(&stats_s[2 * v], (double)f1); atomicAdd(&stats_s[2 * v + 1], (double)f2); }
             zs1 = 0.0f; zs2 = 0.0f;
         }
     };

@@ -470,6 +470,26 @@ def cost_volume_train(features: List[Tensor], ref_proj: Tensor, src_projs: List[
     return out, stats
 
 
+@torch.library.custom_op("mdfnet_b200::bn_running_update", mutates_args=("running_mean", "running_var", "num_batches_tracked"),
+                         device_types="cuda")
+def bn_running_update(batch_stats: Tensor, momentum: float, running_mean: Tensor, running_var: Tensor,
+                      num_batches_tracked: Tensor) -> None:
+    """The momentum updates of BatchNorm3d's running statistics after a train-mode `cost_volume_train`: one per source view, in
+    view order (base.py:50-68 applied per view by homoaggregate.py:40), in place, one launch.  momentum < 0: momentum=None
+    (cumulative moving average)."""
+    stats = _f32c(batch_stats, "batch_stats")
+    if stats.dim() != 2 or stats.shape[1] != 2:
+        raise RuntimeError(f"mdfnet_b200: batch_stats must be (N-1,2), got {tuple(stats.shape)}")
+    for t, name, dt in ((running_mean, "running_mean", torch.float32), (running_var, "running_var", torch.float32),
+                        (num_batches_tracked, "num_batches_tracked", torch.int64)):
+        if t.dtype != dt or t.numel() != 1 or not t.is_cuda or not t.is_contiguous():
+            raise RuntimeError(f"mdfnet_b200: {name} must be a contiguous CUDA {dt} tensor with one element")
+    st = _cabi.lib().mdf_bn_running_update(stats.data_ptr(), stats.shape[0], float(momentum), running_mean.data_ptr(),
+                                           running_var.data_ptr(), num_batches_tracked.data_ptr(), _stream(stats))
+    _cabi.check("mdf_bn_running_update", st)
+    _count(1)
+
+
 @cost_volume_train.register_fake
 def _(features, ref_proj, src_projs, depth_hypos, conv_weight, bn_weight, bn_bias, bn_mean, bn_var, bn_eps,
       fc_weight, fc_bias, groups, training):
