@@ -51,28 +51,6 @@ struct TrainArgs {
 // 1/(1+2^t) with the same MUFU approximations (<= 2 ulp each) as the forward kernel it differentiates
 __device__ __forceinline__ float sigm2(float t) { return rcp_approx(1.0f + ex2_approx(fminf(t, 126.0f))); }
 
-// block-wide sum of `n` doubles per thread -> atomicAdd into dst (one atomic per block and value)
-template <int N>
-__device__ __forceinline__ void block_accumulate(double (&val)[N], double* __restrict__ dst)
-{
-    __shared__ double red[32][N];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
-#pragma unroll
-    for (int k = 0; k < N; ++k)
-        for (int o = 16; o > 0; o >>= 1) val[k] += __shfl_xor_sync(0xffffffffu, val[k], o);
-    if (lane == 0)
-        for (int k = 0; k < N; ++k) red[warp][k] = val[k];
-    __syncthreads();
-    if (warp == 0) {
-        for (int k = 0; k < N; ++k) {
-            double s = lane < nwarp ? red[lane][k] : 0.0;
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane == 0 && s != 0.0) atomicAdd(dst + k, s);
-        }
-    }
-    __syncthreads();
-}
-
 // ---- BatchNorm constants per view (1 thread) ---------------------------------------------------------
 // training: batch statistics from `stats`; else the running statistics.  Also publishes the batch mean and
 // the unbiased variance (momentum update of the running statistics happens on the host side of the ABI).
@@ -168,9 +146,18 @@ bwd_finalize_kernel(const BwdArgs a, const float* __restrict__ vparams, const fl
         wsum += weight_of(v, a.za[(size_t)(3 * v + 1) * total + i], h);
     }
     const float go = __ldg(go_all + i);
-    double gfc[2] = {0.0, 0.0};
+    // the sums: a warp's 32 values in float, across warps and blocks in double; ONE block-wide hand-over for all 2V + 2 of them
+    __shared__ double red[2 * kMaxSrcViews + 2];
+    for (int k = threadIdx.x; k < 2 * kMaxSrcViews + 2; k += blockDim.x) red[k] = 0.0;
+    __syncthreads();
+    auto warp_add = [&](float val, int slot) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+        if ((threadIdx.x & 31) == 0 && val != 0.0f) atomicAdd(&red[slot], (double)val);
+    };
+    float gfc0 = 0.0f, gfc1 = 0.0f;
     for (int v = 0; v < t.V; ++v) {
-        double s[2] = {0.0, 0.0};
+        float s0 = 0.0f, s1 = 0.0f;
         if (ok) {
             const float zs = a.za[(size_t)(3 * v + 1) * total + i], aprime = a.za[(size_t)(3 * v) * total + i];
             float h, dact;
@@ -178,16 +165,21 @@ bwd_finalize_kernel(const BwdArgs a, const float* __restrict__ vparams, const fl
             const float dh = dh_of(a, aprime, go, wsum, w, h, &dact);
             const float z = zs + __ldg(vparams + 4 * v + 3);
             const float zhat = (z - __ldg(t.bnv + 4 * v + 3)) * __ldg(t.bnv + 4 * v + 2);
-            s[0] = dh; s[1] = (double)dh * zhat;
-            gfc[0] += (double)dact * fmaxf(h, 0.0f);
-            gfc[1] += dact;
+            s0 = dh; s1 = dh * zhat;
+            gfc0 = fmaf(dact, fmaxf(h, 0.0f), gfc0);
+            gfc1 += dact;
             a.za[(size_t)(3 * v) * total + i] = dh;
             a.za[(size_t)(3 * v + 1) * total + i] = z;
             a.za[(size_t)(3 * v + 2) * total + i] = w / wsum;
         }
-        block_accumulate<2>(s, bsum + 2 * v);
+        warp_add(s0, 2 * v);
+        warp_add(s1, 2 * v + 1);
     }
-    block_accumulate<2>(gfc, a.gparam + 2);
+    warp_add(gfc0, 2 * t.V);
+    warp_add(gfc1, 2 * t.V + 1);
+    __syncthreads();
+    if ((int)threadIdx.x < 2 * t.V) { if (red[threadIdx.x] != 0.0) atomicAdd(bsum + threadIdx.x, red[threadIdx.x]); }
+    else if ((int)threadIdx.x < 2 * t.V + 2) { if (red[threadIdx.x] != 0.0) atomicAdd(a.gparam + 2 + (threadIdx.x - 2 * t.V), red[threadIdx.x]); }
 }
 
 // predicated 16-byte read-only load at p + OFF bytes (zero when the predicate is off): keeps ONE address register pair per

@@ -103,6 +103,10 @@ def test_argument_validation_without_a_device(libpath):
                                       1, 16, 8, 8, 4, 4, None, None, 0, 0, None, None, None) == -1          # N < 2
     assert lib.mdf_cost_volume_fwd_ex(None, 3, None, None, None, 0, None, None, None, None, None, 1e-5, None, None,
                                       1, 16, 8, 8, 4, 4, None, None, 0, 16, None, None, None) in (-2, -3)   # tuning variants: not in the product build
+    # running statistics of the train-mode BatchNorm
+    assert lib.mdf_bn_running_update(None, 0, 0.1, None, None, None, None) == 0                 # no source view: nothing to do
+    assert lib.mdf_bn_running_update(None, 3, 0.1, P, P, None, None) == -3                      # no batch statistics
+    assert lib.mdf_bn_running_update(P, 99, 0.1, P, P, None, None) == -1                        # more views than the path supports
     # geometric filter
     assert lib.mdf_geo_filter_workspace_bytes(4) >= (20 + 4 * 64) * 4
     assert lib.mdf_geo_filter_fwd(P, P, P, None, None, None, 33, 4, 4, None, 0.8, 5, 4.0, 1300.0, None, None, P, None, None, None,

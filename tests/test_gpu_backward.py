@@ -144,3 +144,32 @@ def test_backward_is_linear_and_eval_train_paths_agree():
     with torch.no_grad():
         fast = m([cu(f) for f in feats], cu(ref_proj), [cu(s) for s in src_projs], cu(hyp)).cpu().numpy()
     assert rel_l2(fast, a["cv"]) < 1e-5
+
+
+@pytest.mark.parametrize("momentum", [0.1, 0.37, None])
+def test_running_statistics_update_is_v_sequential_batchnorm_updates(momentum):
+    """mdf_bn_running_update = what BatchNorm3d does to its buffers when the module is applied once per source view
+    (base.py:50-68 inside homoaggregate.py:40): V momentum updates in view order, or the cumulative average when momentum is None."""
+    from mdf_net_b200 import ops
+    V = 6
+    rng = np.random.default_rng(11)
+    stats = rng.random((V, 2)).astype(np.float32) + 0.1
+    bn = torch.nn.BatchNorm3d(1, momentum=momentum).cuda().train()
+    with torch.no_grad():
+        bn.running_mean.fill_(0.3); bn.running_var.fill_(1.7); bn.num_batches_tracked.fill_(5)
+    rm, rv, nbt = bn.running_mean.clone(), bn.running_var.clone(), bn.num_batches_tracked.clone()
+    ops.bn_running_update(cu(stats), -1.0 if momentum is None else momentum, rm, rv, nbt)
+    # the reference: feed BatchNorm3d inputs whose batch statistics are exactly stats[v]
+    for v in range(V):
+        n = 4096
+        x = torch.randn(n, dtype=torch.float64, device="cuda")
+        x = (x - x.mean()) / x.std(unbiased=True) * float(np.sqrt(stats[v, 1])) + float(stats[v, 0])
+        bn(x.float().view(n, 1, 1, 1, 1))
+    assert int(nbt.item()) == int(bn.num_batches_tracked.item()) == 5 + V
+    assert rm.item() == pytest.approx(bn.running_mean.item(), rel=2e-5)
+    assert rv.item() == pytest.approx(bn.running_var.item(), rel=2e-5)
+    # argument validation
+    with pytest.raises(RuntimeError):
+        ops.bn_running_update(cu(stats[:, :1]), 0.1, rm, rv, nbt)
+    with pytest.raises(RuntimeError):
+        ops.bn_running_update(cu(stats), 0.1, rm, rv, nbt.float())
