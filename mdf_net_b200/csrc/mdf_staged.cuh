@@ -322,13 +322,15 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
     float a_base[MODE == 3 ? PT : 1], a_void[MODE == 3 ? PT : 1];   // MODE 3: A' = a_base + sum_g (gout_g q_g) p_g; A' of an out-of-image sample
     const size_t total = (size_t)a.B * D * HW;
     const size_t e0 = ((size_t)b * D + d0) * HW + (size_t)py * W + px;      // element of plane d0 (+ i * HW)
-    __shared__ double stats_s[MODE == 1 ? 2 * kMaxSrcViews : 2];
+    // MODE 1: one row of sums per warp (plain read-modify-write by lane 0: a shared-memory double atomicAdd is a CAS spin loop)
+    __shared__ double stats_s[MODE == 1 ? Cfg::WARPS : 1][MODE == 1 ? 2 * kMaxSrcViews : 2];
+    double* stats_w = stats_s[MODE == 1 ? ty + TH * pg : 0];
     if (MODE == 2) {
 #pragma unroll
         for (int i = 0; i < PT; ++i) wvoid[i] = 0.0f;
     }
     if (MODE == 1)
-        for (int k = tid; k < 2 * kMaxSrcViews; k += THREADS) stats_s[k] = 0.0;
+        for (int k = tid; k < Cfg::WARPS * 2 * kMaxSrcViews; k += THREADS) (&stats_s[0][0])[k] = 0.0;
     // per-view BatchNorm fold (MODE 2) and, after a gather, the hand-over of this warp's statistics (MODE 1)
     auto set_view = [&](int v) {
         if (MODE == 2) { alpha = __ldg(a.vparams + 4 * v); betap = __ldg(a.vparams + 4 * v + 1); }
@@ -342,7 +344,7 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
             float f1 = zs1, f2 = zs2;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) { f1 += __shfl_xor_sync(0xffffffffu, f1, o); f2 += __shfl_xor_sync(0xffffffffu, f2, o); }
-            if (lane == 0 && (f1 != 0.0f || f2 != 0.0f)) { atomicAdd(&stats_s[2 * v], (double)f1); atomicAdd(&stats_s[2 * v + 1], (double)f2); }
+            if (lane == 0) { stats_w[2 * v] += (double)f1; stats_w[2 * v + 1] += (double)f2; }
             zs1 = 0.0f; zs2 = 0.0f;
         }
     };
@@ -703,7 +705,12 @@ cost_volume_staged_kernel(const __grid_constant__ StagedMaps maps, const StagedA
 
     if (MODE == 1) {
         __syncthreads();                             // every warp has handed its sums over
-        if (tid < 2 * a.V && stats_s[tid] != 0.0) atomicAdd(a.stats + tid, stats_s[tid]);
+        if (tid < 2 * a.V) {
+            double sum = 0.0;
+#pragma unroll
+            for (int w = 0; w < Cfg::WARPS; ++w) sum += stats_s[MODE == 1 ? w : 0][tid];
+            if (sum != 0.0) atomicAdd(a.stats + tid, sum);
+        }
         return;
     }
     if (MODE == 3) return;
