@@ -348,6 +348,125 @@ variance_volume_reg_kernel(const VarArgs a)
         }
 }
 
+// ---- the fast variant (C = 16 / 32 / 64, the reference's channel counts): C/16 lanes share a sample ----------------
+// A layout pass writes the source views as channel quads, planar: P4[v][b][C/4][H][W] float4, so a tap of four channels is
+// one 16-byte load (the NCHW kernels above issue four scalar loads with four address computations for it).  A thread keeps
+// 16 channels of the softmax and of the two running sums in registers (3 x 16 instead of 3 x 64 at C = 64: three blocks per
+// SM instead of one); with C = 32 / 64 a warp is 16 / 8 consecutive samples x 2 / 4 channel parts and the maximum and the sum
+// of exponentials of a view meet over the lanes of a sample by shuffles.  The bilinear blend keeps the reference's tap order;
+// the softmax runs on the MUFU (2^x and ONE reciprocal of the sum per view instead of expf and C true divisions).
+__global__ void __launch_bounds__(256)
+planar4_kernel(FeaPtrs fea, int V, int B, int C, int HW, float4* __restrict__ out)
+{
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= HW) return;
+    const int C4 = C / 4;
+    const int c4 = blockIdx.y % C4, b = (blockIdx.y / C4) % B, v = blockIdx.y / (C4 * B);
+    const float* f = fea.p[v + 1] + ((size_t)b * C + 4 * c4) * HW + pix;
+    out[(((size_t)v * B + b) * C4 + c4) * HW + pix] = make_float4(__ldg(f), __ldg(f + HW), __ldg(f + 2 * (size_t)HW), __ldg(f + 3 * (size_t)HW));
+}
+
+template <int OFF>
+__device__ __forceinline__ float4 ldg4_pred(const float4* p, bool pred)
+{
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t@q ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4+%6];\n\t}"
+        : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w) : "l"(p), "r"((int)pred), "n"(OFF));
+    return v;
+}
+
+template <int LANES>   // lanes per sample: C = 16 * LANES channels, 16 per thread
+__global__ void __launch_bounds__(256, 3)
+variance_volume_quad_kernel(const VarArgs a, const float4* __restrict__ P4)
+{
+    constexpr int CQ = 16, Q = CQ / 4, SPW = 32 / LANES;       // channels / float4 quads per thread, samples per warp
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int part = lane / SPW, slot = lane % SPW;  // which 16 channels; which sample of the warp
+    const uint32_t HW = (uint32_t)a.H * a.W;
+    const uint32_t total = (uint32_t)a.B * a.D * HW; // < 2^31 (host checked): 32-bit index arithmetic
+    const uint32_t sidx = blockIdx.x * (8u * SPW) + warp * SPW + slot;
+    const bool live = sidx < total;
+    const uint32_t idx = live ? sidx : total - 1;    // idle lanes shadow the last sample (the shuffles below are warp wide)
+    const uint32_t pix = idx % HW, bd = idx / HW;
+    const int x = (int)(pix % (uint32_t)a.W), y = (int)(pix / (uint32_t)a.W);
+    const int d = (int)(bd % (uint32_t)a.D), b = (int)(bd / (uint32_t)a.D);
+    constexpr int C = CQ * LANES, C4 = C / 4;
+    const int c0 = part * CQ;
+    const GridNormFast gf = make_grid_norm_fast(a.H, a.W);       // the bit-exact position chain on shared reciprocals (mdf_common.cuh)
+    const float depth = a.per_pixel ? __ldg(a.hypos + (size_t)bd * HW + pix) : __ldg(a.hypos + bd);
+    float s1[CQ], s2[CQ];
+    const float* ref = a.fea.p[0] + ((size_t)b * C + c0) * HW + pix;
+#pragma unroll
+    for (int c = 0; c < CQ; ++c) {
+        const float rv = __ldg(ref + (size_t)c * HW);                       // the raw reference feature (homoaggregate.py:56-57)
+        s1[c] = rv;
+        s2[c] = rv * rv;
+    }
+    for (int v0 = 0; v0 < a.V; v0 += LANES) {
+        // the LANES lanes of a sample find the positions of LANES views, one each, and hand them round by shuffle
+        float myx, myy;
+        {
+            const int mv = min(v0 + part, a.V - 1);
+            float rt[12];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) rt[k] = __ldg(a.rt + ((size_t)mv * a.B + b) * 12 + k);
+            sample_position_fast(rot_xyz(rt, (float)x, (float)y), rt, depth, gf, myx, myy);
+        }
+#pragma unroll
+        for (int k = 0; k < LANES; ++k) {
+            const int v = v0 + k;
+            if (v >= a.V) break;                     // warp uniform
+            const float ix = LANES == 1 ? myx : __shfl_sync(0xffffffffu, myx, slot + k * SPW);
+            const float iy = LANES == 1 ? myy : __shfl_sync(0xffffffffu, myy, slot + k * SPW);
+            const Taps t = make_taps(ix, iy, gf.g);
+            const bool x0in = t.valid && (unsigned)t.x0 < (unsigned)a.W, x1in = t.valid && (unsigned)(t.x0 + 1) < (unsigned)a.W;
+            const bool y0in = (unsigned)t.y0 < (unsigned)a.H, y1in = (unsigned)(t.y0 + 1) < (unsigned)a.H;
+            const bool inw = x0in && y0in, ine = x1in && y0in, isw = x0in && y1in, ise = x1in && y1in;
+            const float4* pn = P4 + (((size_t)v * a.B + b) * C4 + c0 / 4) * HW + (t.y0 * a.W + t.x0);
+            const float4* ps = pn + a.W;
+            float val[CQ];
+#pragma unroll
+            for (int q = 0; q < Q; ++q, pn += HW, ps += HW) {
+                const float4 nw = ldg4_pred<0>(pn, inw), ne = ldg4_pred<16>(pn, ine);
+                const float4 sw = ldg4_pred<0>(ps, isw), se = ldg4_pred<16>(ps, ise);
+                val[4 * q + 0] = blend4(nw.x, ne.x, sw.x, se.x, t); val[4 * q + 1] = blend4(nw.y, ne.y, sw.y, se.y, t);
+                val[4 * q + 2] = blend4(nw.z, ne.z, sw.z, se.z, t); val[4 * q + 3] = blend4(nw.w, ne.w, sw.w, se.w, t);
+            }
+            float m = val[0];
+#pragma unroll
+            for (int c = 1; c < CQ; ++c) m = fmaxf(m, val[c]);
+#pragma unroll
+            for (int o = SPW; o < 32; o <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            // exp(v - m) = 2^((v - m) log2e) on the MUFU (|error| <= ~3 ulp of the largest term: the terms that lose relative
+            // precision are the ones that are tiny next to it), one reciprocal of the sum instead of C divisions
+            const float ml = m * kLog2e;
+            float sum = 0.0f;
+#pragma unroll
+            for (int c = 0; c < CQ; ++c) { val[c] = ex2_approx(fmaf(val[c], kLog2e, -ml)); sum += val[c]; }
+#pragma unroll
+            for (int o = SPW; o < 32; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);      // the same value in all lanes of a sample
+            const float rs = __frcp_rn(sum);
+#pragma unroll
+            for (int c = 0; c < CQ; ++c) {
+                const float pr = val[c] * rs;
+                s1[c] += pr;
+                s2[c] = fmaf(pr, pr, s2[c]);
+            }
+        }
+    }
+    if (!live) return;
+    // volume_sq_sum / n - (volume_sum / n)^2 (homoaggregate.py:66): n is a small integer, the divisions are exact-rounded
+    // through its refined reciprocal (div_by, mdf_common.cuh)
+    const float nviews = (float)(a.V + 1), rn = refine_rcp(nviews);
+    float* o = a.out + ((size_t)b * C + c0) * ((size_t)a.D * HW) + (size_t)d * HW + pix;
+    const size_t ostride = (size_t)a.D * HW;
+#pragma unroll
+    for (int c = 0; c < CQ; ++c) {
+        const float mean = div_by(s1[c], nviews, rn);
+        o[(size_t)c * ostride] = __fsub_rn(div_by(s2[c], nviews, rn), __fmul_rn(mean, mean));
+    }
+}
+
 __global__ void __launch_bounds__(256)
 variance_volume_kernel(const VarArgs a)
 {
@@ -667,11 +786,16 @@ int mdf_homo_warp_fwd(const float* src_fea, const float* src_proj, const float* 
     return launch_status();
 }
 
+static bool variance_quad_supported(int C) { return C == 16 || C == 32 || C == 64; }
+
 size_t mdf_variance_volume_workspace_bytes(int B, int N, int C, int D, int H, int W)
 {
-    (void)C; (void)D; (void)H; (void)W;
+    (void)D;
     if (B <= 0 || N < 2) return 0;
-    return align_up((size_t)(N - 1) * B * 12 * sizeof(float), 256);
+    size_t bytes = align_up((size_t)(N - 1) * B * 12 * sizeof(float), 256);
+    // the fast variant's channel-quad copy of the source views
+    if (variance_quad_supported(C) && H > 0 && W > 0) bytes += align_up((size_t)(N - 1) * B * C * H * W * sizeof(float), 256);
+    return bytes;
 }
 
 int mdf_variance_volume_fwd(const float* const* features, int N, const float* ref_proj, const float* const* src_projs,
@@ -707,6 +831,20 @@ int mdf_variance_volume_fwd(const float* const* features, int N, const float* re
     const size_t total = (size_t)B * D * H * W;
     if ((total + 255) / 256 > 0x7fffffffull) return MDF_ERR_UNSUPPORTED;
     const unsigned blocks = (unsigned)((total + 255) / 256);
+    const bool grid_ok = (long long)(N - 1) * B * (C / 4) <= 65535 && (long long)H * W <= INT_MAX - 256 && total < 0x7fffffffull;
+    if (variance_quad_supported(C) && grid_ok) {
+        float4* P4 = reinterpret_cast<float4*>(static_cast<uint8_t*>(workspace) + align_up((size_t)(N - 1) * B * 12 * sizeof(float), 256));
+        const int HWi = H * W;
+        planar4_kernel<<<dim3((unsigned)((HWi + 255) / 256), (unsigned)((N - 1) * B * (C / 4))), 256, 0, stream>>>(a.fea, N - 1, B, C, HWi, P4);
+        st = launch_status();
+        if (st != MDF_OK) return st;
+        const int lanes = C / 16, spb = 8 * (32 / lanes);                       // samples per block
+        const unsigned qblocks = (unsigned)((total + spb - 1) / spb);
+        if (lanes == 1) variance_volume_quad_kernel<1><<<qblocks, 256, 0, stream>>>(a, P4);
+        else if (lanes == 2) variance_volume_quad_kernel<2><<<qblocks, 256, 0, stream>>>(a, P4);
+        else variance_volume_quad_kernel<4><<<qblocks, 256, 0, stream>>>(a, P4);
+        return launch_status();
+    }
     if (C <= 16) variance_volume_reg_kernel<16><<<blocks, 256, 0, stream>>>(a);
     else if (C <= 32) variance_volume_reg_kernel<32><<<blocks, 256, 0, stream>>>(a);
     else if (C <= 64) variance_volume_reg_kernel<64><<<blocks, 256, 0, stream>>>(a);
