@@ -256,10 +256,11 @@ def test_variance_aggregate_golden(name):
     assert_cost_close(out.cpu().numpy(), z["cost_volume"], name)
 
 
-@pytest.mark.parametrize("C", [12, 32, 64, 72])
+@pytest.mark.parametrize("C", [12, 16, 32, 64, 72])
 def test_variance_aggregate_channel_counts_vs_oracle(C):
-    """The register-resident kernels (C <= 16 / 32 / 64, incl. a count that is not a multiple of 8) and the chunked
-    kernel (C > 64) against the oracle."""
+    """The channel-quad kernels (C = 16 / 32 / 64: 1 / 2 / 4 lanes per sample, a sample count that does not fill the last
+    block), the register-resident kernels (other C <= 64, incl. a count that is not a multiple of 8) and the chunked kernel
+    (C > 64) against the oracle."""
     import mdf_net_b200 as mdf
     from oracle import c_oracle as co
     B, N, D, H, W = 2, 4, 5, 20, 28
