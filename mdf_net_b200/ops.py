@@ -522,7 +522,7 @@ def cost_volume_bwd(features: List[Tensor], ref_proj: Tensor, src_projs: List[Te
         _f32c(batch_stats, "batch_stats").data_ptr() if training and batch_stats.numel() else None,
         _cabi.ptr_array([g.data_ptr() for g in gfeats]), gparams.data_ptr(), ws.data_ptr(), ws.numel(), _stream(cv))
     _cabi.check("mdf_cost_volume_bwd", st)
-    _count(7)           # setup, layout pass, fold, per-element pass, plane sweep, finish, parameter gradients
+    _count(8)           # setup, layout pass, fold, staged gather (phase 1a), per-element pass (1b), plane sweep, finish, parameter gradients
     return gfeats, gparams
 
 
