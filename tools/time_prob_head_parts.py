@@ -55,4 +55,11 @@ for stage in range(3):
     def full():
         ops.prob_head(x, w, hyp, curve, want_logits=False, want_prob=False, want_confidence=stage == 2)
 
+    if stage > 0:
+        hu = cu(syn.uniform_hypos(1, D))
+
+        def full_uniform():
+            ops.prob_head(x, w, hu, curve, want_logits=False, want_prob=False, want_confidence=stage == 2)
+
+        print(f"   stage {stage} with per-plane (uniform) hypotheses instead of per-pixel ones: {timeit(full_uniform):.1f} us")
     print(f"stage {stage}: conv + logits store {timeit(conv_only):.1f} us, + softmax/regression {timeit(no_fit):.1f} us, whole launch {timeit(full):.1f} us")
