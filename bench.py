@@ -347,7 +347,7 @@ def time_other_rows(dev):
     out = {"not_in_value": True}
     h0, w0, nviews, batch = 576, 768, 5, 8
     K, E = syn.camera_rig(batch, nviews, h0, w0, seed=3)
-    train = []
+    train, steady = [], []
     for s in range(3):
         H, W = syn.stage_shapes(h0, w0)[s]
         C, D, G = syn.STAGE_CHANNELS[s], syn.STAGE_DEPTHS[s], syn.STAGE_GROUPS[s]
@@ -358,8 +358,12 @@ def time_other_rows(dev):
         m = mdf.VectorAggregate(G).to(dev).train()
         go = torch.randn((batch, G, D, H, W), device=dev)
         train.append(med(lambda: m(feats, rp, sps, hyp).backward(go), n=3, warm=1))
+        # steady state: four iterations follow each other (the CPU runs ahead of the GPU, as in a training loop); the single-call
+        # figure above starts every measurement on an idle GPU and so includes ~0.2 ms of Python / autograd before the first launch
+        steady.append(med(lambda: [m(feats, rp, sps, hyp).backward(go) for _ in range(4)], n=3, warm=1) / 4.0)
         del feats, go, m
     out["train_fwd_bwd_ms_768x576_n5_b8"] = train
+    out["train_fwd_bwd_steady_state_ms_768x576_n5_b8"] = steady
     K, E = syn.camera_rig(1, 5, 1152, 1600, seed=1)
     H, W = syn.stage_shapes(1152, 1600)[0]
     P = syn.projection_matrices(K, E, 8.0)

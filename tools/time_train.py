@@ -21,4 +21,5 @@ for stage in range(3):
         me = make_module(G, p).eval()
         t_eval = timeit(lambda: me([f.detach() for f in fs], rp, sps, hy))
     t_f, t_b = timeit(fwd), timeit(both)
-    print(f"stage {stage}: eval fwd {t_eval:.2f} ms, train fwd {t_f:.2f} ms, fwd+bwd {t_b:.2f} ms")
+    t_s = timeit(lambda: [both() for _ in range(4)]) / 4.0
+    print(f"stage {stage}: eval fwd {t_eval:.2f} ms, train fwd {t_f:.2f} ms, fwd+bwd {t_b:.2f} ms (steady state, 4 iterations back to back: {t_s:.2f} ms)")
