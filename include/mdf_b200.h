@@ -228,7 +228,7 @@ MDF_API int mdf_hypos_generate_fwd(const float *depth, const float *s, const flo
  * threshold i = 2..10 (dist < i/thre1 px and relative depth difference < i/thre2), i.e. the `masks` list of
  * check_geometric_consistency; depth_reprojected (S,H,W), zero where the loosest mask fails; depth_averaged (H,W);
  * geo_mask / photo_mask / final_mask (H,W) uint8 as filter() computes them (photo_mask = confidence > photo_threshold,
- * all ones when confidence is NULL). */
+ * all ones when confidence is NULL).  thre1 and thre2 must be positive and finite (MDF_ERR_UNSUPPORTED otherwise). */
 #define MDF_MAX_FILTER_VIEWS 32
 MDF_API size_t mdf_geo_filter_workspace_bytes(int S);
 MDF_API int mdf_geo_filter_fwd(const float *ref_depth, const float *ref_intrinsics, const float *ref_extrinsics,

@@ -94,7 +94,8 @@ struct GeoArgs {
     uint8_t* geo;               // (H,W) or nullptr
     uint8_t* photo;
     uint8_t* fin;
-    float photo_threshold, thre1, thre2;
+    float photo_threshold;
+    float thr1[9], thr2[9];     // i / thre1, i / thre2 for i = 2..10 (the host's float divisions are the same IEEE quotients)
     int nconditions, S, H, W;
 };
 
@@ -135,22 +136,21 @@ static __global__ void __launch_bounds__(256)
 geo_filter_kernel(const GeoArgs a)
 {
     extern __shared__ float mat_s[];                 // ref_mats[18] (+pad to 20), then S x kGeoMat
-    __shared__ float thr_s[18];                      // i / thre1, i / thre2 for i = 2..10: the same true divisions, once per CTA
     for (int i = threadIdx.x; i < 20 + a.S * kGeoMat; i += blockDim.x)
         mat_s[i] = i < 18 ? __ldg(a.ref_mats + i) : (i < 20 ? 0.0f : __ldg(a.mats + (i - 20)));
-    if (threadIdx.x < 18) thr_s[threadIdx.x] = __fdiv_rn((float)(threadIdx.x % 9 + 2), threadIdx.x < 9 ? a.thre1 : a.thre2);
     __syncthreads();
-    const size_t HW = (size_t)a.H * a.W;
-    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t HW = (uint32_t)a.H * (uint32_t)a.W;           // < 2^31 (host checked): 32-bit index arithmetic
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= HW) return;
-    const int y = (int)(p / a.W), x = (int)(p % a.W);
+    const int y = (int)(p / (uint32_t)a.W), x = (int)(p % (uint32_t)a.W);
     const float fx = (float)x, fy = (float)y;
     const float d = __ldg(a.ref_depth + p);
     const float* Krinv = mat_s;
     const float* Kr = mat_s + 9;
     const float r_wm1 = refine_rcp((float)(a.W - 1)), r_hm1 = refine_rcp((float)(a.H - 1)), r_d = refine_rcp(d);
-    uint32_t counts = 0;                             // 9 counters of 3 bits would overflow at S > 7: use two words
-    uint32_t counts_hi = 0;
+    // The thresholds grow with i, so a source view passes all of them from some i on: one count per view (how many it
+    // fails, 0..9) and a histogram of those counts, 6 bits per bin (S <= 32), instead of 9 mask bits and 9 counters.
+    unsigned long long hist = 0;
     int nvalid = 0;
     float dsum = 0.0f;
     for (int s = 0; s < a.S; ++s) {
@@ -171,25 +171,23 @@ geo_filter_kernel(const GeoArgs a)
         const float dx = __fsub_rn(xr, fx), dy = __fsub_rn(yr, fy);
         const float dist = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));   // :170
         const float rel = div_shared(fabsf(__fsub_rn(drep, d)), d, r_d);              // :173-174
-        uint32_t b = 0;
+        int nfail = 0;                                                                // :175-177, i = 2..10
 #pragma unroll
-        for (int i = 2; i < 11; ++i)
-            if (dist < thr_s[i - 2] && rel < thr_s[9 + i - 2]) b |= 1u << (i - 2);
-        // per-threshold counters, 6 bits each: thresholds 2-6 in `counts`, 7-10 in `counts_hi`
-#pragma unroll
-        for (int i = 0; i < 5; ++i) counts += ((b >> i) & 1u) << (6 * i);
-#pragma unroll
-        for (int i = 5; i < 9; ++i) counts_hi += ((b >> i) & 1u) << (6 * (i - 5));
-        const bool last = (b >> 8) & 1u;
+        for (int i = 0; i < 9; ++i)
+            if (!(dist < a.thr1[i] && rel < a.thr2[i])) ++nfail;
+        const uint32_t b = (0x1FFu << nfail) & 0x1FFu;        // bit i-2 <-> the mask of threshold i
+        hist += 1ull << (6 * nfail);
+        const bool last = nfail < 9;                          // passes i = 10
         if (a.bits) a.bits[(size_t)s * HW + p] = (uint16_t)b;
         if (a.depth_reprojected) a.depth_reprojected[(size_t)s * HW + p] = last ? drep : 0.0f;      // :180
         if (last) { ++nvalid; dsum = __fadd_rn(dsum, drep); }
     }
-    int geo = 0;
+    int geo = 0, cum = 0;
 #pragma unroll
-    for (int i = 0; i < 5; ++i) geo += (int)((counts >> (6 * i)) & 63u) >= i + 2;                   // filter():86-88
-#pragma unroll
-    for (int i = 5; i < 9; ++i) geo += (int)((counts_hi >> (6 * (i - 5))) & 63u) >= i + 2;
+    for (int i = 0; i < 9; ++i) {                             // views that pass threshold i+2 = views failing at most i of them
+        cum += (int)((hist >> (6 * i)) & 63ull);
+        geo += cum >= i + 2;                                  // filter():86-88
+    }
     const bool g = a.S > 0 && geo >= a.nconditions;
     const bool ph = a.confidence ? __ldg(a.confidence + p) > a.photo_threshold : true;
     if (a.depth_averaged) a.depth_averaged[p] = __fdiv_rn(__fadd_rn(dsum, d), (float)(nvalid + 1));  // :93
@@ -214,6 +212,8 @@ int mdf_geo_filter_fwd(const float* ref_depth, const float* ref_intrinsics, cons
 {
     if (S < 0 || H < 0 || W < 0) return MDF_ERR_INVALID_SHAPE;
     if (S > MDF_MAX_FILTER_VIEWS) return MDF_ERR_UNSUPPORTED;
+    // the kernel counts how many of the nine thresholds i / thre (i = 2..10) a view fails: they must grow with i
+    if (!(thre1 > 0.0f && thre2 > 0.0f && thre1 < 3.0e38f && thre2 < 3.0e38f)) return MDF_ERR_UNSUPPORTED;
     const size_t HW = (size_t)H * W;
     if (HW == 0) return MDF_OK;
     if (!ref_depth || !ref_intrinsics || !ref_extrinsics || !workspace) return MDF_ERR_NULL_POINTER;
@@ -254,10 +254,11 @@ int mdf_geo_filter_fwd(const float* ref_depth, const float* ref_intrinsics, cons
     a.ref_depth = ref_depth; a.confidence = confidence; a.ref_mats = ws; a.mats = ws + 20;
     a.bits = src_bits; a.depth_reprojected = depth_reprojected; a.depth_averaged = depth_averaged;
     a.geo = geo_mask; a.photo = photo_mask; a.fin = final_mask;
-    a.photo_threshold = photo_threshold; a.thre1 = thre1; a.thre2 = thre2; a.nconditions = nconditions;
+    a.photo_threshold = photo_threshold; a.nconditions = nconditions;
+    for (int i = 0; i < 9; ++i) { a.thr1[i] = (float)(i + 2) / thre1; a.thr2[i] = (float)(i + 2) / thre2; }
     a.S = S; a.H = H; a.W = W;
     const size_t blocks = (HW + 255) / 256;
-    if (blocks > 0x7fffffffu) return MDF_ERR_UNSUPPORTED;
+    if (HW > 0x7fffffffu) return MDF_ERR_UNSUPPORTED;
     const size_t smem = (size_t)(20 + S * kGeoMat) * sizeof(float);
     geo_filter_kernel<<<(unsigned)blocks, 256, smem, stream>>>(a);
     return launch_status();

@@ -115,6 +115,8 @@ def test_argument_validation_without_a_device(libpath):
                                   P, 1 << 20, None) == -3                                   # no output requested
     assert lib.mdf_geo_filter_fwd(P, P, P, None, None, None, 0, 4, 4, None, 0.8, 5, 4.0, 1300.0, None, None, P, None, None, None,
                                   P, 16, None) == -4                                        # workspace too small
+    assert lib.mdf_geo_filter_fwd(P, P, P, None, None, None, 0, 4, 4, None, 0.8, 5, 0.0, 1300.0, None, None, P, None, None, None,
+                                  P, 1 << 20, None) == -2                                   # thresholds must be positive
     assert lib.mdf_geo_filter_fwd(None, None, None, None, None, None, 0, 0, 4, None, 0.8, 5, 4.0, 1300.0, None, None, None, None,
                                   None, None, None, 0, None) == 0                           # empty map
 
