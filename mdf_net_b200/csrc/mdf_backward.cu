@@ -116,9 +116,9 @@ struct BwdArgs {
 };
 
 // dL/dh_v of one element given the per-view forward values
-__device__ __forceinline__ float dh_of(const BwdArgs& a, float aprime, float go, float wsum, float w, float h, float* dact_out)
+__device__ __forceinline__ float dh_of(const BwdArgs& a, float aprime, float go, float rwsum, float w, float h, float* dact_out)
 {
-    const float dw = (aprime - go) / wsum;              // d out_g / d w_v = (sim_vg - out_g) / wsum
+    const float dw = (aprime - go) * rwsum;             // d out_g / d w_v = (sim_vg - out_g) / wsum
     const float dact = dw * w * (1.0f - w);             // sigmoid
     if (dact_out) *dact_out = dact;
     return h > 0.0f ? dact * __ldg(a.t.fc) : 0.0f;      // Conv3d(1,1,1) then ReLU
@@ -136,41 +136,51 @@ bwd_finalize_kernel(const BwdArgs a, const float* __restrict__ vparams, const fl
     const bool ok = idx < total;
     const size_t i = ok ? idx : 0;
     const float fcw = __ldg(t.fc), fcb = __ldg(t.fc + 1);
+    // the view weight exactly as the forward kernel evaluates it (mdf_staged.cuh: BatchNorm fold, ReLU, Conv3d(1,1,1), sigmoid on
+    // the MUFU): the backward differentiates the function the forward computed
     auto weight_of = [&](int v, float zs, float& h) {
         h = fmaf(zs, __ldg(vparams + 4 * v), __ldg(vparams + 4 * v + 1));
-        return 1.0f / (1.0f + expf(-fmaf(fmaxf(h, 0.0f), fcw, fcb)));
+        return rcp_approx(1.0f + ex2_approx(-kLog2e * fmaf(fmaxf(h, 0.0f), fcw, fcb)));
     };
     float wsum = 0.0f;
-    for (int v = 0; v < t.V; ++v) {
-        float h;
-        wsum += weight_of(v, a.za[(size_t)(3 * v + 1) * total + i], h);
+    {
+        const float* zp = a.za + total + i;          // slot 3v+1 of view v
+        for (int v = 0; v < t.V; ++v, zp += 3 * total) {
+            float h;
+            wsum += weight_of(v, *zp, h);
+        }
     }
+    const float rws = __frcp_rn(wsum);
     const float go = __ldg(go_all + i);
-    // the sums: a warp's 32 values in float, across warps and blocks in double; ONE block-wide hand-over for all 2V + 2 of them
-    __shared__ double red[2 * kMaxSrcViews + 2];
-    for (int k = threadIdx.x; k < 2 * kMaxSrcViews + 2; k += blockDim.x) red[k] = 0.0;
+    // the sums: a warp's 32 values in float, across warps and blocks in double; one row per warp in shared memory (plain
+    // read-modify-write by lane 0: a shared-memory double atomicAdd is a CAS spin loop), ONE block-wide hand-over at the end
+    constexpr int NW = 8, NS = 2 * kMaxSrcViews + 2;
+    __shared__ double red[NW][NS];
+    for (int k = threadIdx.x; k < NW * NS; k += blockDim.x) (&red[0][0])[k] = 0.0;
     __syncthreads();
+    double* red_w = red[threadIdx.x >> 5];
     auto warp_add = [&](float val, int slot) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
-        if ((threadIdx.x & 31) == 0 && val != 0.0f) atomicAdd(&red[slot], (double)val);
+        if ((threadIdx.x & 31) == 0) red_w[slot] += (double)val;
     };
     float gfc0 = 0.0f, gfc1 = 0.0f;
-    for (int v = 0; v < t.V; ++v) {
+    float* slot = a.za + i;                          // (A'_v, z_v, -) of view v -> (dh_v, true z_v, w_v / sum w)
+    for (int v = 0; v < t.V; ++v, slot += 3 * total) {
         float s0 = 0.0f, s1 = 0.0f;
         if (ok) {
-            const float zs = a.za[(size_t)(3 * v + 1) * total + i], aprime = a.za[(size_t)(3 * v) * total + i];
+            const float zs = slot[total], aprime = slot[0];
             float h, dact;
             const float w = weight_of(v, zs, h);
-            const float dh = dh_of(a, aprime, go, wsum, w, h, &dact);
+            const float dh = dh_of(a, aprime, go, rws, w, h, &dact);
             const float z = zs + __ldg(vparams + 4 * v + 3);
             const float zhat = (z - __ldg(t.bnv + 4 * v + 3)) * __ldg(t.bnv + 4 * v + 2);
             s0 = dh; s1 = dh * zhat;
             gfc0 = fmaf(dact, fmaxf(h, 0.0f), gfc0);
             gfc1 += dact;
-            a.za[(size_t)(3 * v) * total + i] = dh;
-            a.za[(size_t)(3 * v + 1) * total + i] = z;
-            a.za[(size_t)(3 * v + 2) * total + i] = w / wsum;
+            slot[0] = dh;
+            slot[total] = z;
+            slot[2 * total] = w * rws;
         }
         warp_add(s0, 2 * v);
         warp_add(s1, 2 * v + 1);
@@ -178,8 +188,12 @@ bwd_finalize_kernel(const BwdArgs a, const float* __restrict__ vparams, const fl
     warp_add(gfc0, 2 * t.V);
     warp_add(gfc1, 2 * t.V + 1);
     __syncthreads();
-    if ((int)threadIdx.x < 2 * t.V) { if (red[threadIdx.x] != 0.0) atomicAdd(bsum + threadIdx.x, red[threadIdx.x]); }
-    else if ((int)threadIdx.x < 2 * t.V + 2) { if (red[threadIdx.x] != 0.0) atomicAdd(a.gparam + 2 + (threadIdx.x - 2 * t.V), red[threadIdx.x]); }
+    if ((int)threadIdx.x < 2 * t.V + 2) {
+        double sum = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) sum += red[w][threadIdx.x];
+        if (sum != 0.0) atomicAdd((int)threadIdx.x < 2 * t.V ? bsum + threadIdx.x : a.gparam + 2 + (threadIdx.x - 2 * t.V), sum);
+    }
 }
 
 // predicated 16-byte read-only load at p + OFF bytes (zero when the predicate is off): keeps ONE address register pair per
