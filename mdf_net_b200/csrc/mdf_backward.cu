@@ -243,9 +243,9 @@ bwd_sweep_kernel(const BwdArgs a)
     const GridNormFast gn = make_grid_norm_fast(t.H, t.W);
     const size_t total = (size_t)t.B * t.D * HW;
     const size_t gstride = (size_t)t.D * HW;
-    __shared__ double dcw_s[GS];
+    __shared__ float dcw_s[8][GS];                    // one row per warp (plain stores; a shared-memory double atomicAdd is a CAS spin loop)
     __shared__ float cw_s[GS];                        // the slice's conv weights: read per use (8 registers the plane loop needs more)
-    if (threadIdx.x < GS) { dcw_s[threadIdx.x] = 0.0; cw_s[threadIdx.x] = __ldg(t.cw + s * GS + threadIdx.x); }
+    if (threadIdx.x < GS) cw_s[threadIdx.x] = __ldg(t.cw + s * GS + threadIdx.x);
     __syncthreads();
     float rt[12];                                     // registers: the reductions below clobber memory, a pointer would be re-read per plane
 #pragma unroll
@@ -349,16 +349,21 @@ bwd_sweep_kernel(const BwdArgs a)
         for (int jj = 0; jj < JS; ++jj)
             red_add_v4(dqp + (size_t)jj * HW, make_float4(dq[4 * jj], dq[4 * jj + 1], dq[4 * jj + 2], dq[4 * jj + 3]));
     }
-    // d conv.weight: warp shuffle -> shared-memory doubles -> one global atomic per block and group
+    // d conv.weight: warp shuffle -> one row per warp in shared memory -> one global (double) atomic per block and group
 #pragma unroll
     for (int k = 0; k < GS; ++k) {
         float c = live ? dcw[k] : 0.0f;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-        if ((threadIdx.x & 31) == 0 && c != 0.0f) atomicAdd(&dcw_s[k], (double)c);
+        if ((threadIdx.x & 31) == 0) dcw_s[threadIdx.x >> 5][k] = c;
     }
     __syncthreads();
-    if (threadIdx.x < GS && dcw_s[threadIdx.x] != 0.0) atomicAdd(a.gparam + 4 + s * GS + threadIdx.x, dcw_s[threadIdx.x]);
+    if (threadIdx.x < GS) {
+        double sum = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sum += (double)dcw_s[w][threadIdx.x];
+        if (sum != 0.0) atomicAdd(a.gparam + 4 + s * GS + threadIdx.x, sum);
+    }
 }
 
 // dS4 / dQ4 -> NCHW feature gradients.  One thread per pixel per view; blockIdx.y = view * B + b.
