@@ -208,7 +208,8 @@ MDF_API int mdf_confidence_fwd(const float *prob, int B, int D, int H, int W,
                        float *confidence, mdf_stream_t stream);
 
 /* ---- next-stage depth hypotheses: HyposByFit (net/unit/depthhypos.py:27-76) -----------------
- * curve: 1 = "gauss1" (:169-215), 2 = "laplace" (:78-125).  mdf_hypos_fit_fwd gives the fitted scale s (B,H,W) of
+ * curve: 1 = "gauss1" (:169-215), 2 = "laplace" (:78-125), 3 = "gauss0" (:127-167; these two entries only -- the fused
+ * tails above take the curves config.py wires, 1 and 2).  mdf_hypos_fit_fwd gives the fitted scale s (B,H,W) of
  * every pixel's probability column; mdf_hypos_generate_fwd upsamples s and depth x2 (bilinear, align_corners
  * = False) when `upsample`, derives the search range from prob_thresh, applies the reference's clamps and writes
  * `ndepths` hypotheses (B,ndepths,2H|H,2W|W).  depth_range: (B,2) device floats (min, max).

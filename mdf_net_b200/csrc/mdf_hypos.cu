@@ -1,7 +1,8 @@
 // mdf_hypos.cu -- next-stage depth hypotheses: HyposByFit of MDF-Net (net/unit/depthhypos.py) for sm_100a.
 //
 // The reference (depthhypos.py:40-76) fits, per pixel, a curve to the probability column the regulariser
-// produced -- "gauss1" after stage 0 (:169-215), "laplace" after stage 1 (:78-125) --, upsamples the fitted
+// produced -- "gauss1" after stage 0 (:169-215), "laplace" after stage 1 (:78-125); "gauss0" (:127-167) is available but
+// not wired by config.py --, upsamples the fitted
 // scale s and the regressed depth x2 (bilinear, align_corners=False), turns s into a search range with
 // prob_thresh, clamps it, and spreads `ndepths` hypotheses over it.  It does so with ~40 ATen launches, a
 // per-pixel batched 3x3 torch.inverse, and Python loops over the depth planes and the batch.
@@ -30,7 +31,7 @@ struct FitArgs {
     int per_pixel, B, D, H, W;
 };
 
-template <int MODE>   // 1 = gauss1, 2 = laplace
+template <int MODE>   // 1 = gauss1, 2 = laplace, 3 = gauss0
 __global__ void __launch_bounds__(128)
 hypos_fit_kernel(const FitArgs a)
 {
@@ -53,6 +54,27 @@ hypos_fit_kernel(const FitArgs a)
             sxx = __fadd_rn(sxx, __fmul_rn(x, x));
         }
         a.s[pix] = __fdiv_rn(1.0f, fabsf(__fdiv_rn(sxy, sxx)));
+        return;
+    }
+    if (MODE == 3) {
+        // gauss0: least squares of ln p on [x, 1] with x = (hypo - depth)^2 in float32 as the reference forms it (:153);
+        // s = |-1 / b0|, b0 = S_xz / S_xx.  The 2x2 normal equations have entries up to 510^4 * 48: like gauss1, the sums are
+        // taken in float64 around the column mean of x (the reference's own float32 result is its noise, not the target).
+        const float dep = __ldg(a.depth + pix);
+        double xm = 0.0;
+        for (int d = 0; d < a.D; ++d) {
+            const float df = __fsub_rn(__ldg(hcol + (size_t)d * hs), dep);
+            xm += (double)__fmul_rn(df, df);
+        }
+        xm /= (double)a.D;
+        double sxx = 0.0, sxz = 0.0;
+        for (int d = 0; d < a.D; ++d) {
+            const float df = __fsub_rn(__ldg(hcol + (size_t)d * hs), dep);
+            const double u = (double)__fmul_rn(df, df) - xm;
+            const double z = log((double)fmaxf(__ldg(pcol + (size_t)d * HW), 1e-40f));
+            sxx += u * u; sxz += u * z;
+        }
+        a.s[pix] = (float)fabs(-sxx / sxz);
         return;
     }
     // gauss1: least squares of ln p on [x^2, x, 1]; s = |-1 / c2|                      (depthhypos.py:189-213)
@@ -138,7 +160,7 @@ int mdf_hypos_fit_fwd(const float* prob, const float* depth_hypos, int hypos_per
                       int B, int D, int H, int W, float* s, mdf_stream_t stream)
 {
     if (B < 0 || D < 0 || H < 0 || W < 0) return MDF_ERR_INVALID_SHAPE;
-    if (curve != 1 && curve != 2) return MDF_ERR_UNSUPPORTED;
+    if (curve != 1 && curve != 2 && curve != 3) return MDF_ERR_UNSUPPORTED;
     const size_t npix = (size_t)B * H * W;
     if (npix == 0) return MDF_OK;
     if (D < 1) return MDF_ERR_INVALID_SHAPE;
@@ -155,6 +177,7 @@ int mdf_hypos_fit_fwd(const float* prob, const float* depth_hypos, int hypos_per
     const size_t blocks = (npix + 127) / 128;
     if (blocks > 0x7fffffffu) return MDF_ERR_UNSUPPORTED;
     if (curve == 1) hypos_fit_kernel<1><<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(a);
+    else if (curve == 3) hypos_fit_kernel<3><<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(a);
     else hypos_fit_kernel<2><<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(a);
     return launch_status();
 }
@@ -163,7 +186,7 @@ int mdf_hypos_generate_fwd(const float* depth, const float* s, const float* dept
                            int upsample, int B, int H, int W, int ndepths, float* depth_hypos, mdf_stream_t stream)
 {
     if (B < 0 || H < 0 || W < 0 || ndepths < 2) return MDF_ERR_INVALID_SHAPE;
-    if (curve != 1 && curve != 2) return MDF_ERR_UNSUPPORTED;
+    if (curve != 1 && curve != 2 && curve != 3) return MDF_ERR_UNSUPPORTED;
     const size_t npix = (size_t)B * H * W * (upsample ? 4 : 1);
     if (npix == 0) return MDF_OK;
     if (!depth || !s || !depth_range || !depth_hypos) return MDF_ERR_NULL_POINTER;
@@ -176,7 +199,8 @@ int mdf_hypos_generate_fwd(const float* depth, const float* s, const float* dept
     GenArgs a;
     a.depth = depth; a.s = s; a.range = depth_range; a.out = depth_hypos;
     a.log_thresh = logf(prob_thresh);
-    a.mode = curve; a.upsample = upsample ? 1 : 0; a.B = B; a.H = H; a.W = W; a.ND = ndepths;
+    a.mode = curve == 2 ? 2 : 1;                    // gauss0 and gauss1 share the range formula (depthhypos.py:53-54)
+    a.upsample = upsample ? 1 : 0; a.B = B; a.H = H; a.W = W; a.ND = ndepths;
     const size_t blocks = (npix + 255) / 256;
     if (blocks > 0x7fffffffu) return MDF_ERR_UNSUPPORTED;
     hypos_generate_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);

@@ -267,7 +267,8 @@ def _(features, ref_proj, src_projs, depth_hypos):
 
 
 # ------------------------------------------------------------------------------------------- head
-_CURVES = {"gauss1": 1, "laplace": 2}      # depthhypos.py:44-47 (config.py:200 wires None, "gauss1", "laplace")
+_CURVES = {"gauss1": 1, "laplace": 2}      # depthhypos.py:44-47 (config.py:200 wires None, "gauss1", "laplace"): the fused tails
+_FIT_CURVES = {**_CURVES, "gauss0": 3}     # the stand-alone fit / generation also cover "gauss0" (depthhypos.py:42-43, 127-167)
 
 def _prob(t: Tensor, what: str) -> Tensor:
     t = _f32c(t, what)
@@ -536,8 +537,8 @@ def _(features, ref_proj, src_projs, depth_hypos, conv_weight, bn_weight, bn_bia
 @torch.library.custom_op("mdfnet_b200::hypos_fit", mutates_args=(), device_types="cuda")
 def hypos_fit(prob_volume: Tensor, depth_hypos: Tensor, depth: Tensor, curve: str) -> Tensor:
     """Fitted scale s (B,H,W) of every pixel's probability column: depthhypos.py:78-125 ('laplace'), :169-215 ('gauss1')."""
-    if curve not in _CURVES:
-        raise RuntimeError(f"mdfnet_b200: curve must be one of {sorted(_CURVES)}, got {curve!r}")
+    if curve not in _FIT_CURVES:
+        raise RuntimeError(f"mdfnet_b200: curve must be one of {sorted(_FIT_CURVES)}, got {curve!r}")
     p = _prob(prob_volume, "prob_volume")
     B, D, H, W = p.shape
     hyp, per_pixel = _head_hypos(depth_hypos, B, D, H, W)
@@ -545,7 +546,7 @@ def hypos_fit(prob_volume: Tensor, depth_hypos: Tensor, depth: Tensor, curve: st
     if d.shape != (B, H, W):
         raise RuntimeError(f"mdfnet_b200: depth must be (B,H,W) = {(B, H, W)}, got {tuple(d.shape)}")
     s = torch.empty((B, H, W), dtype=torch.float32, device=p.device)
-    st = _cabi.lib().mdf_hypos_fit_fwd(p.data_ptr(), hyp.data_ptr(), per_pixel, d.data_ptr(), _CURVES[curve], B, D, H, W,
+    st = _cabi.lib().mdf_hypos_fit_fwd(p.data_ptr(), hyp.data_ptr(), per_pixel, d.data_ptr(), _FIT_CURVES[curve], B, D, H, W,
                                        s.data_ptr(), _stream(p))
     _cabi.check("mdf_hypos_fit_fwd", st)
     _count(_LAUNCHES_SIMPLE)
@@ -562,8 +563,8 @@ def _(prob_volume, depth_hypos, depth, curve):
 def hypos_generate(depth: Tensor, s: Tensor, depth_range: Tensor, curve: str, prob_thresh: float, ndepths: int,
                    upsample: bool) -> Tensor:
     """Hypotheses (B,ndepths,2H|H,2W|W) from the fitted scale: depthhypos.py:48-76."""
-    if curve not in _CURVES:
-        raise RuntimeError(f"mdfnet_b200: curve must be one of {sorted(_CURVES)}, got {curve!r}")
+    if curve not in _FIT_CURVES:
+        raise RuntimeError(f"mdfnet_b200: curve must be one of {sorted(_FIT_CURVES)}, got {curve!r}")
     d, sv = _f32c(depth, "depth"), _f32c(s, "s")
     B, H, W = d.shape
     rng = _f32c(depth_range.float(), "depth_range")
@@ -571,7 +572,7 @@ def hypos_generate(depth: Tensor, s: Tensor, depth_range: Tensor, curve: str, pr
         raise RuntimeError("mdfnet_b200: s must match depth (B,H,W) and depth_range must be (B,2)")
     f = 2 if upsample else 1
     out = torch.empty((B, ndepths, H * f, W * f), dtype=torch.float32, device=d.device)
-    st = _cabi.lib().mdf_hypos_generate_fwd(d.data_ptr(), sv.data_ptr(), rng.data_ptr(), _CURVES[curve], float(prob_thresh),
+    st = _cabi.lib().mdf_hypos_generate_fwd(d.data_ptr(), sv.data_ptr(), rng.data_ptr(), _FIT_CURVES[curve], float(prob_thresh),
                                             int(upsample), B, H, W, int(ndepths), out.data_ptr(), _stream(d))
     _cabi.check("mdf_hypos_generate_fwd", st)
     _count(_LAUNCHES_SIMPLE)

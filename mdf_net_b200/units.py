@@ -172,7 +172,7 @@ class HyposByFit(nn.Module):
 
     depth is None (stage 0): `ndepths` uniform hypotheses over depth_range, (B,ndepths,1,1) -- B*ndepths numbers,
     computed with the same two torch ops as the reference (:31-38).  Otherwise: per-pixel curve fit of the previous
-    stage's probability volume ("gauss1" or "laplace"), x2 upsampling of the fitted scale and of the depth, search
+    stage's probability volume ("gauss1", "laplace" or the unwired "gauss0"), x2 upsampling of the fitted scale and of the depth, search
     range from prob_thresh, the reference's clamps, `ndepths` hypotheses per pixel -- two kernels of libmdf_b200.so
     instead of ~40 ATen launches, a batched 3x3 torch.inverse and Python loops over planes and batch items.
     No gradient flows through the reference's version either (depthhypos.py:40 is under no_grad).
@@ -189,9 +189,8 @@ class HyposByFit(nn.Module):
             interval = (dmax - dmin) / (self.ndepths - 1)
             steps = torch.arange(0, self.ndepths, device=depth_range.device).reshape(1, -1)
             return (dmin + steps * interval).view(B, self.ndepths, 1, 1)
-        if self.curve_calss not in ("gauss1", "laplace"):
-            raise NotImplementedError(f"HyposByFit: curve {self.curve_calss!r} is not wired by the reference's config.py "
-                                      "and not implemented here")
+        if self.curve_calss not in ("gauss0", "gauss1", "laplace"):       # depthhypos.py:42-47 knows no other
+            raise NotImplementedError(f"HyposByFit: unknown curve {self.curve_calss!r}")
         with torch.no_grad():
             s = ops.hypos_fit(prob_volume, depth_hypos, depth, self.curve_calss)
             return ops.hypos_generate(depth, s, depth_range, self.curve_calss, float(self.prob_thresh), self.ndepths,

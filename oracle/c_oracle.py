@@ -239,11 +239,11 @@ def host_threads() -> int:
         return os.cpu_count() or 1
 
 
-_FIT_MODES = {"gauss1": 1, "laplace": 2}
+_FIT_MODES = {"gauss1": 1, "laplace": 2, "gauss0": 3}
 
 
 def hypos_fit(prob_volume, depth_hypos, depth, curve, prec="f32"):
-    """Per-pixel curve fit of HyposByFit (depthhypos.py:78-125 'laplace', :169-215 'gauss1') -> s (B,H,W)."""
+    """Per-pixel curve fit of HyposByFit (depthhypos.py:78-125 'laplace', :127-167 'gauss0', :169-215 'gauss1') -> s (B,H,W)."""
     p = _arr(prob_volume, prec)
     B, D, H, W = p.shape
     h, pp = _hypos(depth_hypos, prec, B, D, H, W)

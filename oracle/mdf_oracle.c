@@ -439,6 +439,7 @@ int SYM(mdf_oracle_confidence)(const REAL *prob, int B, int D, int H, int W,
 /*   fit         : per-pixel curve fit of the probability column               */
 /*                 "gauss1"  depthhypos.py:169-215  s = |-1/b0|, ln p ~ b0 x^2 + b1 x + b2 */
 /*                 "laplace" depthhypos.py:78-125   s = 1/|sum(x y)/sum(x x)|, x = |hypo - depth| */
+/*                 "gauss0"  depthhypos.py:127-167  s = |-1/b0|, ln p ~ b0 x + b1, x = (hypo - depth)^2 */
 /*   generate    : bilinear x2 upsampling of s and depth (F.interpolate, align_corners=False), */
 /*                 search range from s and prob_thresh, clamps, D' hypotheses   depthhypos.py:48-76 */
 /* The gauss1 normal equations (entries up to 935^4 * 48) are hopeless in float32: the reference's */
@@ -447,10 +448,10 @@ int SYM(mdf_oracle_confidence)(const REAL *prob, int B, int D, int H, int W,
 /* under shifts), for both REAL types: it is the yardstick, not a rounding-for-rounding copy. */
 /* ------------------------------------------------------------------------- */
 int SYM(mdf_oracle_hypos_fit)(const REAL *prob, const REAL *hypos, int per_pixel, const REAL *depth,
-                              int mode /* 1 = gauss1, 2 = laplace */, int B, int D, int H, int W, REAL *s_out)
+                              int mode /* 1 = gauss1, 2 = laplace, 3 = gauss0 */, int B, int D, int H, int W, REAL *s_out)
 {
     const size_t HW = (size_t)H * W;
-    if (mode != 1 && mode != 2) return MDF_EINVAL;
+    if (mode != 1 && mode != 2 && mode != 3) return MDF_EINVAL;
     for (int b = 0; b < B; ++b)
 #pragma omp parallel for schedule(static)
         for (size_t p = 0; p < HW; ++p) {
@@ -466,6 +467,28 @@ int SYM(mdf_oracle_hypos_fit)(const REAL *prob, const REAL *hypos, int per_pixel
                 }
                 REAL bb = (REAL)fabs((double)(sxy / sxx));
                 s_out[(size_t)b * HW + p] = 1 / bb;
+            } else if (mode == 3) {
+                /* regression of z = ln p on [x, 1] with x = (hypo - depth)^2 formed in REAL as the reference does
+                 * (depthhypos.py:153); the 2x2 normal equations (entries up to 510^4 * 48) are solved in long double
+                 * after centring x: the slope is b0 = S_xz / S_xx */
+                long double xm = 0, zm = 0;
+                for (int d = 0; d < D; ++d) {
+                    REAL h = per_pixel ? hypos[((size_t)b * D + d) * HW + p] : hypos[(size_t)b * D + d];
+                    REAL df = h - depth[(size_t)b * HW + p];
+                    xm += (long double)(REAL)(df * df);
+                }
+                xm /= D;
+                long double sxx = 0, sxz = 0;
+                for (int d = 0; d < D; ++d) {
+                    REAL pr = prob[((size_t)b * D + d) * HW + p];
+                    if (pr < (REAL)1e-40) pr = (REAL)1e-40;
+                    REAL h = per_pixel ? hypos[((size_t)b * D + d) * HW + p] : hypos[(size_t)b * D + d];
+                    REAL df = h - depth[(size_t)b * HW + p];
+                    long double u = (long double)(REAL)(df * df) - xm;
+                    sxx += u * u; sxz += u * logl((long double)pr);
+                }
+                (void)zm;
+                s_out[(size_t)b * HW + p] = (REAL)fabsl(-1.0L / (sxz / sxx));
             } else {
                 long double mean = 0;
                 for (int d = 0; d < D; ++d) mean += per_pixel ? hypos[((size_t)b * D + d) * HW + p] : hypos[(size_t)b * D + d];
@@ -506,7 +529,7 @@ static inline REAL up2(const REAL *m, int H, int W, int Y, int X)
 int SYM(mdf_oracle_hypos_generate)(const REAL *depth, const REAL *s, const REAL *depth_range, int mode, REAL prob_thresh,
                                    int upsample, int B, int H, int W, int ND, REAL *out)
 {
-    if (mode != 1 && mode != 2) return MDF_EINVAL;
+    if (mode != 1 && mode != 2 && mode != 3) return MDF_EINVAL;
     const int Ho = upsample ? 2 * H : H, Wo = upsample ? 2 * W : W;
     REAL gmax = depth_range[1], gmin = depth_range[0];
     for (int b = 1; b < B; ++b) {
@@ -523,7 +546,7 @@ int SYM(mdf_oracle_hypos_generate)(const REAL *depth, const REAL *s, const REAL 
             for (int X = 0; X < Wo; ++X) {
                 REAL sv = upsample ? up2(s + (size_t)b * H * W, H, W, Y, X) : s[((size_t)b * H + Y) * W + X];
                 REAL dv = upsample ? up2(depth + (size_t)b * H * W, H, W, Y, X) : depth[((size_t)b * H + Y) * W + X];
-                REAL res = mode == 1 ? R_SQRT(-1 * sv * lt) : (REAL)fabs((double)(sv * lt));
+                REAL res = mode != 2 ? R_SQRT(-1 * sv * lt) : (REAL)fabs((double)(sv * lt));    /* gauss0 | gauss1 : laplace */
                 if (res < (REAL)1e-6) res = (REAL)1e-6;          /* clamp(min, max): NaN propagates like torch */
                 if (res > cap_all) res = cap_all;
                 if (res > cap_b) res = cap_b;

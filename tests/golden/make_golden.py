@@ -216,6 +216,34 @@ def gen_hypos():
     save("hypos_fit", **out)
 
 
+def gen_hypos_gauss0():
+    """The curve config.py does not wire: HyposByFit(curve 'gauss0') (depthhypos.py:42-43, 127-167) on uniform (stage 0 -> 1)
+    and on per-pixel hypotheses, float32 and float64 runs of the reference (its 2x2 normal equations are as ill conditioned
+    in float32 as gauss1's)."""
+    from net.unit.depthhypos import HyposByFit
+    B, H, W = 2, 12, 16
+    dr = np.array([[425.0, 935.0], [480.0, 900.0]], np.float32)
+    out = {"depth_range": dr}
+    hyp0 = HyposByFit(48, None, 0.0)(None, T(dr), None, None, upsample=True)
+    prob0 = F.softmax(T(syn.regulariser_logits(B, 48, H, W, seed=83, peak=6.0)), 1)
+    depth0 = regress.depth_regression(prob0, hyp0)
+    m = HyposByFit(24, "gauss0", 0.95)
+    out.update(hypos0=hyp0.numpy(), prob0=prob0.numpy(), depth0=depth0.numpy(),
+               s=m._gauss_fitting0(depth0, prob0, hyp0).numpy(),
+               s_f64=m._gauss_fitting0(depth0.double(), prob0.double(), hyp0.double()).numpy(),
+               hypos1=m(depth0, T(dr), prob0, hyp0, upsample=True).numpy(),
+               hypos1_f64=m(depth0.double(), T(dr).double(), prob0.double(), hyp0.double(), upsample=True).numpy())
+    hyp_p = T(syn.pixel_hypos(B, 24, H, W, seed=84))
+    prob_p = F.softmax(T(syn.regulariser_logits(B, 24, H, W, seed=85, peak=6.0)), 1)
+    depth_p = regress.depth_regression(prob_p, hyp_p)
+    m8 = HyposByFit(8, "gauss0", 0.9)
+    out.update(hypos_p=hyp_p.numpy(), prob_p=prob_p.numpy(), depth_p=depth_p.numpy(),
+               s_p=m8._gauss_fitting0(depth_p, prob_p, hyp_p).numpy(),
+               s_p_f64=m8._gauss_fitting0(depth_p.double(), prob_p.double(), hyp_p.double()).numpy(),
+               hypos2_f64=m8(depth_p.double(), T(dr).double(), prob_p.double(), hyp_p.double(), upsample=False).numpy())
+    save("hypos_fit_gauss0", **out)
+
+
 # ------------------------------------------------------ regulariser tail: prob conv + softmax + head + fit
 def gen_prob_head():
     """The last layer of the reference's regularisers (net/unit/regular.py:43,67-69 and :110,130-133) with what follows
@@ -439,6 +467,6 @@ def gen_output_files():
 
 if __name__ == "__main__":
     only = sys.argv[1:]
-    for fn in (gen_output_files, gen_warp, gen_vecagg, gen_vecagg_grad, gen_varagg, gen_head, gen_hypos, gen_prob_head, gen_geo_filter, gen_scale, gen_corenet):
+    for fn in (gen_output_files, gen_warp, gen_vecagg, gen_vecagg_grad, gen_varagg, gen_head, gen_hypos, gen_hypos_gauss0, gen_prob_head, gen_geo_filter, gen_scale, gen_corenet):
         if not only or fn.__name__ in only:
             fn()

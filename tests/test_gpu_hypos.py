@@ -33,7 +33,28 @@ def test_hypos_by_fit_golden():
     h2n = m2(cu(z["depth1"]), dr, cu(z["prob1"]), cu(z["hypos1"]), upsample=False)     # the upsample=False branch
     assert h2n.shape == (2, 8, 24, 32)
     with pytest.raises(NotImplementedError):
-        mdf.HyposByFit(8, "gauss0", 0.9)(cu(z["depth1"]), dr, cu(z["prob1"]), cu(z["hypos1"]))
+        mdf.HyposByFit(8, "cauchy", 0.9)(cu(z["depth1"]), dr, cu(z["prob1"]), cu(z["hypos1"]))
+
+
+def test_hypos_by_fit_gauss0_golden():
+    """'gauss0' (depthhypos.py:127-167; config.py does not wire it): the stand-alone fit and generation kernels against the
+    reference's float64 and float32 runs, uniform and per-pixel hypotheses, with and without the x2 upsampling."""
+    import mdf_net_b200 as mdf
+    from mdf_net_b200 import ops
+    z = load_golden("hypos_fit_gauss0")
+    dr = cu(z["depth_range"])
+    s = ops.hypos_fit(cu(z["prob0"]), cu(z["hypos0"]), cu(z["depth0"]), "gauss0").cpu().numpy()
+    assert (np.abs(s - z["s_f64"]) / np.abs(z["s_f64"])).max() < 2e-6
+    assert (np.abs(s - z["s"]) / np.abs(z["s"])).max() < 5e-6
+    h1 = mdf.HyposByFit(24, "gauss0", 0.95)(cu(z["depth0"]), dr, cu(z["prob0"]), cu(z["hypos0"]), upsample=True).cpu().numpy()
+    assert h1.shape == z["hypos1"].shape and np.abs(h1 - z["hypos1_f64"]).max() < 1e-3
+    sp = ops.hypos_fit(cu(z["prob_p"]), cu(z["hypos_p"]), cu(z["depth_p"]), "gauss0").cpu().numpy()
+    assert (np.abs(sp - z["s_p_f64"]) / np.abs(z["s_p_f64"])).max() < 5e-6
+    h2 = mdf.HyposByFit(8, "gauss0", 0.9)(cu(z["depth_p"]), dr, cu(z["prob_p"]), cu(z["hypos_p"]), upsample=False).cpu().numpy()
+    assert np.abs(h2 - z["hypos2_f64"]).max() < 1e-3
+    # the fused tails only take the curves config.py wires
+    with pytest.raises(RuntimeError):
+        ops.softmax_regress_fit(cu(z["prob0"]).log(), cu(z["hypos0"]), "gauss0")
 
 
 @pytest.mark.parametrize("stage", [0, 1])

@@ -185,6 +185,21 @@ def test_hypos_by_fit():
     assert h2.shape == z["hypos2"].shape == (2, 8, 48, 64)
 
 
+def test_hypos_by_fit_gauss0():
+    """The curve config.py does not wire (depthhypos.py:127-167), on uniform and on per-pixel hypotheses: the oracle against the
+    reference's float64 run (and its float32 run, which is well behaved for this curve), then the hypotheses."""
+    z = load_golden("hypos_fit_gauss0")
+    s = co.hypos_fit(z["prob0"], z["hypos0"], z["depth0"], "gauss0")
+    assert (np.abs(s - z["s_f64"]) / np.abs(z["s_f64"])).max() < 2e-6
+    assert (np.abs(s - z["s"]) / np.abs(z["s"])).max() < 5e-6
+    h1 = co.hypos_generate(z["depth0"], s, z["depth_range"], "gauss0", 0.95, 24)
+    assert h1.shape == z["hypos1"].shape and np.abs(h1 - z["hypos1_f64"]).max() < 5e-4
+    sp = co.hypos_fit(z["prob_p"], z["hypos_p"], z["depth_p"], "gauss0")
+    assert (np.abs(sp - z["s_p_f64"]) / np.abs(z["s_p_f64"])).max() < 5e-6
+    h2 = co.hypos_generate(z["depth_p"], sp, z["depth_range"], "gauss0", 0.9, 8, upsample=False)
+    assert np.abs(h2 - z["hypos2_f64"]).max() < 5e-4
+
+
 @pytest.mark.parametrize("name", ["prob_head_s0", "prob_head_s1", "prob_head_s2"])
 def test_prob_conv_and_tail(name):
     """Last layer of the reference's regularisers (input / output of `.prob` captured by hooks) and what CoreNet does
